@@ -1,0 +1,156 @@
+/* qtcnn.h — C ABI of the B200-native QuadtreeCNN hot path (libqtcnn.so).
+ *
+ * The reference (Avirup221/Multimodal-Hierarchical-CNN-for-Sun-Salutation-Pose-Classification) has no
+ * FFI of its own: its only boundary is the nn.Module surface of `models.py`. Each entry point below
+ * replaces the ATen/cuDNN primitive that one reference call site reaches; the citation names that call
+ * site (paths relative to the reference root, "QS" = "Quadtree_from scratch").
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library
+ *     never allocates, frees or retains device memory; scratch is passed in as `ws` / `ws_bytes`
+ *   - activations are channels-last bf16 (NHWC / NDHWC), statistics, biases and weight gradients fp32
+ *   - `stream` is a cudaStream_t; launches are asynchronous, never synchronise, and are graph-capturable
+ *   - return 0 on success, <0 invalid argument / unsupported shape (text via qt_last_error()),
+ *     >0 a cudaError_t. There is no CPU, cuDNN or Triton fallback: unsupported shapes fail.
+ */
+#ifndef QTCNN_H_
+#define QTCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* qt_stream_t; /* cudaStream_t */
+
+/* Convolution geometry (2-D convs use *_d = 1). Strides are in ELEMENTS of the (n, d, h, w) axes of a
+ * channels-last view, so the four quadrant views of the level-1 split (QS/models.py:277-282) are plain
+ * descriptors: groups = 4 with per-group element offsets. */
+typedef struct qt_conv_desc {
+  int n;
+  int in_d, in_h, in_w, in_c;
+  int out_c;
+  int k_d, k_h, k_w;
+  int stride_d, stride_h, stride_w;
+  int pad_d, pad_h, pad_w;
+  int groups;
+  long long x_stride[4];
+  long long y_stride[4];
+  long long x_group_off[4];
+  long long y_group_off[4];
+} qt_conv_desc;
+
+/* epilogue flags of qt_conv_fprop / qt_linear_fprop */
+#define QT_EPI_BIAS 1
+#define QT_EPI_RELU 2
+#define QT_EPI_STATS 4
+#define QT_EPI_OUT_F32 16
+
+int qt_version(void);
+const char* qt_last_error(void);
+/* 1 if any bounded barrier wait inside a kernel timed out since the last call (debug aid); resets it. */
+int qt_take_timeout_flag(void);
+
+/* ---- layout / packing ------------------------------------------------------------------------- */
+/* images.to(device) feeding base_cnn.conv1 (QS/Quadtree_train.py:61, QS/models.py:222):
+ * NCHW fp32 [n,3,h,w] -> zero-padded NHWC4 bf16 [n,h+7,w+8,4]. */
+int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream);
+int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream);
+int qt_nhwc_bf16_to_nchw_f32(const void* x, float* out, int n, int c, long long hw, int c_pad, qt_stream_t stream);
+/* fp32 parameter [cout][cin][taps] -> bf16 GEMM operands (forward [cout][taps][cin], dgrad [cin][taps][cout]). */
+int qt_wpack_fprop(const float* w, void* wf, int cout, int cin, int taps, qt_stream_t stream);
+int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_stream_t stream);
+int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream);
+int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
+
+/* ---- tensor-core implicit GEMM ------------------------------------------------------------------ */
+/* nn.Conv2d / nn.Conv3d forward (torchvision resnet BasicBlock convs reached from QS/models.py:222-243,
+ * quadrant_processor.0 QS/models.py:234-238 & 284-287, 3dcnn/models.py:107-139).
+ * y = conv(x, wf) [+ bias] [ReLU]; with QT_EPI_STATS also writes per-tile column sum / sum-of-squares
+ * partials [qt_conv_stat_rows][2][out_c] for the train-mode BatchNorm that follows. */
+int qt_conv_stat_rows(const qt_conv_desc* d);
+size_t qt_conv_fprop_workspace_bytes(const qt_conv_desc* d);
+int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y, const float* bias, float* stats,
+                  int flags, void* ws, size_t ws_bytes, qt_stream_t stream);
+/* convolution_backward, data gradient: dx = conv_transpose(dy, w) [+ dx when accumulate]. */
+int qt_conv_dgrad(const qt_conv_desc* d, const void* dy, const void* wd, void* dx, int accumulate,
+                  qt_stream_t stream);
+/* convolution_backward, weight gradient: dw[cout][cin][taps] fp32 (+= when accumulate). */
+size_t qt_conv_wgrad_workspace_bytes(const qt_conv_desc* d);
+int qt_conv_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
+                  size_t ws_bytes, qt_stream_t stream);
+/* base_cnn.conv1 (7x7, stride 2, pad 3, 3 channels; torchvision resnet.py:197) on the packed input. */
+int qt_stem_stat_rows(int n, int h, int w);
+int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, int h, int w, int cout,
+                  qt_stream_t stream);
+size_t qt_stem_wgrad_workspace_bytes(int n, int h, int w, int cout);
+int qt_stem_wgrad(const void* xp, const void* dy, float* dw, int accumulate, int n, int h, int w, int cout, int cin,
+                  void* ws, size_t ws_bytes, qt_stream_t stream);
+/* nn.Linear on the tensor cores (classifier.0, QS/models.py:266-271): x bf16 [b][k] (row stride ldx),
+ * w bf16 [n][k]; out bf16 or fp32 [b][n]. */
+size_t qt_linear_workspace_bytes(int b, int n, int k);
+int qt_linear_fprop(const void* x, long long ldx, const void* w, const float* bias, void* out, long long ldo,
+                    int flags, int b, int n, int k, void* ws, size_t ws_bytes, qt_stream_t stream);
+int qt_linear_dgrad(const void* dy, long long ldy, const void* wt, void* dx, long long ldx, int b, int n, int k,
+                    void* ws, size_t ws_bytes, qt_stream_t stream);
+int qt_linear_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, int accumulate, int b,
+                    int n, int k, void* ws, size_t ws_bytes, qt_stream_t stream);
+
+/* ---- BatchNorm (train-mode batch statistics; torchvision resnet.py bn1/bn2, 3dcnn/models.py:109) ---- */
+size_t qt_bn_workspace_bytes(int c);
+int qt_bn_stats(const void* y, long long m, int c, float* partial, int partial_rows, qt_stream_t stream);
+int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                   qt_stream_t stream);
+int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, float* scale, float* shift, qt_stream_t stream);
+int qt_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* out, long long m,
+                int c, int relu, qt_stream_t stream);
+/* native_batch_norm_backward fused with the ReLU mask: dz = dout*(act>0) when act != NULL;
+ * dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optionally stores dz (identity-branch gradient). */
+int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
+                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, void* dy,
+                   void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream);
+int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream);
+int qt_colsum(const void* x, long long m, int c, float* out, int accumulate, void* ws, size_t ws_bytes,
+              qt_stream_t stream);
+int qt_add_bf16(const void* a, const void* b, void* out, long long n, qt_stream_t stream);
+
+/* ---- pooling ----------------------------------------------------------------------------------- */
+/* base_cnn.maxpool (MaxPool2d(3,2,1), torchvision resnet.py:200) and its backward. */
+int qt_maxpool2d_fwd(const void* x, void* out, void* argmax, int n, int h, int w, int c, int ksize, int stride,
+                     int pad, qt_stream_t stream);
+int qt_maxpool2d_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c, int ksize,
+                     int stride, int pad, qt_stream_t stream);
+/* Quadtree stage (QS/models.py:277-294): MaxPool2d(2,2)+flatten of the four quadrant maps and the global
+ * average pool of layer4, written at their offsets of the fused feature row [global | TL | TR | BL | BR | ...]. */
+int qt_quadtree_pool_fwd(const void* q, const void* l4, void* feat, int b, int qh, int qw, int cq, int ghw, int cg,
+                         int ldf, qt_stream_t stream);
+int qt_quadtree_pool_bwd(const void* dfeat, const void* q, void* dq, void* dl4, int b, int qh, int qw, int cq,
+                         int ghw, int cg, int ldf, qt_stream_t stream);
+/* ReLU + AdaptiveAvgPool2d((1,1)) of the level-1 / level-2 region convs (QS/models.py:21-30, 64-79). */
+int qt_region_avgpool_fwd(const void* x, void* out, long long regions, int p, int c, long long ldo,
+                          qt_stream_t stream);
+int qt_region_avgpool_bwd(const void* dout, const void* x, void* dx, long long regions, int p, int c, long long ldo,
+                          int relu_mask, qt_stream_t stream);
+
+/* ---- small fp32 linears of the fusion head (numerical_mlp, classifier.3; QS/models.py:255-271) ------ */
+int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float* w, const float* bias, int b, int n,
+                        int k, int relu, float drop_p, unsigned long long seed, float* out, long long ldo,
+                        void* out16, long long ldo16, qt_stream_t stream);
+int qt_small_linear_bwd_dx(const void* dy, int dy_is_bf16, long long ldy, const float* w, int b, int n, int k,
+                           const float* act, long long lda, float drop_p, unsigned long long seed, float* dx,
+                           long long ldx, void* dx16, long long ldx16, qt_stream_t stream);
+int qt_small_linear_bwd_dw(const void* dy, int dy_is_bf16, long long ldy, const void* x, int x_is_bf16,
+                           long long ldx, int b, int n, int k, float* dw, float* db, int accumulate,
+                           qt_stream_t stream);
+int qt_relu_dropout(float* h, void* h16, long long n, float drop_p, unsigned long long seed, int relu,
+                    qt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTCNN_H_ */

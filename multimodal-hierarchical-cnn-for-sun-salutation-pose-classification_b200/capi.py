@@ -1,0 +1,175 @@
+"""ctypes binding of libqtcnn.so (the C ABI declared in include/qtcnn.h).
+
+PyTorch is only the allocator / stream provider here: every call passes raw device pointers
+(`tensor.data_ptr()`) and the current CUDA stream. There is no fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqtcnn.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "qtcnn.h")
+
+QT_EPI_BIAS = 1
+QT_EPI_RELU = 2
+QT_EPI_STATS = 4
+QT_EPI_OUT_F32 = 16
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of `qt_conv_desc`."""
+
+    _fields_ = [
+        ("n", c_int),
+        ("in_d", c_int), ("in_h", c_int), ("in_w", c_int), ("in_c", c_int),
+        ("out_c", c_int),
+        ("k_d", c_int), ("k_h", c_int), ("k_w", c_int),
+        ("stride_d", c_int), ("stride_h", c_int), ("stride_w", c_int),
+        ("pad_d", c_int), ("pad_h", c_int), ("pad_w", c_int),
+        ("groups", c_int),
+        ("x_stride", c_longlong * 4),
+        ("y_stride", c_longlong * 4),
+        ("x_group_off", c_longlong * 4),
+        ("y_group_off", c_longlong * 4),
+    ]
+
+
+def conv_desc(n, in_dhw, in_c, out_c, k_dhw, stride_dhw, pad_dhw, x_stride=None, y_stride=None,
+              groups=1, x_group_off=(0, 0, 0, 0), y_group_off=(0, 0, 0, 0)) -> ConvDesc:
+    """Dense channels-last descriptor unless explicit strides are given."""
+    d = ConvDesc()
+    d.n = n
+    d.in_d, d.in_h, d.in_w = in_dhw
+    d.in_c, d.out_c = in_c, out_c
+    d.k_d, d.k_h, d.k_w = k_dhw
+    d.stride_d, d.stride_h, d.stride_w = stride_dhw
+    d.pad_d, d.pad_h, d.pad_w = pad_dhw
+    d.groups = groups
+    od, oh, ow = (out_size(i, k, s, p) for i, k, s, p in zip(in_dhw, k_dhw, stride_dhw, pad_dhw))
+    if x_stride is None:
+        x_stride = (in_dhw[0] * in_dhw[1] * in_dhw[2] * in_c, in_dhw[1] * in_dhw[2] * in_c, in_dhw[2] * in_c, in_c)
+    if y_stride is None:
+        y_stride = (od * oh * ow * out_c, oh * ow * out_c, ow * out_c, out_c)
+    for i in range(4):
+        d.x_stride[i] = x_stride[i]
+        d.y_stride[i] = y_stride[i]
+        d.x_group_off[i] = x_group_off[i]
+        d.y_group_off[i] = y_group_off[i]
+    return d
+
+
+def out_size(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+_SIGNATURES = {
+    "qt_version": (c_int, []),
+    "qt_last_error": (c_char_p, []),
+    "qt_take_timeout_flag": (c_int, []),
+    "qt_stem_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "qt_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "qt_wpack_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_wpack_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_wpack_stem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "qt_conv_stat_rows": (c_int, [ctypes.POINTER(ConvDesc)]),
+    "qt_conv_fprop_workspace_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
+    "qt_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_size_t, c_void_p]),
+    "qt_conv_dgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "qt_conv_wgrad_workspace_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
+    "qt_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                              c_void_p]),
+    "qt_stem_stat_rows": (c_int, [c_int, c_int, c_int]),
+    "qt_stem_fprop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_stem_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "qt_stem_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_size_t, c_void_p]),
+    "qt_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "qt_linear_fprop": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                c_int, c_void_p, c_size_t, c_void_p]),
+    "qt_linear_dgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p,
+                                c_size_t, c_void_p]),
+    "qt_linear_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int,
+                                c_void_p, c_size_t, c_void_p]),
+    "qt_bn_workspace_bytes": (c_size_t, [c_int]),
+    "qt_bn_stats": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_int, c_void_p]),
+    "qt_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qt_bn_eval_coeffs": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                  c_void_p]),
+    "qt_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "qt_bn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qt_relu_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "qt_colsum": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "qt_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "qt_maxpool2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "qt_maxpool2d_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "qt_quadtree_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
+    "qt_quadtree_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_void_p]),
+    "qt_region_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_void_p]),
+    "qt_region_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_int,
+                                      c_void_p]),
+    "qt_small_linear_fwd": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_float, c_ulonglong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
+    "qt_small_linear_bwd_dx": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p,
+                                       c_longlong, c_float, c_ulonglong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                       c_void_p]),
+    "qt_small_linear_bwd_dw": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_int, c_void_p]),
+    "qt_relu_dropout": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_ulonglong, c_int, c_void_p]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function name `include/qtcnn.h` declares (parsed from the header)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(qt_[a-z0-9_]+)\s*\(", text)) - {"qt_stream_t"})
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libqtcnn.so once; fail loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` — the CUDA "
+                "extension is the only implementation of this package (no CPU / cuDNN fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().qt_last_error().decode(errors="replace")
+        raise RuntimeError(f"libqtcnn {what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

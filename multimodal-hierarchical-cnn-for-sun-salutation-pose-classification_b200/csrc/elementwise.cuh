@@ -1,0 +1,703 @@
+// Bandwidth-bound kernels of the QuadtreeCNN hot path (NHWC / NDHWC bf16 activations, fp32 statistics):
+// layout transforms, train-mode BatchNorm (finalize / apply+ReLU+residual / backward), max pools,
+// the quadtree pooling stage (quadrant 2x2 max-pool + flatten + global average pool written straight
+// into the fused feature buffer), weight packing and the small fp32 linear layers of the fusion head.
+// All of them use 128-bit accesses along the contiguous channel dimension.
+#pragma once
+#include "ptx.cuh"
+
+namespace qt {
+
+struct bf16x8 {
+  uint4 q;
+};
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(h);
+    f[2 * e + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]);
+  q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]);
+  q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// Counter-based Bernoulli keep-mask for dropout: identical in forward and backward, nothing stored.
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  const uint32_t h = hash_u32(idx ^ hash_u32(static_cast<uint32_t>(seed) + 0x9e3779b9U * static_cast<uint32_t>(seed >> 32)));
+  const float u = (h >> 8) * (1.0f / 16777216.0f);
+  return (u >= p) ? 1.f / (1.f - p) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem input packing: NCHW fp32 [N,3,H,W] -> zero-padded NHWC4 bf16 [N, H+7, W+8, 4]
+// (3 rows/cols of padding before the image so that every 7x7/s2 window starts 16-byte aligned).
+// ---------------------------------------------------------------------------------------------
+__global__ void stem_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
+                                       int H, int W) {
+  const int Hp = H + 7, Wp = W + 8;
+  const long long total = static_cast<long long>(N) * Hp * Wp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wp = i % Wp;
+    const int hp = (i / Wp) % Hp;
+    const int n = i / (static_cast<long long>(Wp) * Hp);
+    const int h = hp - 3, w = wp - 3;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      for (int c = 0; c < C && c < 4; ++c) v[c] = x[((static_cast<long long>(n) * C + c) * H + h) * W + w];
+    }
+    uint2 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(out + i * 4) = q;
+  }
+}
+
+// NCHW fp32 -> NHWC bf16 with channel padding to Cp (generic; used by the 3-D stack and tests).
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N,
+                                             int C, long long HW, int Cp) {
+  const long long total = static_cast<long long>(N) * HW * Cp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = i % Cp;
+    const long long p = (i / Cp) % HW;
+    const long long n = i / (static_cast<long long>(Cp) * HW);
+    out[i] = __float2bfloat16_rn(c < C ? x[(n * C + c) * HW + p] : 0.f);
+  }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N,
+                                             int C, long long HW, int Cp) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i % HW;
+    const int c = (i / HW) % C;
+    const long long n = i / (static_cast<long long>(C) * HW);
+    out[i] = __bfloat162float(x[(n * HW + p) * Cp + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing. w: fp32 [Cout][Cin][T] (PyTorch layout, T = taps).
+//   fprop layout wf[Cout][T][Cin]  (K-major B operand of the forward GEMM)
+//   dgrad layout wd[Cin][T][Cout]  (K-major B operand of the data-gradient GEMM)
+// ---------------------------------------------------------------------------------------------
+__global__ void wpack_fprop_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin,
+                                   int T) {
+  const long long total = static_cast<long long>(Cout) * T * Cin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = i % Cin;
+    const int t = (i / Cin) % T;
+    const long long co = i / (static_cast<long long>(Cin) * T);
+    wf[i] = __float2bfloat16_rn(w[(co * Cin + ci) * T + t]);
+  }
+}
+// Tiled transpose: block (32, 8), grid (ceil(Cin/32), ceil(Cout/32), T).
+__global__ void wpack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Cout, int Cin,
+                                   int T) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int co = co0 + j, ci = ci0 + threadIdx.x;
+    tile[j][threadIdx.x] = (co < Cout && ci < Cin) ? w[(static_cast<long long>(co) * Cin + ci) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int ci = ci0 + j, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout)
+      wd[(static_cast<long long>(ci) * T + t) * Cout + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+// Stem 7x7x3 filter -> [Cout][8 row-taps][32 = (s, c4)] with zero padding (s == 7, c == 3, r == 7).
+__global__ void wpack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin,
+                                  int R, int S) {
+  const int total = Cout * 8 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 3, s = (i >> 2) & 7, r = (i >> 5) & 7, co = i >> 8;
+    float v = 0.f;
+    if (c < Cin && s < S && r < R) v = w[((co * Cin + c) * R + r) * S + s];
+    wf[i] = __float2bfloat16_rn(v);
+  }
+}
+// Inverse map for the stem weight gradient: g8[Cout][Cin=32 -> (s,c4)][8 taps r] (layout produced by
+// splitk_reduce_wgrad_kernel with cin=32, ntaps=8) -> grad[Cout][3][7][7].
+__global__ void stem_wgrad_unpack_kernel(const float* __restrict__ g8, float* __restrict__ grad, int Cout, int Cin,
+                                         int R, int S, int accumulate) {
+  const int total = Cout * Cin * R * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % S, r = (i / S) % R, c = (i / (S * R)) % Cin, co = i / (S * R * Cin);
+    const float v = g8[(co * 32 + (s * 4 + c)) * 8 + r];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column reductions over tiles of partial sums: in[T][K] (K = 2*C, or C) -> out[K] (double
+// accumulation, fixed order => deterministic). Stage 1 reduces T -> S slices, stage 2 finishes.
+// ---------------------------------------------------------------------------------------------
+__global__ void colreduce_stage1_kernel(const float* __restrict__ in, int T, int K, int S, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (k >= K) return;
+  const int per = (T + S - 1) / S;
+  const int t0 = s * per, t1 = min(T, t0 + per);
+  double acc = 0.0;
+  for (int t = t0; t < t1; ++t) acc += static_cast<double>(in[static_cast<long long>(t) * K + k]);
+  out[static_cast<long long>(s) * K + k] = acc;
+}
+
+// BatchNorm finalize (train mode): sums[S][2][C] (double) over `count` rows per channel.
+//   mean, biased var -> invstd ; scale = gamma*invstd ; shift = beta - mean*scale
+//   running_mean/var updated with momentum (unbiased var), as torch.nn.BatchNorm*d does.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = 0; s < S; ++s) {
+    s1 += sums[(static_cast<long long>(s) * 2 + 0) * C + c];
+    s2 += sums[(static_cast<long long>(s) * 2 + 1) * C + c];
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  scale_out[c] = g * invstd;
+  shift_out[c] = b - static_cast<float>(mean) * g * invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+// Eval mode: scale/shift from running statistics.
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(running_var[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale_out[c] = g * invstd;
+  shift_out[c] = b - running_mean[c] * g * invstd;
+}
+
+// Per-channel sum / sum of squares of a dense bf16 [M][C] tensor -> partial[blocks][2][C] (used when the
+// statistics are not produced by a GEMM epilogue). Block = 256 threads: (C/8) channel groups x row lanes.
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [lanes][2][C]
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float s1[8] = {0}, s2[8] = {0};
+  if (rl < lanes) {
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
+      float f[8];
+      unpack8(ld_nc16(y + r * C + cg * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1[e] += f[e]; s2[e] += f[e] * f[e]; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[(rl * 2 + 0) * C + cg * 8 + e] = s1[e];
+      sm[(rl * 2 + 1) * C + cg * 8 + e] = s2[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * 2 * C + i];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C + i] = acc;
+  }
+}
+
+// out = act(y*scale[c] + shift[c] (+ residual)); dense [M][C] bf16, C % 8 == 0.
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
+                                __nv_bfloat16* __restrict__ out, long long total8, int C, int relu) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    float f[8], r[8];
+    unpack8(ld_nc16(y + i * 8), f);
+    if (residual) unpack8(ld_nc16(residual + i * 8), r);
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(scale + c0));
+    const float4 sb = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    const float4 ha = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    const float4 hb = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = fmaf(f[e], sc[e], sh[e]);
+      if (residual) v += r[e];
+      if (relu) v = fmaxf(v, 0.f);
+      f[e] = v;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+// BatchNorm backward, pass 1: dz = dout * (act > 0) (mask only when act != nullptr);
+// partial[blocks][2][C] = { sum dz, sum dz * xhat }, xhat = (y - mean) * invstd.
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, long long M, int C,
+                                     float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float s1[8] = {0}, s2[8] = {0};
+  if (rl < lanes) {
+    float mu[8], is[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
+      float d[8], a[8], v[8];
+      unpack8(ld_nc16(dout + r * C + cg * 8), d);
+      unpack8(ld_nc16(y + r * C + cg * 8), v);
+      if (act) unpack8(ld_nc16(act + r * C + cg * 8), a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+        s1[e] += dz;
+        s2[e] += dz * (v[e] - mu[e]) * is[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[(rl * 2 + 0) * C + cg * 8 + e] = s1[e];
+      sm[(rl * 2 + 1) * C + cg * 8 + e] = s2[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * 2 * C + i];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C + i] = acc;
+  }
+}
+// Finish the reduction: sums[S][2][C] -> dgamma, dbeta (fp32, optional accumulate) and the two
+// per-channel coefficients used by pass 2: c1 = sum_dz / M, c2 = sum_dz_xhat / M.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int S, int C, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                       float* __restrict__ c1, float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = 0; s < S; ++s) {
+    s1 += sums[(static_cast<long long>(s) * 2 + 0) * C + c];
+    s2 += sums[(static_cast<long long>(s) * 2 + 1) * C + c];
+  }
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s1) : static_cast<float>(s1);
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(s2) : static_cast<float>(s2);
+  c1[c] = static_cast<float>(s1 / count);
+  c2[c] = static_cast<float>(s2 / count);
+}
+// Pass 2: dy = gamma*invstd * (dz - c1 - xhat*c2); optionally also writes dz (gradient of the
+// residual/identity branch).
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ c1, const float* __restrict__ c2,
+                                    __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dz_out,
+                                    long long total8, int C) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>((i * 8) % C);
+    float d[8], a[8], v[8], o[8], z[8];
+    unpack8(ld_nc16(dout + i * 8), d);
+    unpack8(ld_nc16(y + i * 8), v);
+    if (act) unpack8(ld_nc16(act + i * 8), a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      const float dzv = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+      const float is = __ldg(invstd + c);
+      const float xhat = (v[e] - __ldg(mean + c)) * is;
+      const float g = gamma ? __ldg(gamma + c) : 1.f;
+      o[e] = g * is * (dzv - __ldg(c1 + c) - xhat * __ldg(c2 + c));
+      z[e] = dzv;
+    }
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+    if (dz_out) *reinterpret_cast<uint4*>(dz_out + i * 8) = pack8(z);
+  }
+}
+
+// dz = dout * (act > 0): ReLU backward for layers without BatchNorm.
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
+                                __nv_bfloat16* __restrict__ dz, long long total8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float d[8], a[8];
+    unpack8(ld_nc16(dout + i * 8), d);
+    unpack8(ld_nc16(act + i * 8), a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = (a[e] > 0.f) ? d[e] : 0.f;
+    *reinterpret_cast<uint4*>(dz + i * 8) = pack8(d);
+  }
+}
+
+// Column sums of a dense bf16 [M][C] tensor -> partial[blocks][C] (bias gradients).
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float s1[8] = {0};
+  if (rl < lanes) {
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
+      float f[8];
+      unpack8(ld_nc16(x + r * C + cg * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1[e] += f[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[rl * C + cg * 8 + e] = s1[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * C + i];
+    partial[static_cast<long long>(blockIdx.x) * C + i] = acc;
+  }
+}
+__global__ void colreduce_final_f32_kernel(const double* __restrict__ sums, int S, int K, float* __restrict__ out,
+                                           int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += sums[static_cast<long long>(s) * K + k];
+  out[k] = accumulate ? out[k] + static_cast<float>(acc) : static_cast<float>(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(kernel, stride, pad) on NHWC bf16 with an int8 argmax plane (first maximum in
+// row-major window order, like ATen's max_pool2d_with_indices), C % 8 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool2d_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                     signed char* __restrict__ argmax, int N, int H, int W, int C, int Ho, int Wo,
+                                     int ksize, int stride, int pad) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = i % groups;
+    const int wo = (i / groups) % Wo;
+    const int ho = (i / (static_cast<long long>(groups) * Wo)) % Ho;
+    const int n = i / (static_cast<long long>(groups) * Wo * Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = -1; }
+    for (int r = 0; r < ksize; ++r) {
+      const int h = ho * stride - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < ksize; ++s) {
+        const int w = wo * stride - pad + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld_nc16(x + ((static_cast<long long>(n) * H + h) * W + w) * C + cg * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (f[e] > best[e] || bi[e] < 0) { best[e] = f[e]; bi[e] = r * ksize + s; }
+      }
+    }
+    const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
+    *reinterpret_cast<uint4*>(out + o) = pack8(best);
+    if (argmax) {
+      uint2 pk;
+      pk.x = (bi[0] & 0xff) | ((bi[1] & 0xff) << 8) | ((bi[2] & 0xff) << 16) | ((bi[3] & 0xff) << 24);
+      pk.y = (bi[4] & 0xff) | ((bi[5] & 0xff) << 8) | ((bi[6] & 0xff) << 16) | ((bi[7] & 0xff) << 24);
+      *reinterpret_cast<uint2*>(argmax + o) = pk;
+    }
+  }
+}
+// Scatter-free backward: each input pixel gathers from the output windows that cover it.
+__global__ void maxpool2d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const signed char* __restrict__ argmax,
+                                     __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo,
+                                     int ksize, int stride, int pad) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(N) * H * W * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = i % groups;
+    const int w = (i / groups) % W;
+    const int h = (i / (static_cast<long long>(groups) * W)) % H;
+    const int n = i / (static_cast<long long>(groups) * W * H);
+    float acc[8] = {0};
+    // output rows ho with ho*stride - pad <= h <= ho*stride - pad + ksize - 1
+    const int ho_lo = max(0, (h + pad - ksize + stride) / stride);
+    const int ho_hi = min(Ho - 1, (h + pad) / stride);
+    const int wo_lo = max(0, (w + pad - ksize + stride) / stride);
+    const int wo_hi = min(Wo - 1, (w + pad) / stride);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      const int r = h - (ho * stride - pad);
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int s = w - (wo * stride - pad);
+        const int code = r * ksize + s;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
+        float d[8];
+        unpack8(ld_nc16(dout + o), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int a = (e < 4 ? (pk.x >> (8 * e)) : (pk.y >> (8 * (e - 4)))) & 0xff;
+          if (a == code) acc[e] += d[e];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quadtree pooling stage of QuadtreeCNN (reference: Quadtree_from scratch/models.py:277-294).
+//   q    : [4][B][QH][QW][Cq] bf16, quadrant conv output after bias+ReLU (quadrant-major)
+//   l4   : [B][GH*GW][Cg] bf16, layer4 output
+//   feat : [B][ldf] bf16, columns [0,Cg) = mean over GH*GW, then per quadrant (TL,TR,BL,BR)
+//          Cq*PH*PW values in NCHW flatten order c*(PH*PW) + ph*PW + pw, MaxPool2d(2,2) floor mode.
+// One thread per (b, quadrant, channel) / (b, global channel); loads are coalesced across channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ l4,
+                                         __nv_bfloat16* __restrict__ feat, int B, int QH, int QW, int Cq, int GHW,
+                                         int Cg, int ldf) {
+  const int PH = QH / 2, PW = QW / 2;
+  const long long nq = static_cast<long long>(B) * 4 * Cq;
+  const long long ng = static_cast<long long>(B) * Cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nq + ng;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nq) {
+      const int c = i % Cq;
+      const int qi = (i / Cq) % 4;
+      const int b = i / (static_cast<long long>(Cq) * 4);
+      const __nv_bfloat16* src = q + ((static_cast<long long>(qi) * B + b) * QH * QW) * Cq + c;
+      __nv_bfloat16* dst = feat + static_cast<long long>(b) * ldf + Cg + static_cast<long long>(qi) * Cq * PH * PW +
+                           static_cast<long long>(c) * PH * PW;
+      for (int ph = 0; ph < PH; ++ph)
+        for (int pw = 0; pw < PW; ++pw) {
+          float m = -INFINITY;
+          for (int r = 0; r < 2; ++r)
+            for (int s = 0; s < 2; ++s)
+              m = fmaxf(m, __bfloat162float(src[((2 * ph + r) * QW + (2 * pw + s)) * static_cast<long long>(Cq)]));
+          dst[ph * PW + pw] = __float2bfloat16_rn(m);
+        }
+    } else {
+      const long long j = i - nq;
+      const int c = j % Cg;
+      const int b = j / Cg;
+      const __nv_bfloat16* src = l4 + static_cast<long long>(b) * GHW * Cg + c;
+      float acc = 0.f;
+      for (int p = 0; p < GHW; ++p) acc += __bfloat162float(src[static_cast<long long>(p) * Cg]);
+      feat[static_cast<long long>(b) * ldf + c] = __float2bfloat16_rn(acc / GHW);
+    }
+  }
+}
+// Backward (scatter-free broadcast): every quadrant-conv output element looks up whether it is the
+// (first) arg-max of its pooling window and whether its ReLU was active; every layer4 element
+// receives dfeat/GHW.  dfeat: [B][ldf] bf16.
+__global__ void quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat, const __nv_bfloat16* __restrict__ q,
+                                         __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dl4, int B,
+                                         int QH, int QW, int Cq, int GHW, int Cg, int ldf) {
+  const int PH = QH / 2, PW = QW / 2;
+  const long long nq = static_cast<long long>(B) * 4 * QH * QW * Cq;
+  const long long ng = static_cast<long long>(B) * GHW * Cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nq + ng;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nq) {
+      const int c = i % Cq;
+      const int w = (i / Cq) % QW;
+      const int h = (i / (static_cast<long long>(Cq) * QW)) % QH;
+      const int b = (i / (static_cast<long long>(Cq) * QW * QH)) % B;
+      const int qi = i / (static_cast<long long>(Cq) * QW * QH * B);
+      const int ph = h >> 1, pw = w >> 1;
+      float g = 0.f;
+      if (ph < PH && pw < PW) {
+        const __nv_bfloat16* win = q + (((static_cast<long long>(qi) * B + b) * QH + 2 * ph) * QW + 2 * pw) * Cq + c;
+        const float v00 = __bfloat162float(win[0]);
+        const float v01 = __bfloat162float(win[Cq]);
+        const float v10 = __bfloat162float(win[static_cast<long long>(QW) * Cq]);
+        const float v11 = __bfloat162float(win[static_cast<long long>(QW) * Cq + Cq]);
+        int am = 0; float m = v00;
+        if (v01 > m) { m = v01; am = 1; }
+        if (v10 > m) { m = v10; am = 2; }
+        if (v11 > m) { m = v11; am = 3; }
+        const int me = (h & 1) * 2 + (w & 1);
+        if (am == me && m > 0.f)
+          g = __bfloat162float(dfeat[static_cast<long long>(b) * ldf + Cg + static_cast<long long>(qi) * Cq * PH * PW +
+                                     static_cast<long long>(c) * PH * PW + ph * PW + pw]);
+      }
+      dq[i] = __float2bfloat16_rn(g);
+    } else {
+      const long long j = i - nq;
+      const int c = j % Cg;
+      const int b = j / (static_cast<long long>(Cg) * GHW);
+      dl4[j] = __float2bfloat16_rn(__bfloat162float(dfeat[static_cast<long long>(b) * ldf + c]) / GHW);
+    }
+  }
+}
+
+// Region average pooling for the level-2 models (AttentionHierarchicalCNN): x [R][P][C] bf16 (R regions of
+// P pixels, already bias+ReLU) -> out[R][C] written at feat + r_off(r): caller passes a dense [R][C]
+// destination with row stride ldo.
+__global__ void region_avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                          long long R, int P, int C, long long ldo) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < R * C;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const long long r = i / C;
+    const __nv_bfloat16* src = x + r * P * C + c;
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc += __bfloat162float(src[static_cast<long long>(p) * C]);
+    out[r * ldo + c] = __float2bfloat16_rn(acc / P);
+  }
+}
+// Backward of (ReLU -> mean over P): dx[r][p][c] = dout[r][c]/P * (x[r][p][c] > 0).
+__global__ void region_avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                                          __nv_bfloat16* __restrict__ dx, long long R, int P, int C, long long ldo,
+                                          int relu_mask) {
+  const long long total = R * P * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const long long r = i / (static_cast<long long>(C) * P);
+    float g = __bfloat162float(dout[r * ldo + c]) / P;
+    if (relu_mask && !(__bfloat162float(x[i]) > 0.f)) g = 0.f;
+    dx[i] = __float2bfloat16_rn(g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small fp32 linear layers of the fusion head (numerical MLP 47->94->256, classifier.3 2688->nc).
+// One warp per output element; inputs fp32 or bf16, fp32 weights and accumulation.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float ld_as_float(const TIn* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// out[b][n] = drop(act(x[b][:] . w[n][:] + bias[n])); out fp32 (ldo) and/or bf16 (ldo16).
+template <typename TIn>
+__global__ void small_linear_fwd_kernel(const TIn* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                        const float* __restrict__ bias, int B, int N, int K, int relu, float drop_p,
+                                        unsigned long long seed, float* __restrict__ out, long long ldo,
+                                        __nv_bfloat16* __restrict__ out16, long long ldo16) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= static_cast<long long>(B) * N) return;
+  const int n = warp % N;
+  const int b = warp / N;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(ld_as_float<TIn>(x + b * ldx + k), w[static_cast<long long>(n) * K + k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (bias) acc += bias[n];
+    if (relu) acc = fmaxf(acc, 0.f);
+    acc *= dropout_scale(seed, static_cast<uint32_t>(b) * N + n, drop_p);
+    if (out) out[b * ldo + n] = acc;
+    if (out16) out16[b * ldo16 + n] = __float2bfloat16_rn(acc);
+  }
+}
+// dx[b][k] = mask(b,k) * sum_n dy[b][n] * w[n][k]; mask = (act[b][k] > 0) (post-ReLU/dropout output, optional).
+template <typename TDy>
+__global__ void small_linear_bwd_dx_kernel(const TDy* __restrict__ dy, long long ldy, const float* __restrict__ w,
+                                           int B, int N, int K, const float* __restrict__ act, long long lda,
+                                           float drop_p, unsigned long long seed, float* __restrict__ dx,
+                                           long long ldx, __nv_bfloat16* __restrict__ dx16, long long ldx16) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * K) return;
+  const int k = i % K;
+  const int b = i / K;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc = fmaf(ld_as_float<TDy>(dy + b * ldy + n), w[static_cast<long long>(n) * K + k], acc);
+  if (act) {
+    // act holds the layer's stored output relu(z)*dropout_scale: zero wherever either gate was closed.
+    const float a = act[b * lda + k];
+    acc = (a > 0.f) ? acc * dropout_scale(seed, static_cast<uint32_t>(b) * K + k, drop_p) : 0.f;
+  }
+  if (dx) dx[b * ldx + k] = acc;
+  if (dx16) dx16[b * ldx16 + k] = __float2bfloat16_rn(acc);
+}
+// dw[n][k] (+)= sum_b dy[b][n] * x[b][k]; db[n] (+)= sum_b dy[b][n] (k == 0 thread).
+template <typename TDy, typename TX>
+__global__ void small_linear_bwd_dw_kernel(const TDy* __restrict__ dy, long long ldy, const TX* __restrict__ x,
+                                           long long ldx, int B, int N, int K, float* __restrict__ dw,
+                                           float* __restrict__ db, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int k = i % K;
+  const int n = i / K;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float d = ld_as_float<TDy>(dy + b * ldy + n);
+    acc = fmaf(d, ld_as_float<TX>(x + b * ldx + k), acc);
+    accb += d;
+  }
+  dw[i] = accumulate ? dw[i] + acc : acc;
+  if (db && k == 0) db[n] = accumulate ? db[n] + accb : accb;
+}
+
+// Elementwise helpers on dense tensors.
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ out, long long total8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ld_nc16(a + i * 8), x);
+    unpack8(ld_nc16(b + i * 8), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(x);
+  }
+}
+// Post-GEMM head epilogue on an fp32 [B][N] tensor: h = relu(h) * dropout -> fp32 in place + bf16 copy.
+__global__ void relu_dropout_kernel(float* __restrict__ h, __nv_bfloat16* __restrict__ h16, long long total, float drop_p,
+                                    unsigned long long seed, int relu) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = h[i];
+    if (relu) v = fmaxf(v, 0.f);
+    v *= dropout_scale(seed, static_cast<uint32_t>(i), drop_p);
+    h[i] = v;
+    if (h16) h16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace qt

@@ -1,0 +1,705 @@
+// libqtcnn.so — C ABI (include/qtcnn.h) over the sm_100a kernels in igemm.cuh / elementwise.cuh.
+// Single translation unit; build: see __graft_entry__.build().
+#include "../../include/qtcnn.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "elementwise.cuh"
+#include "igemm.cuh"
+
+using namespace qt;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+int cuda_status(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+inline cudaStream_t S(qt_stream_t s) { return static_cast<cudaStream_t>(s); }
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return static_cast<int>(g);
+}
+inline int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+inline int out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+constexpr int kNumSMs = 148;
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launch helpers
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+int launch_kmajor(const IgemmParams& p, dim3 grid, cudaStream_t st) {
+  using L = KMajorSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(igemm_kmajor_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    configured = true;
+  }
+  igemm_kmajor_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, st>>>(p);
+  return cuda_status("igemm_kmajor_kernel");
+}
+template <int BN, int STAGES>
+int launch_wgrad(const IgemmParams& p, dim3 grid, cudaStream_t st) {
+  using L = WgradSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(igemm_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    configured = true;
+  }
+  igemm_wgrad_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, st>>>(p);
+  return cuda_status("igemm_wgrad_kernel");
+}
+
+inline int pick_bn(int nout) { return nout <= 64 ? 64 : 128; }
+
+// Chooses split-K and launches the K-major kernel (+ the split-K reduction when used).
+// `dense_out_ld` > 0 means the output is a dense row-major [M][nout] matrix with that row stride
+// (required for split-K).
+int run_kmajor(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, long long dense_out_ld) {
+  const int BN = pick_bn(p.nout);
+  const int gx = (p.M + kBM - 1) / kBM, gy = (p.nout + BN - 1) / BN;
+  p.num_kb = (p.ntaps * p.cin + kBK - 1) / kBK;
+  if (p.num_kb < 1) return fail("igemm: empty K");
+  int ksplit = 1;
+  const long long tiles = static_cast<long long>(gx) * gy * p.groups;
+  if (dense_out_ld > 0 && p.groups == 1 && !(p.flags & (EPI_STATS | EPI_ADDEND)) && tiles < kNumSMs && p.num_kb >= 8) {
+    ksplit = static_cast<int>((2 * kNumSMs + tiles - 1) / tiles);
+    if (ksplit > p.num_kb / 4) ksplit = p.num_kb / 4;
+    if (ksplit > 32) ksplit = 32;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+  ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.ksplit = ksplit;
+  p.Mpad = gx * kBM;
+  p.Npad = gy * BN;
+  const int user_flags = p.flags;
+  if (ksplit > 1) {
+    const size_t need = static_cast<size_t>(ksplit) * p.Mpad * p.Npad * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) return fail("igemm: split-K workspace too small (%zu < %zu)", ws_bytes, need);
+    p.splitk_ws = static_cast<float*>(ws);
+    p.flags = EPI_SPLITK;
+  }
+  dim3 grid(gx, gy, p.groups * ksplit);
+  int rc = (BN == 64) ? launch_kmajor<64, 4>(p, grid, st) : launch_kmajor<128, 3>(p, grid, st);
+  if (rc) return rc;
+  if (ksplit > 1) {
+    const long long total = static_cast<long long>(p.M) * p.nout;
+    splitk_reduce_rows_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, st>>>(
+        p.splitk_ws, ksplit, p.M, p.nout, p.Mpad, p.Npad, (user_flags & EPI_BIAS) ? p.bias : nullptr,
+        (user_flags & EPI_RELU) ? 1 : 0, (user_flags & EPI_OUT_F32) ? 1 : 0, p.out, dense_out_ld);
+    rc = cuda_status("splitk_reduce_rows_kernel");
+  }
+  return rc;
+}
+
+void fill_groups(IgemmParams& p, const qt_conv_desc* d, bool a_is_x) {
+  p.groups = d->groups < 1 ? 1 : d->groups;
+  for (int g = 0; g < 4; ++g) {
+    p.a_goff[g] = a_is_x ? d->x_group_off[g] : d->y_group_off[g];
+    p.o_goff[g] = a_is_x ? d->y_group_off[g] : d->x_group_off[g];
+    p.b_goff[g] = 0;
+  }
+}
+
+int check_desc(const qt_conv_desc* d) {
+  if (!d) return fail("null conv descriptor");
+  if (d->n < 1 || d->in_c < 1 || d->out_c < 1) return fail("conv: bad sizes");
+  if (d->groups < 1 || d->groups > 4) return fail("conv: groups must be 1..4");
+  if (d->k_d * d->k_h * d->k_w > kMaxTaps) return fail("conv: more than %d taps", kMaxTaps);
+  if (d->in_c % 8 || d->out_c % 8) return fail("conv: channel counts must be multiples of 8 (got %d -> %d)", d->in_c, d->out_c);
+  return 0;
+}
+
+struct OutDims { int d, h, w; };
+OutDims conv_out_dims(const qt_conv_desc* d) {
+  return {out_dim(d->in_d, d->k_d, d->stride_d, d->pad_d), out_dim(d->in_h, d->k_h, d->stride_h, d->pad_h),
+          out_dim(d->in_w, d->k_w, d->stride_w, d->pad_w)};
+}
+
+size_t wgrad_ws_bytes(int F, int nout, int groups, long long pixels, int* ksplit_out) {
+  const int BN = pick_bn(nout);
+  const int gx = (F + kBM - 1) / kBM, gy = (nout + BN - 1) / BN;
+  const long long num_kb = (pixels + 63) / 64;
+  const long long tiles = static_cast<long long>(gx) * gy * groups;
+  long long ksplit = (2 * kNumSMs + tiles - 1) / tiles;
+  if (ksplit > num_kb / 8) ksplit = num_kb / 8;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > 256) ksplit = 256;
+  long long per = (num_kb + ksplit - 1) / ksplit;
+  ksplit = (num_kb + per - 1) / per;
+  if (ksplit_out) *ksplit_out = static_cast<int>(ksplit);
+  return static_cast<size_t>(groups) * ksplit * gx * kBM * gy * BN * sizeof(float);
+}
+
+// Shared wgrad driver. p must describe the forward gather (A = x) and the dy view (ov / b).
+int run_wgrad(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, float* dw, int accumulate, int cin_real,
+              int taps_real) {
+  const int F = p.ntaps * p.cin;
+  const int BN = pick_bn(p.nout);
+  const int gx = (F + kBM - 1) / kBM, gy = (p.nout + BN - 1) / BN;
+  int ksplit = 1;
+  const size_t need = wgrad_ws_bytes(F, p.nout, p.groups, p.M, &ksplit);
+  if (ws == nullptr || ws_bytes < need) return fail("wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.num_kb = (p.M + 63) / 64;
+  p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+  p.ksplit = ksplit;
+  p.Mpad = gx * kBM;
+  p.Npad = gy * BN;
+  p.splitk_ws = static_cast<float*>(ws);
+  {  // 64 pixels decomposed over the logical output grid
+    int r = 64;
+    p.adv_w = r % p.ow; r /= p.ow;
+    p.adv_h = r % p.oh; r /= p.oh;
+    p.adv_d = r % p.od; r /= p.od;
+    p.adv_n = r;
+  }
+  dim3 grid(gx, gy, p.groups * ksplit);
+  int rc = (BN == 64) ? launch_wgrad<64, 4>(p, grid, st) : launch_wgrad<128, 3>(p, grid, st);
+  if (rc) return rc;
+  const long long total = static_cast<long long>(F) * p.nout;
+  splitk_reduce_wgrad_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, st>>>(
+      p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad, cin_real, taps_real, dw, accumulate);
+  return cuda_status("splitk_reduce_wgrad_kernel");
+}
+
+// Forward-gather description shared by fprop and wgrad.
+int fill_forward(IgemmParams& p, const qt_conv_desc* d) {
+  const OutDims o = conv_out_dims(d);
+  if (o.d < 1 || o.h < 1 || o.w < 1) return fail("conv: empty output");
+  memset(&p, 0, sizeof(p));
+  p.av = {d->x_stride[0], d->x_stride[1], d->x_stride[2], d->x_stride[3]};
+  p.ov = {d->y_stride[0], d->y_stride[1], d->y_stride[2], d->y_stride[3]};
+  p.id = d->in_d; p.ih = d->in_h; p.iw = d->in_w;
+  p.nb = d->n; p.od = o.d; p.oh = o.h; p.ow = o.w;
+  p.mult_d = d->stride_d; p.mult_h = d->stride_h; p.mult_w = d->stride_w;
+  p.ntaps = d->k_d * d->k_h * d->k_w;
+  p.wtaps = p.ntaps;
+  p.cin = d->in_c;
+  p.cin_log2 = ilog2_exact(d->in_c);
+  if (p.ntaps > 1 && p.cin_log2 < 0) return fail("conv: in_c must be a power of two for multi-tap kernels (got %d)", d->in_c);
+  int t = 0;
+  for (int kd = 0; kd < d->k_d; ++kd)
+    for (int kh = 0; kh < d->k_h; ++kh)
+      for (int kw = 0; kw < d->k_w; ++kw, ++t) {
+        p.off_d[t] = static_cast<signed char>(kd - d->pad_d);
+        p.off_h[t] = static_cast<signed char>(kh - d->pad_h);
+        p.off_w[t] = static_cast<signed char>(kw - d->pad_w);
+        p.wtap[t] = static_cast<short>(t);
+      }
+  p.nout = d->out_c;
+  p.M = d->n * o.d * o.h * o.w;
+  fill_groups(p, d, true);
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int qt_version(void) { return 100; }
+const char* qt_last_error(void) { return g_err; }
+int qt_take_timeout_flag(void) {
+  unsigned int v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, g_timeout_flag, sizeof(v));
+  if (v) cudaMemcpyToSymbol(g_timeout_flag, &z, sizeof(z));
+  return static_cast<int>(v);
+}
+
+// ---- layout / packing -----------------------------------------------------------------------------
+int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream) {
+  if (c > 4) return fail("stem_pack_input: at most 4 channels");
+  const long long total = static_cast<long long>(n) * (h + 7) * (w + 8);
+  stem_pack_input_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(xp), n, c, h, w);
+  return cuda_status("stem_pack_input");
+}
+int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {
+  const long long total = static_cast<long long>(n) * hw * c_pad;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n, c, hw, c_pad);
+  return cuda_status("nchw_f32_to_nhwc_bf16");
+}
+int qt_nhwc_bf16_to_nchw_f32(const void* x, float* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {
+  const long long total = static_cast<long long>(n) * hw * c;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), out, n, c, hw, c_pad);
+  return cuda_status("nhwc_bf16_to_nchw_f32");
+}
+int qt_wpack_fprop(const float* w, void* wf, int cout, int cin, int taps, qt_stream_t stream) {
+  const long long total = static_cast<long long>(cout) * cin * taps;
+  wpack_fprop_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), cout, cin, taps);
+  return cuda_status("wpack_fprop");
+}
+int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_stream_t stream) {
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps), block(32, 8);
+  wpack_dgrad_kernel<<<grid, block, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), cout, cin, taps);
+  return cuda_status("wpack_dgrad");
+}
+int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream) {
+  if (cin > 4 || r > 8 || s > 8) return fail("wpack_stem: filter does not fit the 8x(8x4) packing");
+  wpack_stem_kernel<<<grid_for(cout * 256, 256), 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(w8), cout, cin, r, s);
+  return cuda_status("wpack_stem");
+}
+int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
+  f32_to_bf16_kernel<<<grid_for(n, 256, 1 << 20), 256, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n);
+  return cuda_status("f32_to_bf16");
+}
+
+// ---- convolutions -----------------------------------------------------------------------------------
+int qt_conv_stat_rows(const qt_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  const OutDims o = conv_out_dims(d);
+  const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
+  return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));
+}
+size_t qt_conv_fprop_workspace_bytes(const qt_conv_desc* d) { (void)d; return 0; }
+
+int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y, const float* bias, float* stats,
+                  int flags, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (int rc = check_desc(d)) return rc;
+  IgemmParams p;
+  if (int rc = fill_forward(p, d)) return rc;
+  p.a = static_cast<const __nv_bfloat16*>(x);
+  p.b = static_cast<const __nv_bfloat16*>(wf);
+  p.out = y;
+  p.bias = bias;
+  p.stats = stats;
+  p.flags = flags & (EPI_BIAS | EPI_RELU | EPI_STATS | EPI_OUT_F32);
+  if ((p.flags & EPI_BIAS) && !bias) return fail("conv_fprop: QT_EPI_BIAS without bias");
+  if ((p.flags & EPI_STATS) && !stats) return fail("conv_fprop: QT_EPI_STATS without stats buffer");
+  return run_kmajor(p, S(stream), ws, ws_bytes, 0);
+}
+
+int qt_conv_dgrad(const qt_conv_desc* d, const void* dy, const void* wd, void* dx, int accumulate,
+                  qt_stream_t stream) {
+  if (int rc = check_desc(d)) return rc;
+  const OutDims o = conv_out_dims(d);
+  const int sd = d->stride_d, sh = d->stride_h, sw = d->stride_w;
+  if (ilog2_exact(d->out_c) < 0 && d->k_d * d->k_h * d->k_w > 1) return fail("conv_dgrad: out_c must be a power of two");
+  bool any_empty = false;
+  // One launch per stride-parity class; for stride 1 there is exactly one.
+  for (int pd = 0; pd < sd; ++pd)
+    for (int ph = 0; ph < sh; ++ph)
+      for (int pw = 0; pw < sw; ++pw) {
+        IgemmParams p;
+        memset(&p, 0, sizeof(p));
+        int t = 0;
+        for (int kd = 0; kd < d->k_d; ++kd) {
+          if ((pd + d->pad_d - kd) % sd) continue;
+          for (int kh = 0; kh < d->k_h; ++kh) {
+            if ((ph + d->pad_h - kh) % sh) continue;
+            for (int kw = 0; kw < d->k_w; ++kw) {
+              if ((pw + d->pad_w - kw) % sw) continue;
+              p.off_d[t] = static_cast<signed char>((pd + d->pad_d - kd) / sd);
+              p.off_h[t] = static_cast<signed char>((ph + d->pad_h - kh) / sh);
+              p.off_w[t] = static_cast<signed char>((pw + d->pad_w - kw) / sw);
+              p.wtap[t] = static_cast<short>((kd * d->k_h + kh) * d->k_w + kw);
+              ++t;
+            }
+          }
+        }
+        const int gd = (d->in_d - pd + sd - 1) / sd, gh = (d->in_h - ph + sh - 1) / sh, gw = (d->in_w - pw + sw - 1) / sw;
+        if (gd < 1 || gh < 1 || gw < 1) continue;
+        if (t == 0) { any_empty = true; continue; }
+        p.ntaps = t;
+        p.wtaps = d->k_d * d->k_h * d->k_w;
+        p.cin = d->out_c;
+        p.cin_log2 = ilog2_exact(d->out_c);
+        p.a = static_cast<const __nv_bfloat16*>(dy);
+        p.av = {d->y_stride[0], d->y_stride[1], d->y_stride[2], d->y_stride[3]};
+        p.id = o.d; p.ih = o.h; p.iw = o.w;
+        p.nb = d->n; p.od = gd; p.oh = gh; p.ow = gw;
+        p.mult_d = p.mult_h = p.mult_w = 1;
+        p.b = static_cast<const __nv_bfloat16*>(wd);
+        p.nout = d->in_c;
+        p.out = dx;
+        p.ov = {d->x_stride[0], d->x_stride[1] * sd, d->x_stride[2] * sh, d->x_stride[3] * sw};
+        fill_groups(p, d, false);
+        const long long poff = pd * d->x_stride[1] + ph * d->x_stride[2] + pw * d->x_stride[3];
+        for (int g = 0; g < 4; ++g) p.o_goff[g] += poff;
+        p.M = d->n * gd * gh * gw;
+        p.flags = accumulate ? EPI_ADDEND : 0;
+        p.addend = static_cast<const __nv_bfloat16*>(dx);
+        if (int rc = run_kmajor(p, S(stream), nullptr, 0, 0)) return rc;
+      }
+  if (any_empty && !accumulate)
+    return fail("conv_dgrad: stride leaves input positions without taps; zero dx and call with accumulate=1");
+  return 0;
+}
+
+size_t qt_conv_wgrad_workspace_bytes(const qt_conv_desc* d) {
+  if (check_desc(d)) return 0;
+  const OutDims o = conv_out_dims(d);
+  const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
+  return wgrad_ws_bytes(d->k_d * d->k_h * d->k_w * d->in_c, d->out_c, d->groups, M, nullptr);
+}
+int qt_conv_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
+                  size_t ws_bytes, qt_stream_t stream) {
+  if (int rc = check_desc(d)) return rc;
+  IgemmParams p;
+  if (int rc = fill_forward(p, d)) return rc;
+  p.a = static_cast<const __nv_bfloat16*>(x);
+  p.b = static_cast<const __nv_bfloat16*>(dy);
+  for (int g = 0; g < 4; ++g) p.b_goff[g] = d->y_group_off[g];
+  return run_wgrad(p, S(stream), ws, ws_bytes, dw, accumulate, d->in_c, p.ntaps);
+}
+
+// ---- stem (7x7 s2 p3 on 3 channels) as an 8-tap x 32-"channel" GEMM over the packed input ---------------
+static int fill_stem(IgemmParams& p, int n, int h, int w, int cout) {
+  if (h % 2 || w % 2) return fail("stem: even image sizes only");
+  memset(&p, 0, sizeof(p));
+  const int Hp = h + 7, Wp = w + 8;
+  p.av = {static_cast<long long>(Hp) * Wp * 4, 0, static_cast<long long>(Wp) * 4, 4};
+  p.id = 1; p.ih = Hp; p.iw = Wp;  // packed buffer already holds the zero padding
+  p.nb = n; p.od = 1; p.oh = h / 2; p.ow = w / 2;
+  p.mult_d = 1; p.mult_h = 2; p.mult_w = 2;
+  p.ntaps = 8; p.wtaps = 8; p.cin = 32; p.cin_log2 = 5;
+  for (int r = 0; r < 8; ++r) { p.off_d[r] = 0; p.off_h[r] = static_cast<signed char>(r); p.off_w[r] = 0; p.wtap[r] = static_cast<short>(r); }
+  p.nout = cout;
+  const long long ohw = static_cast<long long>(p.oh) * p.ow;
+  p.ov = {ohw * cout, 0, static_cast<long long>(p.ow) * cout, cout};
+  p.M = n * p.oh * p.ow;
+  p.groups = 1;
+  return 0;
+}
+int qt_stem_stat_rows(int n, int h, int w) { return (n * (h / 2) * (w / 2) + kBM - 1) / kBM; }
+int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, int h, int w, int cout,
+                  qt_stream_t stream) {
+  IgemmParams p;
+  if (int rc = fill_stem(p, n, h, w, cout)) return rc;
+  p.a = static_cast<const __nv_bfloat16*>(xp);
+  p.b = static_cast<const __nv_bfloat16*>(w8);
+  p.out = y;
+  p.stats = stats;
+  p.flags = stats ? EPI_STATS : 0;
+  return run_kmajor(p, S(stream), nullptr, 0, 0);
+}
+size_t qt_stem_wgrad_workspace_bytes(int n, int h, int w, int cout) {
+  return wgrad_ws_bytes(256, cout, 1, static_cast<long long>(n) * (h / 2) * (w / 2), nullptr) +
+         static_cast<size_t>(cout) * 256 * sizeof(float);
+}
+int qt_stem_wgrad(const void* xp, const void* dy, float* dw, int accumulate, int n, int h, int w, int cout, int cin,
+                  void* ws, size_t ws_bytes, qt_stream_t stream) {
+  IgemmParams p;
+  if (int rc = fill_stem(p, n, h, w, cout)) return rc;
+  const size_t g8_bytes = static_cast<size_t>(cout) * 256 * sizeof(float);
+  if (ws_bytes < g8_bytes) return fail("stem_wgrad: workspace too small");
+  float* g8 = static_cast<float*>(ws);
+  p.a = static_cast<const __nv_bfloat16*>(xp);
+  p.b = static_cast<const __nv_bfloat16*>(dy);
+  if (int rc = run_wgrad(p, S(stream), static_cast<char*>(ws) + g8_bytes, ws_bytes - g8_bytes, g8, 0, 32, 8)) return rc;
+  stem_wgrad_unpack_kernel<<<grid_for(cout * cin * 49, 256), 256, 0, S(stream)>>>(g8, dw, cout, cin, 7, 7, accumulate);
+  return cuda_status("stem_wgrad_unpack");
+}
+
+// ---- tensor-core linear layers ------------------------------------------------------------------------
+static void fill_linear(IgemmParams& p, const void* a, long long lda, const void* b, int rows, int nout, int k) {
+  memset(&p, 0, sizeof(p));
+  p.a = static_cast<const __nv_bfloat16*>(a);
+  p.av = {lda, 0, 0, 0};
+  p.id = p.ih = p.iw = 1;
+  p.nb = rows; p.od = p.oh = p.ow = 1;
+  p.mult_d = p.mult_h = p.mult_w = 1;
+  p.ntaps = 1; p.wtaps = 1; p.cin = k; p.cin_log2 = 0;
+  p.b = static_cast<const __nv_bfloat16*>(b);
+  p.nout = nout;
+  p.M = rows;
+  p.groups = 1;
+}
+size_t qt_linear_workspace_bytes(int b, int n, int k) {
+  // upper bound over fprop / dgrad split-K and wgrad partials
+  const size_t mp = static_cast<size_t>((b + kBM - 1) / kBM) * kBM;
+  size_t need = 32 * mp * (static_cast<size_t>((n + 127) / 128) * 128) * sizeof(float);
+  const size_t need2 = 32 * mp * (static_cast<size_t>((k + 127) / 128) * 128) * sizeof(float);
+  if (need2 > need) need = need2;
+  const size_t need3 = wgrad_ws_bytes(k, n, 1, b, nullptr);
+  return need3 > need ? need3 : need;
+}
+int qt_linear_fprop(const void* x, long long ldx, const void* w, const float* bias, void* out, long long ldo,
+                    int flags, int b, int n, int k, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (k % 8 || ldx % 8) return fail("linear_fprop: k and ldx must be multiples of 8");
+  IgemmParams p;
+  fill_linear(p, x, ldx, w, b, n, k);
+  p.out = out;
+  p.ov = {ldo, 0, 0, 0};
+  p.bias = bias;
+  p.flags = flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32);
+  return run_kmajor(p, S(stream), ws, ws_bytes, ldo);
+}
+int qt_linear_dgrad(const void* dy, long long ldy, const void* wt, void* dx, long long ldx, int b, int n, int k,
+                    void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (n % 8 || ldy % 8) return fail("linear_dgrad: n and ldy must be multiples of 8");
+  IgemmParams p;
+  fill_linear(p, dy, ldy, wt, b, k, n);  // dx[b][k] = dy[b][:] . wt[k][:]
+  p.out = dx;
+  p.ov = {ldx, 0, 0, 0};
+  p.flags = 0;
+  return run_kmajor(p, S(stream), ws, ws_bytes, ldx);
+}
+int qt_linear_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, int accumulate, int b,
+                    int n, int k, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (k % 8 || n % 8) return fail("linear_wgrad: n and k must be multiples of 8");
+  IgemmParams p;
+  fill_linear(p, x, ldx, dy, b, n, k);
+  p.ov = {ldy, 0, 0, 0};
+  return run_wgrad(p, S(stream), ws, ws_bytes, dw, accumulate, k, 1);
+}
+
+// ---- BatchNorm ----------------------------------------------------------------------------------------------
+namespace {
+constexpr int kRedSlices = 64;
+int reduce_partials(const float* partial, int rows, int K, double* sums, int* slices, cudaStream_t st) {
+  int s = rows < kRedSlices ? rows : kRedSlices;
+  if (s < 1) s = 1;
+  dim3 grid((K + 127) / 128, s);
+  colreduce_stage1_kernel<<<grid, 128, 0, st>>>(partial, rows, K, s, sums);
+  *slices = s;
+  return cuda_status("colreduce_stage1");
+}
+int rowlane_block(int c) {  // threads per block for the (C/8 groups) x lanes kernels
+  const int groups = c / 8;
+  int lanes = 256 / groups;
+  if (lanes < 1) lanes = 1;
+  return groups * lanes;
+}
+constexpr int kBwdBlocks = 148 * 4;
+}  // namespace
+
+size_t qt_bn_workspace_bytes(int c) {
+  // stage-1 sums (double) + per-block partials of the backward reduction + c1/c2
+  return static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double) + static_cast<size_t>(kBwdBlocks) * 2 * c * sizeof(float) +
+         2 * static_cast<size_t>(c) * sizeof(float) + 256;
+}
+int qt_bn_stats(const void* y, long long m, int c, float* partial, int partial_rows, qt_stream_t stream) {
+  if (c % 8 || c > 2048) return fail("bn_stats: c must be a multiple of 8 and <= 2048");
+  const int block = rowlane_block(c);
+  const int lanes = block / (c / 8);
+  bn_stats_kernel<<<partial_rows, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), m, c, partial);
+  return cuda_status("bn_stats");
+}
+int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                   qt_stream_t stream) {
+  if (ws_bytes < static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double)) return fail("bn_finalize: workspace too small");
+  double* sums = static_cast<double*>(ws);
+  int slices = 0;
+  if (int rc = reduce_partials(partial, partial_rows, 2 * c, sums, &slices, S(stream))) return rc;
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, count, gamma, beta, eps, momentum,
+                                                              running_mean, running_var, mean, invstd, scale, shift);
+  return cuda_status("bn_finalize");
+}
+int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, float* scale, float* shift, qt_stream_t stream) {
+  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(c, gamma, beta, running_mean, running_var, eps, scale, shift);
+  return cuda_status("bn_eval_coeffs");
+}
+int qt_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* out, long long m,
+                int c, int relu, qt_stream_t stream) {
+  if (c % 8) return fail("bn_apply: c must be a multiple of 8");
+  const long long total8 = m * c / 8;
+  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(y), scale, shift,
+                                                                static_cast<const __nv_bfloat16*>(residual),
+                                                                static_cast<__nv_bfloat16*>(out), total8, c, relu);
+  return cuda_status("bn_apply");
+}
+int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
+                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, void* dy,
+                   void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (c % 8 || c > 2048) return fail("bn_backward: c must be a multiple of 8 and <= 2048");
+  if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_backward: workspace too small");
+  double* sums = static_cast<double*>(ws);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
+  float* c1 = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;
+  float* c2 = c1 + c;
+  const int block = rowlane_block(c);
+  const int lanes = block / (c / 8);
+  long long want = (m + lanes - 1) / lanes;
+  const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
+  bn_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
+      static_cast<const __nv_bfloat16*>(y), mean, invstd, m, c, partial);
+  if (int rc = cuda_status("bn_bwd_reduce")) return rc;
+  int slices = 0;
+  if (int rc = reduce_partials(partial, blocks, 2 * c, sums, &slices, S(stream))) return rc;
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, static_cast<double>(m), dgamma, dbeta,
+                                                                  accumulate, c1, c2);
+  if (int rc = cuda_status("bn_bwd_finalize")) return rc;
+  const long long total8 = m * c / 8;
+  bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
+      static_cast<const __nv_bfloat16*>(y), mean, invstd, gamma, c1, c2, static_cast<__nv_bfloat16*>(dy),
+      static_cast<__nv_bfloat16*>(dz_out), total8, c);
+  return cuda_status("bn_bwd_apply");
+}
+int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream) {
+  if (n % 8) return fail("relu_backward: n must be a multiple of 8");
+  relu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                               static_cast<const __nv_bfloat16*>(act),
+                                                               static_cast<__nv_bfloat16*>(dz), n / 8);
+  return cuda_status("relu_backward");
+}
+int qt_colsum(const void* x, long long m, int c, float* out, int accumulate, void* ws, size_t ws_bytes,
+              qt_stream_t stream) {
+  if (c % 8 || c > 2048) return fail("colsum: c must be a multiple of 8 and <= 2048");
+  if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("colsum: workspace too small");
+  double* sums = static_cast<double*>(ws);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
+  const int block = rowlane_block(c);
+  const int lanes = block / (c / 8);
+  long long want = (m + lanes - 1) / lanes;
+  const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
+  colsum_bf16_kernel<<<blocks, block, static_cast<size_t>(lanes) * c * sizeof(float), S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), m, c, partial);
+  if (int rc = cuda_status("colsum")) return rc;
+  int slices = 0;
+  if (int rc = reduce_partials(partial, blocks, c, sums, &slices, S(stream))) return rc;
+  colreduce_final_f32_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, out, accumulate);
+  return cuda_status("colreduce_final");
+}
+int qt_add_bf16(const void* a, const void* b, void* out, long long n, qt_stream_t stream) {
+  if (n % 8) return fail("add_bf16: n must be a multiple of 8");
+  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(a),
+                                                               static_cast<const __nv_bfloat16*>(b),
+                                                               static_cast<__nv_bfloat16*>(out), n / 8);
+  return cuda_status("add_bf16");
+}
+
+// ---- pooling ------------------------------------------------------------------------------------------------
+int qt_maxpool2d_fwd(const void* x, void* out, void* argmax, int n, int h, int w, int c, int ksize, int stride,
+                     int pad, qt_stream_t stream) {
+  if (c % 8) return fail("maxpool2d: c must be a multiple of 8");
+  const int ho = out_dim(h, ksize, stride, pad), wo = out_dim(w, ksize, stride, pad);
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
+  maxpool2d_fwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                    static_cast<__nv_bfloat16*>(out),
+                                                                    static_cast<signed char*>(argmax), n, h, w, c, ho, wo,
+                                                                    ksize, stride, pad);
+  return cuda_status("maxpool2d_fwd");
+}
+int qt_maxpool2d_bwd(const void* dout, const void* argmax, void* dx, int n, int h, int w, int c, int ksize,
+                     int stride, int pad, qt_stream_t stream) {
+  if (c % 8) return fail("maxpool2d: c must be a multiple of 8");
+  const int ho = out_dim(h, ksize, stride, pad), wo = out_dim(w, ksize, stride, pad);
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  maxpool2d_bwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                                    static_cast<const signed char*>(argmax),
+                                                                    static_cast<__nv_bfloat16*>(dx), n, h, w, c, ho, wo,
+                                                                    ksize, stride, pad);
+  return cuda_status("maxpool2d_bwd");
+}
+int qt_quadtree_pool_fwd(const void* q, const void* l4, void* feat, int b, int qh, int qw, int cq, int ghw, int cg,
+                         int ldf, qt_stream_t stream) {
+  const long long total = static_cast<long long>(b) * 4 * cq + static_cast<long long>(b) * cg;
+  quadtree_pool_fwd_kernel<<<grid_for(total, 128), 128, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(q),
+                                                                        static_cast<const __nv_bfloat16*>(l4),
+                                                                        static_cast<__nv_bfloat16*>(feat), b, qh, qw, cq,
+                                                                        ghw, cg, ldf);
+  return cuda_status("quadtree_pool_fwd");
+}
+int qt_quadtree_pool_bwd(const void* dfeat, const void* q, void* dq, void* dl4, int b, int qh, int qw, int cq,
+                         int ghw, int cg, int ldf, qt_stream_t stream) {
+  const long long total = static_cast<long long>(b) * 4 * qh * qw * cq + static_cast<long long>(b) * ghw * cg;
+  quadtree_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dfeat), static_cast<const __nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(dq),
+      static_cast<__nv_bfloat16*>(dl4), b, qh, qw, cq, ghw, cg, ldf);
+  return cuda_status("quadtree_pool_bwd");
+}
+int qt_region_avgpool_fwd(const void* x, void* out, long long regions, int p, int c, long long ldo,
+                          qt_stream_t stream) {
+  region_avgpool_fwd_kernel<<<grid_for(regions * c, 128), 128, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                               static_cast<__nv_bfloat16*>(out), regions, p,
+                                                                               c, ldo);
+  return cuda_status("region_avgpool_fwd");
+}
+int qt_region_avgpool_bwd(const void* dout, const void* x, void* dx, long long regions, int p, int c, long long ldo,
+                          int relu_mask, qt_stream_t stream) {
+  region_avgpool_bwd_kernel<<<grid_for(regions * p * c, 256), 256, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(dx), regions,
+      p, c, ldo, relu_mask);
+  return cuda_status("region_avgpool_bwd");
+}
+
+// ---- small linears ------------------------------------------------------------------------------------------
+int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float* w, const float* bias, int b, int n,
+                        int k, int relu, float drop_p, unsigned long long seed, float* out, long long ldo,
+                        void* out16, long long ldo16, qt_stream_t stream) {
+  const long long warps = static_cast<long long>(b) * n;
+  const int grid = static_cast<int>((warps * 32 + 255) / 256);
+  if (x_is_bf16)
+    small_linear_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, w, bias, b, n,
+                                                                       k, relu, drop_p, seed, out, ldo,
+                                                                       static_cast<__nv_bfloat16*>(out16), ldo16);
+  else
+    small_linear_fwd_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(x), ldx, w, bias, b, n, k, relu,
+                                                               drop_p, seed, out, ldo, static_cast<__nv_bfloat16*>(out16),
+                                                               ldo16);
+  return cuda_status("small_linear_fwd");
+}
+int qt_small_linear_bwd_dx(const void* dy, int dy_is_bf16, long long ldy, const float* w, int b, int n, int k,
+                           const float* act, long long lda, float drop_p, unsigned long long seed, float* dx,
+                           long long ldx, void* dx16, long long ldx16, qt_stream_t stream) {
+  const long long total = static_cast<long long>(b) * k;
+  const int grid = static_cast<int>((total + 255) / 256);
+  if (dy_is_bf16)
+    small_linear_bwd_dx_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(dy), ldy, w, b, n, k,
+                                                                          act, lda, drop_p, seed, dx, ldx,
+                                                                          static_cast<__nv_bfloat16*>(dx16), ldx16);
+  else
+    small_linear_bwd_dx_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(dy), ldy, w, b, n, k, act, lda,
+                                                                  drop_p, seed, dx, ldx, static_cast<__nv_bfloat16*>(dx16),
+                                                                  ldx16);
+  return cuda_status("small_linear_bwd_dx");
+}
+int qt_small_linear_bwd_dw(const void* dy, int dy_is_bf16, long long ldy, const void* x, int x_is_bf16,
+                           long long ldx, int b, int n, int k, float* dw, float* db, int accumulate,
+                           qt_stream_t stream) {
+  const long long total = static_cast<long long>(n) * k;
+  const int grid = static_cast<int>((total + 255) / 256);
+  cudaStream_t st = S(stream);
+  if (dy_is_bf16 && x_is_bf16)
+    small_linear_bwd_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), ldy, static_cast<const __nv_bfloat16*>(x), ldx, b, n, k, dw, db, accumulate);
+  else if (dy_is_bf16)
+    small_linear_bwd_dw_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ldy,
+                                                                          static_cast<const float*>(x), ldx, b, n, k, dw, db,
+                                                                          accumulate);
+  else if (x_is_bf16)
+    small_linear_bwd_dw_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), ldy,
+                                                                          static_cast<const __nv_bfloat16*>(x), ldx, b, n, k,
+                                                                          dw, db, accumulate);
+  else
+    small_linear_bwd_dw_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), ldy,
+                                                                  static_cast<const float*>(x), ldx, b, n, k, dw, db,
+                                                                  accumulate);
+  return cuda_status("small_linear_bwd_dw");
+}
+int qt_relu_dropout(float* h, void* h16, long long n, float drop_p, unsigned long long seed, int relu,
+                    qt_stream_t stream) {
+  relu_dropout_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(h, static_cast<__nv_bfloat16*>(h16), n, drop_p, seed, relu);
+  return cuda_status("relu_dropout");
+}
+
+}  // extern "C"

@@ -1,0 +1,426 @@
+"""Per-kernel parity tests (need a B200): every C-ABI entry point is compared with a plain PyTorch fp32
+evaluation of the same operator on the same bf16-rounded inputs.
+
+Tolerances: bf16 outputs rel_L2 <= 4e-3 and max_abs <= 2^-7 * max|ref| (one bf16 ulp of the
+largest value, plus accumulation-order noise); fp32 outputs (statistics, weight gradients, logits)
+rel_L2 <= 1e-4 (fp32 accumulation in a different order than cuDNN/cuBLAS). Index work (pool argmax, quadrant
+assignment, feature-row offsets) is bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL_L2 = 4e-3
+F32_REL_L2 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def C():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import qtcnn_b200.capi as capi
+    capi.lib()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return capi
+
+
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def report(name, got, ref, tol, bf16_out=False):
+    got = got.float()
+    ref = ref.float()
+    err = rel_l2(got, ref)
+    maxabs = float((got - ref).abs().max())
+    refmax = float(ref.abs().max())
+    msg = f"{name}: rel_l2={err:.3e} max_abs={maxabs:.3e} ref_max={refmax:.3e} shape={tuple(ref.shape)}"
+    print(msg)
+    if not (err <= tol) or not math.isfinite(err):
+        # coarse error map to make a single remote run diagnosable
+        d = (got - ref).abs().reshape(ref.shape[0], -1) if ref.dim() > 1 else (got - ref).abs().reshape(1, -1)
+        rows = d.max(dim=1).values
+        bad_rows = (rows > 10 * tol * max(refmax, 1e-6)).nonzero().flatten()[:32].tolist()
+        cols = d.max(dim=0).values
+        bad_cols = (cols > 10 * tol * max(refmax, 1e-6)).nonzero().flatten()[:32].tolist()
+        pytest.fail(msg + f"\n first bad rows {bad_rows}\n first bad cols {bad_cols}\n got[0,:8]={got.flatten()[:8].tolist()}\n"
+                    f" ref[0,:8]={ref.flatten()[:8].tolist()}")
+    if bf16_out:
+        assert maxabs <= 2.0 ** -7 * refmax + 1e-6, msg
+
+
+def bf16(t):
+    return t.to(torch.bfloat16)
+
+
+def run(C, rc, what):
+    C.check(rc, what)
+    torch.cuda.synchronize()
+    assert C.lib().qt_take_timeout_flag() == 0, f"{what}: a barrier wait timed out inside the kernel"
+
+
+def nhwc(t):  # logical NCHW tensor -> dense NHWC bf16 buffer
+    return bf16(t).permute(0, 2, 3, 1).contiguous()
+
+
+def conv_case(C, n, cin, cout, h, w, k, stride, pad, bias=False, relu=False, stats=False, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, device="cuda", generator=g) if bias else None
+    xb, wb = bf16(x).float(), bf16(wt).float()
+    ref = F.conv2d(xb, wb, b, stride=stride, padding=pad)
+    if relu:
+        ref = ref.relu()
+    ho, wo = ref.shape[2], ref.shape[3]
+    x_nhwc = nhwc(x)
+    wf = torch.empty(cout, k * k, cin, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_fprop(C.ptr(wt.contiguous()), C.ptr(wf), cout, cin, k * k, C.stream()), "wpack_fprop")
+    assert torch.equal(wf, bf16(wt).permute(0, 2, 3, 1).reshape(cout, k * k, cin)), "wpack_fprop layout"
+    d = C.conv_desc(n, (1, h, w), cin, cout, (1, k, k), (1, stride, stride), (0, pad, pad))
+    y = torch.full((n, ho, wo, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rows = C.lib().qt_conv_stat_rows(d)
+    st = torch.zeros(rows, 2, cout, device="cuda") if stats else None
+    flags = (C.QT_EPI_BIAS if bias else 0) | (C.QT_EPI_RELU if relu else 0) | (C.QT_EPI_STATS if stats else 0)
+    run(C, C.lib().qt_conv_fprop(d, C.ptr(x_nhwc), C.ptr(wf), C.ptr(y), C.ptr(b), C.ptr(st), flags, None, 0, C.stream()),
+        "conv_fprop")
+    report(f"conv_fprop n{n} c{cin}->{cout} {h}x{w} k{k} s{stride} p{pad}", y.permute(0, 3, 1, 2), ref, BF16_REL_L2, True)
+    if stats:
+        yf = y.float().reshape(-1, cout)
+        report("  stats sum", st[:, 0].sum(0), yf.sum(0), 1e-4)
+        report("  stats sumsq", st[:, 1].sum(0), (yf * yf).sum(0), 1e-4)
+    return x, wt, ref
+
+
+@pytest.mark.parametrize("b,n,k", [(128, 64, 64), (128, 128, 64), (256, 128, 256), (100, 200, 128), (256, 2688, 5376)])
+def test_linear_fprop(C, b, n, k):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = bf16(torch.randn(b, k, device="cuda", generator=g))
+    w = bf16(torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k))
+    bias = torch.randn(n, device="cuda", generator=g)
+    ref = (x.float() @ w.float().t() + bias).relu()
+    ws_bytes = C.lib().qt_linear_workspace_bytes(b, n, k)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    out = torch.full((b, n), float("nan"), device="cuda")
+    run(C, C.lib().qt_linear_fprop(C.ptr(x), k, C.ptr(w), C.ptr(bias), C.ptr(out), n,
+                                   C.QT_EPI_BIAS | C.QT_EPI_RELU | C.QT_EPI_OUT_F32, b, n, k, C.ptr(ws), ws_bytes,
+                                   C.stream()), "linear_fprop")
+    report(f"linear_fprop f32 {b}x{n}x{k}", out, ref, F32_REL_L2)
+    out16 = torch.full((b, n), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_linear_fprop(C.ptr(x), k, C.ptr(w), C.ptr(bias), C.ptr(out16), n, C.QT_EPI_BIAS | C.QT_EPI_RELU,
+                                   b, n, k, C.ptr(ws), ws_bytes, C.stream()), "linear_fprop bf16")
+    report(f"linear_fprop bf16 {b}x{n}x{k}", out16, ref, BF16_REL_L2, True)
+
+
+@pytest.mark.parametrize("b,n,k", [(128, 64, 128), (256, 2688, 5376), (96, 200, 256)])
+def test_linear_dgrad_wgrad(C, b, n, k):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = bf16(torch.randn(b, k, device="cuda", generator=g))
+    w = torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k)
+    dy = bf16(torch.randn(b, n, device="cuda", generator=g))
+    wt = torch.empty(k, n, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_dgrad(C.ptr(w), C.ptr(wt), n, k, 1, C.stream()), "wpack_dgrad")
+    assert torch.equal(wt, bf16(w).t().contiguous()), "wpack_dgrad layout"
+    ws_bytes = C.lib().qt_linear_workspace_bytes(b, n, k)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    dx = torch.full((b, k), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_linear_dgrad(C.ptr(dy), n, C.ptr(wt), C.ptr(dx), k, b, n, k, C.ptr(ws), ws_bytes, C.stream()),
+        "linear_dgrad")
+    report(f"linear_dgrad {b}x{n}x{k}", dx, dy.float() @ bf16(w).float(), BF16_REL_L2, True)
+    dw = torch.full((n, k), float("nan"), device="cuda")
+    run(C, C.lib().qt_linear_wgrad(C.ptr(x), k, C.ptr(dy), n, C.ptr(dw), 0, b, n, k, C.ptr(ws), ws_bytes, C.stream()),
+        "linear_wgrad")
+    report(f"linear_wgrad {b}x{n}x{k}", dw, dy.float().t() @ x.float(), F32_REL_L2)
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,k,stride,pad", [
+    (2, 64, 64, 8, 8, 3, 1, 1),
+    (3, 64, 64, 56, 56, 3, 1, 1),
+    (4, 64, 128, 28, 28, 3, 2, 1),
+    (4, 64, 128, 28, 28, 1, 2, 0),
+    (5, 128, 128, 14, 14, 3, 1, 1),
+    (8, 256, 512, 14, 14, 3, 2, 1),
+    (6, 512, 512, 7, 7, 3, 1, 1),
+    (2, 32, 64, 9, 11, 3, 1, 1),
+])
+def test_conv_fprop(C, n, cin, cout, h, w, k, stride, pad):
+    conv_case(C, n, cin, cout, h, w, k, stride, pad, stats=True)
+
+
+def test_conv_fprop_bias_relu(C):
+    conv_case(C, 4, 256, 128, 7, 7, 3, 1, 1, bias=True, relu=True)
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w,k,stride,pad", [
+    (2, 64, 64, 8, 8, 3, 1, 1),
+    (3, 64, 64, 30, 30, 3, 1, 1),
+    (4, 64, 128, 28, 28, 3, 2, 1),
+    (4, 64, 128, 28, 28, 1, 2, 0),
+    (6, 512, 512, 7, 7, 3, 1, 1),
+    (5, 256, 128, 7, 7, 3, 1, 1),
+])
+def test_conv_dgrad_wgrad(C, n, cin, cout, h, w, k, stride, pad):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = bf16(torch.randn(n, cin, h, w, device="cuda", generator=g)).float().requires_grad_(True)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+    wq = bf16(wt).float().requires_grad_(True)
+    y = F.conv2d(x, wq, None, stride=stride, padding=pad)
+    dy = bf16(torch.randn_like(y))
+    y.backward(dy.float())
+    ho, wo = y.shape[2], y.shape[3]
+    d = C.conv_desc(n, (1, h, w), cin, cout, (1, k, k), (1, stride, stride), (0, pad, pad))
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
+    x_nhwc = nhwc(x.detach())
+    wd = torch.empty(cin, k * k, cout, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_dgrad(C.ptr(wt.contiguous()), C.ptr(wd), cout, cin, k * k, C.stream()), "wpack_dgrad")
+    assert torch.equal(wd, bf16(wt).permute(1, 2, 3, 0).reshape(cin, k * k, cout)), "wpack_dgrad layout"
+    # dgrad (fresh) and dgrad accumulated onto an existing gradient
+    dx = torch.zeros(n, h, w, cin, device="cuda", dtype=torch.bfloat16)
+    acc = 1 if (stride > 1 and k == 1) else 0
+    run(C, C.lib().qt_conv_dgrad(d, C.ptr(dy_nhwc), C.ptr(wd), C.ptr(dx), acc, C.stream()), "conv_dgrad")
+    report(f"conv_dgrad c{cin}->{cout} {h}x{w} k{k} s{stride}", dx.permute(0, 3, 1, 2), x.grad, BF16_REL_L2, True)
+    base = bf16(torch.randn(n, h, w, cin, device="cuda", generator=g))
+    dx2 = base.clone()
+    run(C, C.lib().qt_conv_dgrad(d, C.ptr(dy_nhwc), C.ptr(wd), C.ptr(dx2), 1, C.stream()), "conv_dgrad accumulate")
+    report("  conv_dgrad accumulate", dx2.permute(0, 3, 1, 2), x.grad + base.float().permute(0, 3, 1, 2), 6e-3)
+    # wgrad
+    ws_bytes = C.lib().qt_conv_wgrad_workspace_bytes(d)
+    ws = torch.empty(max(ws_bytes, 16), device="cuda", dtype=torch.uint8)
+    dw = torch.full((cout, cin, k, k), float("nan"), device="cuda")
+    run(C, C.lib().qt_conv_wgrad(d, C.ptr(x_nhwc), C.ptr(dy_nhwc), C.ptr(dw), 0, C.ptr(ws), ws_bytes, C.stream()),
+        "conv_wgrad")
+    report(f"conv_wgrad c{cin}->{cout} {h}x{w} k{k} s{stride}", dw, wq.grad, F32_REL_L2)
+
+
+def test_quadrant_conv_groups(C):
+    """The four quadrant views of a 14x14 map as one grouped launch (zero halo at the internal seams)."""
+    n, cin, cout = 3, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(4)
+    base = bf16(torch.randn(n, cin, 14, 14, device="cuda", generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9)
+    b = torch.randn(cout, device="cuda", generator=g)
+    quads = [base[:, :, :7, :7], base[:, :, :7, 7:], base[:, :, 7:, :7], base[:, :, 7:, 7:]]
+    ref = torch.stack([F.conv2d(q.float(), bf16(wt).float(), b, padding=1).relu() for q in quads])  # [4,n,cout,7,7]
+    x_nhwc = base.permute(0, 2, 3, 1).contiguous()
+    wf = torch.empty(cout, 9, cin, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_fprop(C.ptr(wt), C.ptr(wf), cout, cin, 9, C.stream()), "wpack")
+    xs = (14 * 14 * cin, 0, 14 * cin, cin)
+    xoff = (0, 7 * cin, 7 * 14 * cin, 7 * 14 * cin + 7 * cin)
+    yoff = tuple(q * n * 49 * cout for q in range(4))
+    d = C.conv_desc(n, (1, 7, 7), cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1), x_stride=xs, groups=4, x_group_off=xoff,
+                    y_group_off=yoff)
+    y = torch.full((4, n, 7, 7, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_conv_fprop(d, C.ptr(x_nhwc), C.ptr(wf), C.ptr(y), C.ptr(b), None,
+                                 C.QT_EPI_BIAS | C.QT_EPI_RELU, None, 0, C.stream()), "quadrant conv")
+    report("quadrant conv fprop", y.permute(0, 1, 4, 2, 3), ref, BF16_REL_L2, True)
+
+
+def test_stem(C):
+    n, h, w, cout = 3, 64, 96, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n, 3, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, 3, 7, 7, device="cuda", generator=g) / math.sqrt(147)
+    xq = bf16(x).float().requires_grad_(True)
+    wq = bf16(wt).float().requires_grad_(True)
+    ref = F.conv2d(xq, wq, None, stride=2, padding=3)
+    xp = torch.empty(n, h + 7, w + 8, 4, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_stem_pack_input(C.ptr(x), C.ptr(xp), n, 3, h, w, C.stream()), "stem_pack_input")
+    w8 = torch.empty(cout, 8, 32, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_stem(C.ptr(wt), C.ptr(w8), cout, 3, 7, 7, C.stream()), "wpack_stem")
+    y = torch.full((n, h // 2, w // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rows = C.lib().qt_stem_stat_rows(n, h, w)
+    st = torch.zeros(rows, 2, cout, device="cuda")
+    run(C, C.lib().qt_stem_fprop(C.ptr(xp), C.ptr(w8), C.ptr(y), C.ptr(st), n, h, w, cout, C.stream()), "stem_fprop")
+    report("stem fprop", y.permute(0, 3, 1, 2), ref, BF16_REL_L2, True)
+    report("  stem stats", st[:, 0].sum(0), y.float().reshape(-1, cout).sum(0), 1e-4)
+    dy = bf16(torch.randn_like(ref))
+    ref.backward(dy.float())
+    ws_bytes = C.lib().qt_stem_wgrad_workspace_bytes(n, h, w, cout)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    dw = torch.full((cout, 3, 7, 7), float("nan"), device="cuda")
+    run(C, C.lib().qt_stem_wgrad(C.ptr(xp), C.ptr(dy.permute(0, 2, 3, 1).contiguous()), C.ptr(dw), 0, n, h, w, cout, 3,
+                                 C.ptr(ws), ws_bytes, C.stream()), "stem_wgrad")
+    report("stem wgrad", dw, wq.grad, F32_REL_L2)
+
+
+@pytest.mark.parametrize("m,c,residual,relu", [(1000, 64, False, True), (4096, 256, True, True), (300, 512, True, False)])
+def test_batchnorm_train(C, m, c, residual, relu):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    y = bf16(torch.randn(m, c, device="cuda", generator=g) * 2 + 0.5)
+    res = bf16(torch.randn(m, c, device="cuda", generator=g)) if residual else None
+    gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+    beta = torch.randn(c, device="cuda", generator=g)
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    # reference
+    yf = y.float().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    z = F.batch_norm(yf, rm_ref, rv_ref, gamma.clone().requires_grad_(True), beta, True, 0.1, 1e-5)
+    gref = gamma.clone().requires_grad_(True)
+    bref = beta.clone().requires_grad_(True)
+    z = F.batch_norm(yf, None, None, gref, bref, True, 0.1, 1e-5)
+    o = z + res.float() if residual else z
+    o = o.relu() if relu else o
+    dout = bf16(torch.randn(m, c, device="cuda", generator=g))
+    o.backward(dout.float())
+    # ours
+    rows = 37
+    partial = torch.zeros(rows, 2, c, device="cuda")
+    run(C, C.lib().qt_bn_stats(C.ptr(y), m, c, C.ptr(partial), rows, C.stream()), "bn_stats")
+    ws_bytes = C.lib().qt_bn_workspace_bytes(c)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    mean, invstd, scale, shift = (torch.empty(c, device="cuda") for _ in range(4))
+    run(C, C.lib().qt_bn_finalize(C.ptr(partial), rows, c, float(m), C.ptr(gamma), C.ptr(beta), 1e-5, 0.1, C.ptr(rm),
+                                  C.ptr(rv), C.ptr(mean), C.ptr(invstd), C.ptr(scale), C.ptr(shift), C.ptr(ws), ws_bytes,
+                                  C.stream()), "bn_finalize")
+    report("bn mean", mean, y.float().mean(0), 1e-5)
+    report("bn invstd", invstd, 1.0 / torch.sqrt(y.float().var(0, unbiased=False) + 1e-5), 1e-5)
+    report("bn running_mean", rm, rm_ref, 1e-5)
+    report("bn running_var", rv, rv_ref, 1e-5)
+    out = torch.empty_like(y)
+    run(C, C.lib().qt_bn_apply(C.ptr(y), C.ptr(scale), C.ptr(shift), C.ptr(res), C.ptr(out), m, c, int(relu), C.stream()),
+        "bn_apply")
+    report("bn apply", out, o.detach(), BF16_REL_L2, True)
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    dy = torch.empty_like(y)
+    dz = torch.empty_like(y)
+    act = out if relu else None
+    run(C, C.lib().qt_bn_backward(C.ptr(dout), C.ptr(act), C.ptr(y), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), m, c,
+                                  C.ptr(dgamma), C.ptr(dbeta), 0, C.ptr(dy), C.ptr(dz), C.ptr(ws), ws_bytes, C.stream()),
+        "bn_backward")
+    # the reference mask comes from fp32 activations; ours from the bf16-rounded ones -> compare loosely on dy
+    report("bn dgamma", dgamma, gref.grad, 2e-2)
+    report("bn dbeta", dbeta, bref.grad, 2e-2)
+    report("bn dy", dy, yf.grad, 2e-2)
+
+
+def test_maxpool_3x3s2(C):
+    n, h, w, c = 3, 20, 24, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = bf16(torch.randn(n, c, h, w, device="cuda", generator=g)).relu()  # many exact ties at 0, like after ReLU
+    xf = x.float().requires_grad_(True)
+    ref, idx = F.max_pool2d(xf, 3, 2, 1, return_indices=True)
+    ho, wo = ref.shape[2], ref.shape[3]
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.bfloat16)
+    am = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.int8)
+    run(C, C.lib().qt_maxpool2d_fwd(C.ptr(x_nhwc), C.ptr(out), C.ptr(am), n, h, w, c, 3, 2, 1, C.stream()), "maxpool fwd")
+    assert torch.equal(out.permute(0, 3, 1, 2).float(), ref.detach()), "maxpool values must be bit-exact"
+    # argmax: decode window code -> flat input index, must equal ATen's indices
+    amn = am.permute(0, 3, 1, 2).long()
+    hh = torch.arange(ho, device="cuda").view(1, 1, -1, 1) * 2 - 1 + amn // 3
+    ww = torch.arange(wo, device="cuda").view(1, 1, 1, -1) * 2 - 1 + amn % 3
+    assert torch.equal(hh * w + ww, idx), "maxpool argmax must match ATen's first-maximum rule"
+    dout = bf16(torch.randn_like(ref))
+    ref.backward(dout.float())
+    dx = torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_maxpool2d_bwd(C.ptr(dout.permute(0, 2, 3, 1).contiguous()), C.ptr(am), C.ptr(dx), n, h, w, c, 3, 2,
+                                    1, C.stream()), "maxpool bwd")
+    report("maxpool bwd", dx.permute(0, 3, 1, 2), xf.grad, BF16_REL_L2)
+
+
+def test_quadtree_pool(C):
+    b, cq, cg = 5, 128, 512
+    g = torch.Generator(device="cuda").manual_seed(8)
+    q = bf16(torch.randn(4, b, cq, 7, 7, device="cuda", generator=g)).relu()
+    l4 = bf16(torch.randn(b, cg, 7, 7, device="cuda", generator=g)).relu()
+    qf = q.float().requires_grad_(True)
+    lf = l4.float().requires_grad_(True)
+    parts = [F.adaptive_avg_pool2d(lf, 1).flatten(1)] + [F.max_pool2d(qf[i], 2, 2).flatten(1) for i in range(4)]
+    ref = torch.cat(parts, dim=1)  # [b, 5120] exactly as models.py:291-294
+    ldf = 5376
+    feat = torch.zeros(b, ldf, device="cuda", dtype=torch.bfloat16)
+    q_nhwc = q.permute(0, 1, 3, 4, 2).contiguous()
+    l_nhwc = l4.permute(0, 2, 3, 1).contiguous()
+    run(C, C.lib().qt_quadtree_pool_fwd(C.ptr(q_nhwc), C.ptr(l_nhwc), C.ptr(feat), b, 7, 7, cq, 49, cg, ldf, C.stream()),
+        "quadtree_pool_fwd")
+    assert torch.equal(feat[:, 512:5120].float(), ref[:, 512:].detach()), "quadrant max-pool / flatten order must be bit-exact"
+    report("quadtree global avg", feat[:, :512], ref[:, :512], BF16_REL_L2, True)
+    assert float(feat[:, 5120:].abs().max()) == 0.0
+    dfeat = bf16(torch.randn(b, ldf, device="cuda", generator=g))
+    ref.backward(dfeat[:, :5120].float())
+    dq = torch.empty_like(q_nhwc)
+    dl = torch.empty_like(l_nhwc)
+    run(C, C.lib().qt_quadtree_pool_bwd(C.ptr(dfeat), C.ptr(q_nhwc), C.ptr(dq), C.ptr(dl), b, 7, 7, cq, 49, cg, ldf,
+                                        C.stream()), "quadtree_pool_bwd")
+    # reference gradient w.r.t. the post-ReLU map, then the ReLU mask (q > 0) our kernel fuses
+    ref_dq = qf.grad * (q.float() > 0)
+    assert torch.equal(dq.permute(0, 1, 4, 2, 3).float(), ref_dq), "quadrant gradient routing must be bit-exact"
+    report("quadtree dl4", dl.permute(0, 3, 1, 2), lf.grad, BF16_REL_L2, True)
+
+
+def test_small_linears(C):
+    b, k, n = 33, 47, 94
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(b, k, device="cuda", generator=g) * 180
+    w = (torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k)).requires_grad_(True)
+    bias = torch.randn(n, device="cuda", generator=g).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.linear(xr, w, bias).relu()
+    out = torch.empty(b, n, device="cuda")
+    out16 = torch.empty(b, n, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_small_linear_fwd(C.ptr(x), 0, k, C.ptr(w), C.ptr(bias), b, n, k, 1, 0.0, 0, C.ptr(out), n,
+                                       C.ptr(out16), n, C.stream()), "small_linear_fwd")
+    report("small_linear fwd", out, ref, 1e-5)
+    dy = torch.randn(b, n, device="cuda", generator=g)
+    ref.backward(dy)
+    # dz through the ReLU using the stored output, then dW/db/dx
+    dz = torch.empty(b, n, device="cuda")
+    eye = torch.eye(n, device="cuda")
+    run(C, C.lib().qt_small_linear_bwd_dx(C.ptr(dy), 0, n, C.ptr(eye), b, n, n, C.ptr(out), n, 0.0, 0, C.ptr(dz), n, None,
+                                          0, C.stream()), "relu mask via bwd_dx")
+    dw = torch.empty(n, k, device="cuda")
+    db = torch.empty(n, device="cuda")
+    run(C, C.lib().qt_small_linear_bwd_dw(C.ptr(dz), 0, n, C.ptr(x), 0, k, b, n, k, C.ptr(dw), C.ptr(db), 0, C.stream()),
+        "small_linear_bwd_dw")
+    report("small_linear dw", dw, w.grad, 1e-5)
+    report("small_linear db", db, bias.grad, 1e-5)
+    dx = torch.empty(b, k, device="cuda")
+    run(C, C.lib().qt_small_linear_bwd_dx(C.ptr(dz), 0, n, C.ptr(w), b, n, k, None, 0, 0.0, 0, C.ptr(dx), k, None, 0,
+                                          C.stream()), "small_linear_bwd_dx")
+    report("small_linear dx", dx, xr.grad, 1e-5)
+
+
+def test_dropout_statistics(C):
+    n = 1 << 20
+    h = torch.ones(n, device="cuda")
+    h16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_relu_dropout(C.ptr(h), C.ptr(h16), n, 0.5, 1234, 1, C.stream()), "relu_dropout")
+    keep = float((h > 0).float().mean())
+    assert abs(keep - 0.5) < 5e-3, keep
+    assert set(h.unique().tolist()) == {0.0, 2.0}
+    h2 = torch.ones(n, device="cuda")
+    run(C, C.lib().qt_relu_dropout(C.ptr(h2), None, n, 0.5, 1234, 1, C.stream()), "relu_dropout again")
+    assert torch.equal(h, h2), "same seed -> same mask (backward regenerates it)"
+
+
+def test_region_avgpool_and_misc(C):
+    r, p, c = 40, 49, 64
+    g = torch.Generator(device="cuda").manual_seed(10)
+    x = bf16(torch.randn(r, p, c, device="cuda", generator=g)).relu()
+    out = torch.empty(r, c, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_region_avgpool_fwd(C.ptr(x), C.ptr(out), r, p, c, c, C.stream()), "region_avgpool_fwd")
+    report("region avgpool", out, x.float().mean(1), BF16_REL_L2, True)
+    dout = bf16(torch.randn(r, c, device="cuda", generator=g))
+    dx = torch.empty_like(x)
+    run(C, C.lib().qt_region_avgpool_bwd(C.ptr(dout), C.ptr(x), C.ptr(dx), r, p, c, c, 1, C.stream()), "region_avgpool_bwd")
+    report("region avgpool bwd", dx, (dout.float() / p).unsqueeze(1) * (x.float() > 0), BF16_REL_L2, True)
+    # colsum / add / relu_backward
+    ws_bytes = C.lib().qt_bn_workspace_bytes(c)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    cs = torch.empty(c, device="cuda")
+    x2 = x.reshape(-1, c)
+    run(C, C.lib().qt_colsum(C.ptr(x2), x2.shape[0], c, C.ptr(cs), 0, C.ptr(ws), ws_bytes, C.stream()), "colsum")
+    report("colsum", cs, x2.float().sum(0), 1e-5)
+    a, b2 = bf16(torch.randn(4096, device="cuda", generator=g)), bf16(torch.randn(4096, device="cuda", generator=g))
+    o = torch.empty_like(a)
+    run(C, C.lib().qt_add_bf16(C.ptr(a), C.ptr(b2), C.ptr(o), 4096, C.stream()), "add")
+    assert torch.equal(o, bf16(a.float() + b2.float()))
+    run(C, C.lib().qt_relu_backward(C.ptr(a), C.ptr(b2), C.ptr(o), 4096, C.stream()), "relu_backward")
+    assert torch.equal(o, torch.where(b2.float() > 0, a, torch.zeros_like(a)))
