@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench.py — QuadtreeCNN train images/s @224^2, per-GPU batch 256, bf16 tensor-core compute (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step = forward + CrossEntropyLoss + backward + Adam over one synthetic batch (SURVEY.md §8d recipe), i.e. the
+hot loop of the reference's `Quadtree_from scratch/Quadtree_train.py:60-66`.
+  value : whole-job images/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same step through the public module API with HOST (pinned) inputs: H2D copies of images /
+          pose vectors / labels and the D2H read of the loss are inside the timed region
+  roofline : dominant kernel family = tcgen05 implicit-GEMM convolutions (tensor bound); per-launch CUDA-event
+          times in a second, event-instrumented pass; achieved = algorithmic conv FLOPs / summed launch time
+  cpu_baseline : the oracle port of the reference's CPU path (fp32, torch CPU) timed on this box's host cores
+`--impl reference` times that same CPU port as the reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "QuadtreeCNN train images/sec @224^2 bs256 bf16"
+UNIT = "images/s"
+TRAIN_GFLOP_PER_IMG = 11.08  # BASELINE.md §3 (fwd + dgrad + wgrad)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (sustained)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(batch, steps, warmup):
+    """The reference's CPU path (oracle port: fp32 torch CPU, fwd + CE + bwd + Adam), images/s."""
+    import torch
+    from oracle import quadtree_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = O.make_params("quadtree", 8, seed=0)
+    images, numerical, labels = O.synthetic_batch(batch, 1234)
+    state = None
+    for _ in range(warmup):
+        _, state = O.train_step_cpu("quadtree", p, (images, numerical), labels, state=state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, state = O.train_step_cpu("quadtree", p, (images, numerical), labels, state=state)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    rate, spi, threads = cpu_reference_rate(args.cpu_batch, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": spi * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"QuadtreeCNN level-1 fwd+bwd+Adam 224x224 batch {args.cpu_batch} on CPU (reference path, oracle port)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of batch {args.cpu_batch} after {warmup} warm-up"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import quadtree_oracle as O  # synthetic-input recipe + cpu_baseline only
+    from qtcnn_b200 import models as M
+    from qtcnn_b200 import ops, parallel
+
+    B = args.batch
+    torch.manual_seed(0)
+    model = M.QuadtreeCNN(num_classes=8).to(dev).train()  # dropout 0.5 active, as in the reference script
+    dp = parallel.DataParallelGrads(model) if world > 1 else None
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-4, fused=True)
+    images_h, numerical_h, labels_h = O.synthetic_batch(B, 1234 + rank)
+    images_h, numerical_h, labels_h = images_h.pin_memory(), numerical_h.pin_memory(), labels_h.pin_memory()
+    images, numerical, labels = images_h.to(dev), numerical_h.to(dev), labels_h.to(dev)
+
+    def step(x, nf, y):
+        opt.zero_grad(set_to_none=True)
+        logits = model(x, nf)
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        if dp is not None:
+            dp.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step(images, numerical, labels)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = ops.launches()
+    ms = timed(lambda: step(images, numerical, labels), args.steps)
+    launches = ops.launches() - n0
+    clocks = sampler.stop() if sampler else None
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # end to end: host (pinned) inputs, H2D inside the timed region, loss read back every step
+    def e2e_step():
+        x = images_h.to(dev, non_blocking=True)
+        nf = numerical_h.to(dev, non_blocking=True)
+        y = labels_h.to(dev, non_blocking=True)
+        return float(step(x, nf, y))
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = images_h.numel() * 4 + numerical_h.numel() * 4 + labels_h.numel() * 8
+
+    roofline = None
+    if not args.no_roofline and rank == 0:
+        ops.profile_begin()
+        for _ in range(min(3, args.steps)):
+            step(images, numerical, labels)
+        torch.cuda.synchronize()
+        prof = ops.profile_end()
+        peaks = load_peaks()
+        gemm = {k: v for k, v in prof.items() if v["flops"] > 0}
+        flops = sum(v["flops"] for v in gemm.values())
+        tms = sum(v["ms"] for v in gemm.values())
+        nlaunch = sum(v["n"] for v in gemm.values())
+        ach = flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                    "traffic": None, "peak_source": peaks["src"], "kernel": "igemm_{kmajor,wgrad}_kernel (all conv/linear GEMM launches)",
+                    "gemm_launches_per_step": nlaunch / min(3, args.steps),
+                    "gemm_ms_per_step": tms / min(3, args.steps), "step_share": (tms / min(3, args.steps)) / (ms / args.steps),
+                    "per_family": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / min(3, args.steps)}
+                                   for k, v in gemm.items() if v["ms"] > 0}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, spi, threads = cpu_reference_rate(args.cpu_batch, 4, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"4 steps of batch {args.cpu_batch} (fwd+bwd+Adam, fp32) after 1 warm-up, {spi:.2f} s/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"QuadtreeCNN level-1 (ResNet-18 + 2x2 quadtree + 47 pose features) fwd+bwd+Adam, 224x224, "
+                                   f"per-GPU batch {B}, dropout 0.5", "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step activations+grads (~3 GB) exceed the 126 MB L2, no explicit flush",
+                       "optimizer": "torch.optim.Adam(fused=True), lr 1e-4, wd 1e-4"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -105,15 +105,18 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                    float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
                    qt_stream_t stream);
+/* eval mode: coefficients from the running statistics (mean/invstd are also returned for the backward). */
 int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
-                      const float* running_var, float eps, float* scale, float* shift, qt_stream_t stream);
+                      const float* running_var, float eps, float* mean, float* invstd, float* scale, float* shift,
+                      qt_stream_t stream);
 int qt_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* out, long long m,
                 int c, int relu, qt_stream_t stream);
 /* native_batch_norm_backward fused with the ReLU mask: dz = dout*(act>0) when act != NULL;
- * dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optionally stores dz (identity-branch gradient). */
+ * dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optionally stores dz (identity-branch gradient).
+ * eval_mode != 0: statistics were constants (model.eval(), e.g. Grad-CAM), dy = gamma*invstd*dz. */
 int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
-                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, void* dy,
-                   void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream);
+                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, int eval_mode,
+                   void* dy, void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream);
 int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream);
 int qt_colsum(const void* x, long long m, int c, float* out, int accumulate, void* ws, size_t ws_bytes,
               qt_stream_t stream);

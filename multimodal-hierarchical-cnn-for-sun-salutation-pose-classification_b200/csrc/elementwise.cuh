@@ -201,10 +201,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C
 // Eval mode: scale/shift from running statistics.
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
-                                      float eps, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+                                      float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                      float* __restrict__ scale_out, float* __restrict__ shift_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float invstd = rsqrtf(running_var[c] + eps);
+  const float invstd = 1.0f / sqrtf(running_var[c] + eps);
+  if (mean_out) mean_out[c] = running_mean[c];
+  if (invstd_out) invstd_out[c] = invstd;
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   scale_out[c] = g * invstd;
   shift_out[c] = b - running_mean[c] * g * invstd;
@@ -310,7 +313,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
 // per-channel coefficients used by pass 2: c1 = sum_dz / M, c2 = sum_dz_xhat / M.
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int S, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                       float* __restrict__ c1, float* __restrict__ c2) {
+                                       int eval_mode, float* __restrict__ c1, float* __restrict__ c2) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
@@ -320,8 +323,9 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int S, i
   }
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s1) : static_cast<float>(s1);
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(s2) : static_cast<float>(s2);
-  c1[c] = static_cast<float>(s1 / count);
-  c2[c] = static_cast<float>(s2 / count);
+  // eval mode: statistics are constants, so the two batch-coupling terms vanish
+  c1[c] = eval_mode ? 0.f : static_cast<float>(s1 / count);
+  c2[c] = eval_mode ? 0.f : static_cast<float>(s2 / count);
 }
 // Pass 2: dy = gamma*invstd * (dz - c1 - xhat*c2); optionally also writes dz (gradient of the
 // residual/identity branch).
@@ -367,28 +371,32 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __
   }
 }
 
-// Column sums of a dense bf16 [M][C] tensor -> partial[blocks][C] (bias gradients).
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, float* __restrict__ partial) {
+// Column sums of a dense bf16 [M][C] tensor -> partial[blocks][C] (bias gradients). blockIdx.y walks
+// channel chunks of Cc <= 2048 channels so any C % 8 == 0 is supported.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int Cc,
+                                   float* __restrict__ partial) {
   extern __shared__ float sm[];
-  const int groups = C / 8;
+  const int cbeg = blockIdx.y * Cc;
+  const int cw = min(Cc, C - cbeg);
+  const int groups = cw / 8;
   const int lanes = blockDim.x / groups;
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   float s1[8] = {0};
   if (rl < lanes) {
     for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
       float f[8];
-      unpack8(ld_nc16(x + r * C + cg * 8), f);
+      unpack8(ld_nc16(x + r * C + cbeg + cg * 8), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s1[e] += f[e];
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sm[rl * C + cg * 8 + e] = s1[e];
+    for (int e = 0; e < 8; ++e) sm[rl * cw + cg * 8 + e] = s1[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
     float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += sm[l * C + i];
-    partial[static_cast<long long>(blockIdx.x) * C + i] = acc;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * cw + i];
+    partial[static_cast<long long>(blockIdx.x) * C + cbeg + i] = acc;
   }
 }
 __global__ void colreduce_final_f32_kernel(const double* __restrict__ sums, int S, int K, float* __restrict__ out,

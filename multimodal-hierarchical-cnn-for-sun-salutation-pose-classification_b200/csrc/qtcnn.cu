@@ -512,8 +512,10 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
   return cuda_status("bn_finalize");
 }
 int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
-                      const float* running_var, float eps, float* scale, float* shift, qt_stream_t stream) {
-  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(c, gamma, beta, running_mean, running_var, eps, scale, shift);
+                      const float* running_var, float eps, float* mean, float* invstd, float* scale, float* shift,
+                      qt_stream_t stream) {
+  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(c, gamma, beta, running_mean, running_var, eps, mean, invstd,
+                                                                 scale, shift);
   return cuda_status("bn_eval_coeffs");
 }
 int qt_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* out, long long m,
@@ -526,8 +528,8 @@ int qt_bn_apply(const void* y, const float* scale, const float* shift, const voi
   return cuda_status("bn_apply");
 }
 int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
-                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, void* dy,
-                   void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream) {
+                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, int eval_mode,
+                   void* dy, void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_backward: c must be a multiple of 8 and <= 2048");
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_backward: workspace too small");
   double* sums = static_cast<double*>(ws);
@@ -545,7 +547,7 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
   int slices = 0;
   if (int rc = reduce_partials(partial, blocks, 2 * c, sums, &slices, S(stream))) return rc;
   bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, static_cast<double>(m), dgamma, dbeta,
-                                                                  accumulate, c1, c2);
+                                                                  accumulate, eval_mode, c1, c2);
   if (int rc = cuda_status("bn_bwd_finalize")) return rc;
   const long long total8 = m * c / 8;
   bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(
@@ -563,16 +565,25 @@ int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, q
 }
 int qt_colsum(const void* x, long long m, int c, float* out, int accumulate, void* ws, size_t ws_bytes,
               qt_stream_t stream) {
-  if (c % 8 || c > 2048) return fail("colsum: c must be a multiple of 8 and <= 2048");
+  if (c % 8) return fail("colsum: c must be a multiple of 8");
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("colsum: workspace too small");
   double* sums = static_cast<double*>(ws);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
-  const int block = rowlane_block(c);
-  const int lanes = block / (c / 8);
+  // channel chunks of at most 1024 channels (128 groups) -> at least 2 row lanes per block
+  int chunks = (c + 1023) / 1024;
+  int cc = ((c / 8 + chunks - 1) / chunks) * 8;
+  chunks = (c + cc - 1) / cc;
+  const int groups_max = cc / 8;
+  int lanes = 256 / groups_max;
+  if (lanes < 1) lanes = 1;
+  // block size must be a multiple of every chunk's group count: use the widest chunk and let the (narrower)
+  // last chunk recompute its own lanes from blockDim
+  const int block = groups_max * lanes;
   long long want = (m + lanes - 1) / lanes;
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
-  colsum_bf16_kernel<<<blocks, block, static_cast<size_t>(lanes) * c * sizeof(float), S(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), m, c, partial);
+  dim3 grid(blocks, chunks);
+  colsum_bf16_kernel<<<grid, block, static_cast<size_t>(block / 1) * 8 * sizeof(float) + 64, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), m, c, cc, partial);
   if (int rc = cuda_status("colsum")) return rc;
   int slices = 0;
   if (int rc = reduce_partials(partial, blocks, c, sums, &slices, S(stream))) return rc;

@@ -1,0 +1,500 @@
+"""Host-side mirror of the reference's `models.py` interface, executing on the sm_100a kernels of libqtcnn.
+
+Same class names, constructor signatures, `forward(image_input, numerical_input) -> fp32 logits`, module tree
+and `state_dict` keys as the reference, so these classes drop into its training / Grad-CAM scripts:
+
+  QuadtreeCNN                 Quadtree_from scratch/models.py:214-305, resnet/models.py:70-180 (mode=, frozen)
+  get_model                   Quadtree_from scratch/models.py:309-325 (and the resnet/ signature via get_model_resnet)
+
+The ResNet-18 container is torchvision's own module tree (what the reference instantiates), so parameter names,
+aliasing (`base_cnn.*` / `features_extractor.*` / `global_processor.*`) and hookability of `base_cnn.layer4`
+are identical; only the arithmetic is replaced: every BasicBlock, the stem and the fusion head run as
+`torch.autograd.Function`s that call the C ABI (bf16 channels-last activations, fp32 parameters/gradients).
+There is no cuDNN / ATen fallback for the hot ops: CPU tensors or a missing libqtcnn.so raise.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torchvision
+from torchvision.models.resnet import BasicBlock
+
+from . import capi, ops
+from .capi import check, ptr, stream
+from .ops import BF16, L
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: the B200 path has no CPU implementation (got a {t.device} tensor); "
+                           "move the model and inputs to a CUDA device")
+
+
+def _zeros_like_param(p):
+    return ops.grad_out(p)
+
+
+# =================================================================================================
+# Stem: conv1 7x7/s2 + bn1 + relu + maxpool 3x3/s2 (torchvision resnet.py:197-200)
+# =================================================================================================
+class _StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, conv_w, bn_w, bn_b, bn_mod, training):
+        _require_cuda(x, "stem")
+        n, c, h, w = x.shape
+        cout = conv_w.shape[0]
+        if conv_w.shape[1:] != (3, 7, 7) or c != 3:
+            raise RuntimeError("stem: expected a 3-channel 7x7 stride-2 convolution (ResNet-18 conv1)")
+        dev = x.device
+        xf = x.detach().float().contiguous()
+        xp = torch.empty(n, h + 7, w + 8, 4, device=dev, dtype=BF16)
+        check(L().qt_stem_pack_input(ptr(xf), ptr(xp), n, 3, h, w, stream()), "stem_pack_input")
+        w8 = ops.packed_stem(conv_w)
+        ho, wo = h // 2, w // 2
+        y = torch.empty(n, ho, wo, cout, device=dev, dtype=BF16)
+        stats = None
+        if training:
+            stats = torch.empty(L().qt_stem_stat_rows(n, h, w), 2, cout, device=dev, dtype=torch.float32)
+        with ops.gemm_scope("stem_fprop", 2.0 * n * ho * wo * 147 * cout):
+            check(L().qt_stem_fprop(ptr(xp), ptr(w8), ptr(y), ptr(stats), n, h, w, cout, stream()), "stem_fprop")
+        ops._count(2)
+        st = ops.bn_finalize(stats, n * ho * wo, bn_mod, cout, dev, training)
+        a = torch.empty_like(y)
+        ops.bn_apply(y, st, a, None, True)
+        po, qo = capi.out_size(ho, 3, 2, 1), capi.out_size(wo, 3, 2, 1)
+        out = torch.empty(n, po, qo, cout, device=dev, dtype=BF16)
+        need_bwd = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
+        am = torch.empty(n, po, qo, cout, device=dev, dtype=torch.int8) if need_bwd else None
+        check(L().qt_maxpool2d_fwd(ptr(a), ptr(out), ptr(am), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_fwd")
+        ops._count()
+        if need_bwd:
+            ctx.saved = (xp, y, a, am, st, conv_w, bn_w)
+            ctx.dims = (n, h, w, cout, ho, wo)
+            ctx.training = training
+        return ops.as_nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, y, a, am, st, conv_w, bn_w = ctx.saved
+        n, h, w, cout, ho, wo = ctx.dims
+        dev = y.device
+        dout = ops.as_nhwc(dout)
+        da = torch.empty_like(y)
+        check(L().qt_maxpool2d_bwd(ptr(dout), ptr(am), ptr(da), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_bwd")
+        ops._count()
+        dgamma = torch.empty(cout, device=dev)
+        dbeta = torch.empty(cout, device=dev)
+        dy = torch.empty_like(y)
+        ops.bn_backward(da, a, y, st, bn_w.detach(), dgamma, dbeta, dy, None, eval_mode=not ctx.training)
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _zeros_like_param(conv_w)
+            nbytes = L().qt_stem_wgrad_workspace_bytes(n, h, w, cout)
+            ws = ops.workspace(nbytes, dev)
+            with ops.gemm_scope("stem_wgrad", 2.0 * n * ho * wo * 147 * cout):
+                check(L().qt_stem_wgrad(ptr(xp), ptr(dy), ptr(dw), 0, n, h, w, cout, 3, ptr(ws), ws.numel(), stream()), "stem_wgrad")
+            ops._count(3)
+        return None, dw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None, None, None
+
+
+# =================================================================================================
+# BasicBlock (torchvision resnet.py:59-105): conv3x3-BN-ReLU-conv3x3-BN (+identity | 1x1 conv-BN) -ReLU
+# =================================================================================================
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, blk, training):
+        _require_cuda(x, "BasicBlock")
+        xb = ops.as_nhwc(x)
+        n, h, w, cin = xb.shape
+        cout = w1.shape[0]
+        stride = blk.conv1.stride[0]
+        dev = xb.device
+        d1 = ops.conv2d_desc(n, h, w, cin, cout, 3, stride, 1)
+        _, ho, wo = ops.conv_out_hw(d1)
+        d2 = ops.conv2d_desc(n, ho, wo, cout, cout, 3, 1, 1)
+        m = n * ho * wo
+        y1 = torch.empty(n, ho, wo, cout, device=dev, dtype=BF16)
+        s1 = ops.conv_fprop(d1, xb, ops.packed_fprop(w1), y1, want_stats=training)
+        st1 = ops.bn_finalize(s1, m, blk.bn1, cout, dev, training)
+        a1 = torch.empty_like(y1)
+        ops.bn_apply(y1, st1, a1, None, True)
+        y2 = torch.empty_like(y1)
+        s2 = ops.conv_fprop(d2, a1, ops.packed_fprop(w2), y2, want_stats=training)
+        st2 = ops.bn_finalize(s2, m, blk.bn2, cout, dev, training)
+        dd = yd = std = None
+        if wd is not None:
+            ds_conv = blk.downsample[0]
+            dd = ops.conv2d_desc(n, h, w, cin, cout, ds_conv.kernel_size[0], ds_conv.stride[0], ds_conv.padding[0])
+            yd = torch.empty_like(y1)
+            sd = ops.conv_fprop(dd, xb, ops.packed_fprop(wd), yd, want_stats=training)
+            std = ops.bn_finalize(sd, m, blk.downsample[1], cout, dev, training)
+            idn = torch.empty_like(y1)
+            ops.bn_apply(yd, std, idn, None, False)
+        else:
+            idn = xb
+        out = torch.empty_like(y1)
+        ops.bn_apply(y2, st2, out, idn, True)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd)
+            ctx.descs = (d1, d2, dd)
+            ctx.training = training
+        return ops.as_nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd = ctx.saved
+        d1, d2, dd = ctx.descs
+        ev = not ctx.training
+        dev = xb.device
+        cout = y1.shape[-1]
+        need = ctx.needs_input_grad
+        dout = ops.as_nhwc(dout)
+
+        def vec():
+            return torch.empty(cout, device=dev)
+
+        # bn2 + residual ReLU
+        dg2, db2 = vec(), vec()
+        dy2 = torch.empty_like(y2)
+        dz = torch.empty_like(y2)
+        ops.bn_backward(dout, out, y2, st2, g2.detach(), dg2, db2, dy2, dz, eval_mode=ev)
+        dw2 = None
+        if need[4]:
+            dw2 = _zeros_like_param(w2)
+            ops.conv_wgrad(d2, a1, dy2, dw2)
+        da1 = torch.empty_like(a1)
+        ops.conv_dgrad(d2, dy2, ops.packed_dgrad(w2), da1)
+        # bn1 + ReLU
+        dg1, db1 = vec(), vec()
+        dy1 = torch.empty_like(y1)
+        ops.bn_backward(da1, a1, y1, st1, g1.detach(), dg1, db1, dy1, None, eval_mode=ev)
+        dw1 = None
+        if need[1]:
+            dw1 = _zeros_like_param(w1)
+            ops.conv_wgrad(d1, xb, dy1, dw1)
+        dwd = dgd = dbd = None
+        dx = None
+        if wd is not None:
+            dgd, dbd = vec(), vec()
+            dyd = torch.empty_like(yd)
+            ops.bn_backward(dz, None, yd, std, gd.detach(), dgd, dbd, dyd, None, eval_mode=ev)
+            if need[7]:
+                dwd = _zeros_like_param(wd)
+                ops.conv_wgrad(dd, xb, dyd, dwd)
+            if need[0]:
+                dx = torch.empty_like(xb)
+                ops.conv_dgrad(d1, dy1, ops.packed_dgrad(w1), dx)
+                ops.conv_dgrad(dd, dyd, ops.packed_dgrad(wd), dx, accumulate=True)
+        elif need[0]:
+            dx = dz  # identity branch gradient; the main-branch dgrad accumulates onto it in place
+            ops.conv_dgrad(d1, dy1, ops.packed_dgrad(w1), dx, accumulate=True)
+        return (ops.as_nchw_view(dx) if dx is not None else None, dw1, dg1 if need[2] else None, db1 if need[3] else None,
+                dw2, dg2 if need[5] else None, db2 if need[6] else None, dwd, dgd if need[8] else None,
+                dbd if need[9] else None, None, None)
+
+
+class FusedBasicBlock(BasicBlock):
+    """torchvision BasicBlock whose forward runs on libqtcnn (same parameters / state_dict / hooks)."""
+
+    def forward(self, x):
+        ds = self.downsample
+        return _BlockFn.apply(x, self.conv1.weight, self.bn1.weight, self.bn1.bias, self.conv2.weight, self.bn2.weight,
+                              self.bn2.bias, ds[0].weight if ds is not None else None,
+                              ds[1].weight if ds is not None else None, ds[1].bias if ds is not None else None, self,
+                              self.training)
+
+
+class FusedFeatures(nn.Sequential):
+    """`nn.Sequential(conv1, bn1, relu, maxpool, layer1, ...)` of the reference (QS/models.py:222-230) with the
+    first four children executed as one fused stem. Children, indices and state_dict keys are unchanged."""
+
+    def forward(self, x):
+        mods = list(self.children())
+        conv1, bn1 = mods[0], mods[1]
+        out = _StemFn.apply(x, conv1.weight, bn1.weight, bn1.bias, bn1, bn1.training)
+        for m in mods[4:]:
+            out = m(out)
+        return out
+
+
+class _GlobalAvgPoolFn(torch.autograd.Function):
+    """AdaptiveAvgPool2d((1,1)) on a channels-last bf16 map (used when global_processor is called directly)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xb = ops.as_nhwc(x)
+        n, h, w, c = xb.shape
+        out = torch.empty(n, c, device=xb.device, dtype=BF16)
+        check(L().qt_region_avgpool_fwd(ptr(xb), ptr(out), n, h * w, c, c, stream()), "avgpool")
+        ops._count()
+        ctx.shape = (n, h, w, c)
+        return out.view(n, c, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, h, w, c = ctx.shape
+        d = dout.reshape(n, c).to(BF16).contiguous()
+        dx = torch.empty(n, h, w, c, device=d.device, dtype=BF16)
+        check(L().qt_region_avgpool_bwd(ptr(d), ptr(dx), ptr(dx), n, h * w, c, c, 0, stream()), "avgpool_bwd")
+        ops._count()
+        return ops.as_nchw_view(dx)
+
+
+class FusedAvgPool(nn.AdaptiveAvgPool2d):
+    def forward(self, x):
+        return _GlobalAvgPoolFn.apply(x)
+
+
+def make_resnet18() -> nn.Module:
+    """torchvision's ResNet-18 module tree (what the reference builds with `models.resnet18(...)`) with fused
+    blocks. ImageNet weights are used only if the checkpoint is already in the local torch hub cache — the
+    reference's `weights=IMAGENET1K_V1` needs a download that is impossible offline; otherwise torchvision's
+    default initialisation (resnet.py:208-213) applies and real weights arrive through `load_state_dict`."""
+    net = torchvision.models.resnet18(weights=None)
+    try:
+        url = torchvision.models.ResNet18_Weights.IMAGENET1K_V1.url
+        ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(url))
+        if os.path.exists(ckpt):
+            net.load_state_dict(torch.load(ckpt, map_location="cpu"))
+    except Exception:  # pragma: no cover - cache probing is best effort
+        pass
+    for m in net.modules():
+        if type(m) is BasicBlock:
+            m.__class__ = FusedBasicBlock
+    net.avgpool.__class__ = FusedAvgPool
+    return net
+
+
+# =================================================================================================
+# Fusion head of QuadtreeCNN: quadrant convs + quadtree pooling + numerical MLP + classifier
+# (QS/models.py:277-303; `mode` variants resnet/models.py:141-180)
+# =================================================================================================
+class _QuadHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base, l4, numerical, qw, qb, m0w, m0b, m3w, m3b, c0w, c0b, c3w, c3b, mode, p_drop, training):
+        use_img = mode in ("fusion", "image_only")
+        use_num = mode in ("fusion", "numerical_only")
+        dev = (base if use_img else numerical).device
+        _require_cuda(base if use_img else numerical, "QuadtreeCNN head")
+        p = float(p_drop) if training else 0.0
+        seed1, seed2 = (ops.new_seed(), ops.new_seed()) if p > 0 else (0, 0)
+        nimg = 5120 if use_img else 0
+        nnum = m3w.shape[0] if use_num else 0
+        ldf = nimg + nnum
+        if ldf != c0w.shape[1]:
+            raise RuntimeError(f"QuadtreeCNN head: classifier expects {c0w.shape[1]} features, built {ldf}")
+        q = bb = l4b = h1 = None
+        if use_img:
+            bb = ops.as_nhwc(base)
+            l4b = ops.as_nhwc(l4)
+            n, h, w, cin = bb.shape
+            cq = qw.shape[0]
+            if (h, w) != (14, 14) or l4b.shape[1:] != (7, 7, 512) or cq != 128:
+                raise RuntimeError("QuadtreeCNN expects 224x224 inputs (layer3 map 14x14), as the reference's "
+                                   "image_feature_dim == 5120 assert does")
+            dq = ops.quadrant_desc(n, h, w, cin, cq, 3, 1)
+            q = torch.empty(4, n, h // 2, w // 2, cq, device=dev, dtype=BF16)
+            ops.conv_fprop(dq, bb, ops.packed_fprop(qw), q, bias=qb.detach(), relu=True)
+        else:
+            n = numerical.shape[0]
+            dq = None
+        feat = torch.empty(n, ldf, device=dev, dtype=BF16)
+        if use_img:
+            check(L().qt_quadtree_pool_fwd(ptr(q), ptr(l4b), ptr(feat), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_fwd")
+            ops._count()
+        numf = None
+        if use_num:
+            numf = numerical.detach().float().contiguous()
+            k0 = numf.shape[1]
+            nh = m0w.shape[0]
+            h1 = torch.empty(n, nh, device=dev)
+            check(L().qt_small_linear_fwd(ptr(numf), 0, k0, ptr(m0w.detach()), ptr(m0b.detach()), n, nh, k0, 1, p, seed1, ptr(h1), nh,
+                                          None, 0, stream()), "numerical_mlp.0")
+            check(L().qt_small_linear_fwd(ptr(h1), 0, nh, ptr(m3w.detach()), ptr(m3b.detach()), n, nnum, nh, 0, 0.0, 0, None, 0,
+                                          feat.data_ptr() + 2 * nimg, ldf, stream()), "numerical_mlp.3")
+            ops._count(2)
+        # classifier.0 on the tensor cores, then ReLU + dropout, then classifier.3
+        nhid = c0w.shape[0]
+        hbuf = torch.empty(n, nhid, device=dev)
+        h16 = torch.empty(n, nhid, device=dev, dtype=BF16)
+        ws = ops.workspace(L().qt_linear_workspace_bytes(n, nhid, ldf), dev)
+        wf0 = ops.packed_fprop(c0w)
+        with ops.gemm_scope("linear_fprop", 2.0 * n * nhid * ldf):
+            check(L().qt_linear_fprop(ptr(feat), ldf, ptr(wf0), ptr(c0b.detach()), ptr(hbuf), nhid,
+                                      capi.QT_EPI_BIAS | capi.QT_EPI_OUT_F32, n, nhid, ldf, ptr(ws), ws.numel(), stream()), "classifier.0")
+        check(L().qt_relu_dropout(ptr(hbuf), ptr(h16), n * nhid, p, seed2, 1, stream()), "classifier relu/dropout")
+        nc = c3w.shape[0]
+        logits = torch.empty(n, nc, device=dev)
+        check(L().qt_small_linear_fwd(ptr(hbuf), 0, nhid, ptr(c3w.detach()), ptr(c3b.detach()), n, nc, nhid, 0, 0.0, 0, ptr(logits), nc,
+                                      None, 0, stream()), "classifier.3")
+        ops._count(4)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w)
+            ctx.cfg = (mode, p, seed1, seed2, n, ldf, nimg, nnum, dq)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w = ctx.saved
+        mode, p, seed1, seed2, n, ldf, nimg, nnum, dq = ctx.cfg
+        need = ctx.needs_input_grad
+        dev = feat.device
+        dl = dlogits.detach().float().contiguous()
+        nc, nhid = c3w.shape
+        # classifier.3
+        dc3w = ops.grad_out(c3w)
+        dc3b = torch.empty(nc, device=dev)
+        check(L().qt_small_linear_bwd_dw(ptr(dl), 0, nc, ptr(hbuf), 0, nhid, n, nc, nhid, ptr(dc3w), ptr(dc3b), 0, stream()), "classifier.3 dW")
+        dh16 = torch.empty(n, nhid, device=dev, dtype=BF16)
+        check(L().qt_small_linear_bwd_dx(ptr(dl), 0, nc, ptr(c3w.detach()), n, nc, nhid, ptr(hbuf), nhid, p, seed2, None, 0,
+                                         ptr(dh16), nhid, stream()), "classifier.3 dX")
+        ops._count(2)
+        # classifier.0
+        ws = ops.workspace(L().qt_linear_workspace_bytes(n, nhid, ldf), dev)
+        dc0w = ops.grad_out(c0w)
+        with ops.gemm_scope("linear_wgrad", 2.0 * n * nhid * ldf):
+            check(L().qt_linear_wgrad(ptr(feat), ldf, ptr(dh16), nhid, ptr(dc0w), 0, n, nhid, ldf, ptr(ws), ws.numel(), stream()), "classifier.0 dW")
+        dc0b = torch.empty(nhid, device=dev)
+        ops.colsum(dh16, dc0b)
+        dfeat = torch.empty(n, ldf, device=dev, dtype=BF16)
+        wd0 = ops.packed_dgrad(c0w)
+        with ops.gemm_scope("linear_dgrad", 2.0 * n * nhid * ldf):
+            check(L().qt_linear_dgrad(ptr(dh16), nhid, ptr(wd0), ptr(dfeat), ldf, n, nhid, ldf, ptr(ws), ws.numel(), stream()),
+                  "classifier.0 dX")
+        ops._count(4)
+        dm0w = dm0b = dm3w = dm3b = None
+        if nnum:
+            nh, k0 = m0w.shape
+            dnum = dfeat.data_ptr() + 2 * nimg
+            dm3w = ops.grad_out(m3w)
+            dm3b = torch.empty(nnum, device=dev)
+            check(L().qt_small_linear_bwd_dw(dnum, 1, ldf, ptr(h1), 0, nh, n, nnum, nh, ptr(dm3w), ptr(dm3b), 0, stream()), "numerical_mlp.3 dW")
+            dh1 = torch.empty(n, nh, device=dev)
+            check(L().qt_small_linear_bwd_dx(dnum, 1, ldf, ptr(m3w.detach()), n, nnum, nh, ptr(h1), nh, p, seed1, ptr(dh1), nh, None, 0,
+                                             stream()), "numerical_mlp.3 dX")
+            dm0w = ops.grad_out(m0w)
+            dm0b = torch.empty(nh, device=dev)
+            check(L().qt_small_linear_bwd_dw(ptr(dh1), 0, nh, ptr(numf), 0, k0, n, nh, k0, ptr(dm0w), ptr(dm0b), 0, stream()), "numerical_mlp.0 dW")
+            ops._count(3)
+        dbase = dl4 = dqw = dqb = None
+        if nimg:
+            dqt = torch.empty_like(q)
+            dl4b = torch.empty(n, 7, 7, 512, device=dev, dtype=BF16)
+            check(L().qt_quadtree_pool_bwd(ptr(dfeat), ptr(q), ptr(dqt), ptr(dl4b), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_bwd")
+            ops._count()
+            dl4 = ops.as_nchw_view(dl4b) if need[1] else None
+            if need[3]:
+                dqw = _zeros_like_param(qw)
+                ops.conv_wgrad(dq, bb, dqt, dqw)
+            if need[4]:
+                dqb = torch.empty(qw.shape[0], device=dev)
+                ops.colsum(dqt.view(-1, qw.shape[0]), dqb)
+            if need[0]:
+                dbb = torch.empty_like(bb)
+                ops.conv_dgrad(dq, dqt, ops.packed_dgrad(qw), dbb)
+                dbase = ops.as_nchw_view(dbb)
+        return (dbase, dl4, None, dqw, dqb, dm0w, dm0b, dm3w, dm3b, dc0w, dc0b, dc3w, dc3b, None, None, None)
+
+
+# =================================================================================================
+# QuadtreeCNN
+# =================================================================================================
+class QuadtreeCNN(nn.Module):
+    """Drop-in for the reference QuadtreeCNN.
+
+    Constructor / attributes / state_dict keys follow `Quadtree_from scratch/models.py:214-271`; `mode` and
+    `freeze_backbone` cover the `resnet/models.py:70-133` variant (frozen backbone, fusion / image_only /
+    numerical_only) including its Grad-CAM hook helpers (:131-139)."""
+
+    def __init__(self, num_classes, cnn_feature_dim=512, numerical_feature_dim=47, dropout_rate=0.5, mode="fusion",
+                 freeze_backbone=False):
+        super().__init__()
+        if mode not in ("fusion", "image_only", "numerical_only"):
+            raise ValueError(f"Invalid mode: {mode}. Choose from 'fusion', 'image_only', 'numerical_only', "
+                             "'standard_resnet_only'.")
+        self.mode = mode
+        self.base_cnn = make_resnet18()
+        if freeze_backbone:
+            for param in self.base_cnn.parameters():
+                param.requires_grad = False
+        b = self.base_cnn
+        self.features_extractor = FusedFeatures(b.conv1, b.bn1, b.relu, b.maxpool, b.layer1, b.layer2, b.layer3)
+        self.quadrant_processor = nn.Sequential(
+            nn.Conv2d(256, cnn_feature_dim // 4, kernel_size=3, padding=1), nn.ReLU(inplace=True),
+            nn.MaxPool2d(kernel_size=2, stride=2))
+        self.global_processor = nn.Sequential(b.layer4, b.avgpool)
+        self.image_feature_dim = 512 + ((cnn_feature_dim // 4) * 3 * 3 * 4)
+        assert self.image_feature_dim == 5120, f"Image feature dim mismatch: Expected 5120, got {self.image_feature_dim}"
+        self.numerical_mlp = nn.Sequential(
+            nn.Linear(numerical_feature_dim, numerical_feature_dim * 2), nn.ReLU(inplace=True), nn.Dropout(dropout_rate),
+            nn.Linear(numerical_feature_dim * 2, cnn_feature_dim // 2))
+        self.numerical_output_dim = cnn_feature_dim // 2
+        self.combined_feature_dim = self.image_feature_dim + self.numerical_output_dim
+        if mode == "fusion":
+            self.final_classifier_input_dim = self.combined_feature_dim
+        elif mode == "image_only":
+            self.final_classifier_input_dim = self.image_feature_dim
+        else:
+            self.final_classifier_input_dim = self.numerical_output_dim
+        d = self.final_classifier_input_dim
+        self.classifier = nn.Sequential(nn.Linear(d, d // 2), nn.ReLU(inplace=True), nn.Dropout(dropout_rate),
+                                        nn.Linear(d // 2, num_classes))
+        self.dropout_rate = dropout_rate
+        self.gradients = None
+        self.activations = None
+
+    # Grad-CAM helpers of the resnet/ variant (resnet/models.py:131-139)
+    def save_gradient_hook(self, module, grad_input, grad_output):
+        self.gradients = grad_output[0]
+
+    def save_activation_hook(self, module, input, output):
+        self.activations = output
+
+    def forward(self, image_input, numerical_input):
+        base = l4 = None
+        if self.mode in ("fusion", "image_only"):
+            base = self.features_extractor(image_input)
+            l4 = self.base_cnn.layer4(base)  # the module call keeps hooks on base_cnn.layer4 alive
+        qp, mlp, cls = self.quadrant_processor[0], self.numerical_mlp, self.classifier
+        return _QuadHeadFn.apply(base, l4, numerical_input, qp.weight, qp.bias, mlp[0].weight, mlp[0].bias, mlp[3].weight,
+                                 mlp[3].bias, cls[0].weight, cls[0].bias, cls[3].weight, cls[3].bias, self.mode,
+                                 self.dropout_rate, self.training)
+
+
+def get_model(model_name="quadtree", num_classes=8, device="cuda", print_num_params=True):
+    """`get_model` of Quadtree_from scratch/models.py:309-325 (same argument names and printout)."""
+    name = model_name.lower()
+    if name == "quadtree":
+        model = QuadtreeCNN(num_classes=num_classes).to(device)
+    else:
+        raise ValueError(f"get_model: '{model_name}' is outside the B200 hot path (SURVEY.md §8); supported: 'quadtree'")
+    if print_num_params:
+        num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        print(f"Model: '{name.upper()}' | Trainable Parameters: {num_params / 1e6:.2f} Million")
+    return model
+
+
+def get_model_resnet(num_classes, device, numerical_feature_dim=47, mode="fusion", print_num_params=True):
+    """`get_model` of resnet/models.py:183-194 (frozen backbone + mode switch)."""
+    if mode == "standard_resnet_only":
+        raise ValueError("standard_resnet_only is outside the accelerated path for now")
+    model = QuadtreeCNN(num_classes=num_classes, numerical_feature_dim=numerical_feature_dim, mode=mode,
+                        freeze_backbone=True).to(device)
+    if print_num_params:
+        num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        print(f"Number of trainable parameters: {num_params / 1e6:.2f} Million (Mode: {mode})")
+    return model
+
+
+def load_oracle_params(model: nn.Module, params: dict) -> None:
+    """Load a parameter dict in the oracle's naming (oracle/quadtree_oracle.make_params) — the names ARE the
+    reference's state_dict keys, aliases resolve through the shared tensors."""
+    own = model.state_dict()
+    sd = {k: v for k, v in params.items() if k in own}
+    res = model.load_state_dict(sd, strict=False)
+    missing = [k for k in res.missing_keys if not k.startswith(("features_extractor.", "global_processor."))]
+    if missing:
+        raise RuntimeError(f"load_oracle_params: missing {missing[:5]}")

@@ -1,0 +1,348 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers, return tensors.
+
+Activations are dense channels-last bf16 buffers ([N,H,W,C] / [N,D,H,W,C]); statistics and weight gradients
+are fp32. Nothing here computes on the host or falls back to ATen kernels for the hot ops.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import capi
+from .capi import check, ptr, stream
+
+BF16 = torch.bfloat16
+_launches = 0  # number of libqtcnn kernel-launching calls (bench.py reports it)
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches
+
+
+def L():
+    return capi.lib()
+
+
+# ------------------------------------------------------------------------------------------------- workspace
+_ws = {}
+
+
+def workspace(nbytes: int, device, tag="gemm") -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    t = _ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _ws[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------- weights
+class _Packed:
+    __slots__ = ("version", "ptr", "wf", "wd", "w8")
+
+    def __init__(self):
+        self.version = -1
+        self.ptr = 0
+        self.wf = self.wd = self.w8 = None
+
+
+class _IdMap:
+    """Tensor-keyed weak map (WeakKeyDictionary cannot be used: it compares keys with ==, which is elementwise
+    for tensors). Entries die with their tensor."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, t, default=None):
+        item = self._d.get(id(t))
+        if item is None or item[0]() is not t:
+            return default
+        return item[1]
+
+    def set(self, t, value):
+        key = id(t)
+        self._d[key] = (weakref.ref(t, lambda _r, k=key, d=self._d: d.pop(k, None)), value)
+
+    def pop(self, t, default=None):
+        item = self._d.pop(id(t), None)
+        return default if item is None else item[1]
+
+
+_packed = _IdMap()
+
+
+def _entry(w: torch.Tensor) -> _Packed:
+    e = _packed.get(w)
+    if e is None:
+        e = _Packed()
+        _packed.set(w, e)
+    if e.version != w._version or e.ptr != w.data_ptr():
+        e.version, e.ptr = w._version, w.data_ptr()
+        e.wf = e.wd = e.w8 = None
+    return e
+
+
+def _w_dims(w: torch.Tensor) -> Tuple[int, int, int]:
+    cout, cin = w.shape[0], w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    return cout, cin, taps
+
+
+def packed_fprop(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [cout][taps][cin] copy of an fp32 parameter, refreshed when the parameter changes."""
+    e = _entry(w)
+    if e.wf is None:
+        cout, cin, taps = _w_dims(w)
+        e.wf = torch.empty(cout, taps, cin, device=w.device, dtype=BF16)
+        wc = w.detach().contiguous()
+        check(L().qt_wpack_fprop(ptr(wc), ptr(e.wf), cout, cin, taps, stream()), "wpack_fprop")
+        _count()
+    return e.wf
+
+
+def packed_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [cin][taps][cout] copy (B operand of the data-gradient GEMM)."""
+    e = _entry(w)
+    if e.wd is None:
+        cout, cin, taps = _w_dims(w)
+        e.wd = torch.empty(cin, taps, cout, device=w.device, dtype=BF16)
+        wc = w.detach().contiguous()
+        check(L().qt_wpack_dgrad(ptr(wc), ptr(e.wd), cout, cin, taps, stream()), "wpack_dgrad")
+        _count()
+    return e.wd
+
+
+def packed_stem(w: torch.Tensor) -> torch.Tensor:
+    e = _entry(w)
+    if e.w8 is None:
+        cout, cin, r, s = w.shape
+        e.w8 = torch.empty(cout, 8, 32, device=w.device, dtype=BF16)
+        wc = w.detach().contiguous()
+        check(L().qt_wpack_stem(ptr(wc), ptr(e.w8), cout, cin, r, s, stream()), "wpack_stem")
+        _count()
+    return e.w8
+
+
+# ------------------------------------------------------------------------------------------------- conv
+_desc_cache = {}
+
+
+def conv2d_desc(n, h, w, cin, cout, k, stride, pad):
+    key = ("2d", n, h, w, cin, cout, k, stride, pad)
+    d = _desc_cache.get(key)
+    if d is None:
+        d = capi.conv_desc(n, (1, h, w), cin, cout, (1, k, k), (1, stride, stride), (0, pad, pad))
+        _desc_cache[key] = d
+    return d
+
+
+def quadrant_desc(n, h, w, cin, cout, k, pad):
+    """Four quadrant views (TL, TR, BL, BR) of a dense [n,h,w,cin] map as one grouped conv; output is
+    quadrant-major [4][n][h/2][w/2][cout]. Even h, w only (the reference's 14x14 / 28x28 maps)."""
+    key = ("quad", n, h, w, cin, cout, k, pad)
+    d = _desc_cache.get(key)
+    if d is None:
+        if h % 2 or w % 2:
+            raise RuntimeError("quadrant_desc: even feature-map sizes only")
+        qh, qw = h // 2, w // 2
+        xs = (h * w * cin, 0, w * cin, cin)
+        xoff = (0, qw * cin, qh * w * cin, qh * w * cin + qw * cin)
+        yoff = tuple(q * n * qh * qw * cout for q in range(4))
+        d = capi.conv_desc(n, (1, qh, qw), cin, cout, (1, k, k), (1, 1, 1), (0, pad, pad), x_stride=xs, groups=4,
+                           x_group_off=xoff, y_group_off=yoff)
+        _desc_cache[key] = d
+    return d
+
+
+def conv_out_hw(d) -> Tuple[int, int, int]:
+    return (capi.out_size(d.in_d, d.k_d, d.stride_d, d.pad_d), capi.out_size(d.in_h, d.k_h, d.stride_h, d.pad_h),
+            capi.out_size(d.in_w, d.k_w, d.stride_w, d.pad_w))
+
+
+def conv_fprop(d, x, wf, y, bias=None, relu=False, want_stats=False):
+    """y = conv(x) [+bias][ReLU]; returns the BatchNorm partial-sum buffer when want_stats."""
+    stats = None
+    flags = (capi.QT_EPI_BIAS if bias is not None else 0) | (capi.QT_EPI_RELU if relu else 0)
+    if want_stats:
+        rows = L().qt_conv_stat_rows(d)
+        stats = torch.empty(rows, 2, d.out_c, device=x.device, dtype=torch.float32)
+        flags |= capi.QT_EPI_STATS
+    with gemm_scope("conv_fprop", conv_flops(d) if _prof is not None else 0.0):
+        check(L().qt_conv_fprop(d, ptr(x), ptr(wf), ptr(y), ptr(bias), ptr(stats), flags, None, 0, stream()), "conv_fprop")
+    _count()
+    return stats
+
+
+def conv_dgrad(d, dy, wd, dx, accumulate=False):
+    with gemm_scope("conv_dgrad", conv_flops(d) if _prof is not None else 0.0):
+        check(L().qt_conv_dgrad(d, ptr(dy), ptr(wd), ptr(dx), 1 if accumulate else 0, stream()), "conv_dgrad")
+    _count(d.stride_h * d.stride_w * d.stride_d)
+
+
+def conv_wgrad(d, x, dy, dw, accumulate=False):
+    nbytes = L().qt_conv_wgrad_workspace_bytes(d)
+    ws = workspace(nbytes, x.device)
+    with gemm_scope("conv_wgrad", conv_flops(d) if _prof is not None else 0.0):
+        check(L().qt_conv_wgrad(d, ptr(x), ptr(dy), ptr(dw), 1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
+              "conv_wgrad")
+    _count(2)
+
+
+# ------------------------------------------------------------------------------------------------- batch norm
+class BNState:
+    """Per-call statistics of one train-mode BatchNorm (saved for backward)."""
+    __slots__ = ("mean", "invstd", "scale", "shift")
+
+    def __init__(self, c, device):
+        buf = torch.empty(4, c, device=device, dtype=torch.float32)
+        self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_finalize(stats, count, bn, c, device, training=True) -> BNState:
+    """Train: batch statistics from the conv epilogue's partial sums (+ running-stat update, as
+    nn.BatchNorm does). Eval: coefficients from the running statistics."""
+    st = BNState(c, device)
+    gamma = bn.weight.detach() if bn.weight is not None else None
+    beta = bn.bias.detach() if bn.bias is not None else None
+    if training:
+        ws = workspace(L().qt_bn_workspace_bytes(c), device, "bn")
+        track = bn.track_running_stats and bn.running_mean is not None
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        check(L().qt_bn_finalize(ptr(stats), stats.shape[0], c, float(count), ptr(gamma), ptr(beta), float(bn.eps), momentum,
+                                 ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                                 ptr(st.mean), ptr(st.invstd), ptr(st.scale), ptr(st.shift), ptr(ws), ws.numel(), stream()),
+              "bn_finalize")
+        _count(2)
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    else:
+        check(L().qt_bn_eval_coeffs(c, ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
+                                    ptr(st.mean), ptr(st.invstd), ptr(st.scale), ptr(st.shift), stream()), "bn_eval_coeffs")
+        _count()
+    return st
+
+
+def bn_apply(y, st: BNState, out, residual=None, relu=True):
+    c = y.shape[-1]
+    m = y.numel() // c
+    check(L().qt_bn_apply(ptr(y), ptr(st.scale), ptr(st.shift), ptr(residual), ptr(out), m, c, 1 if relu else 0, stream()),
+          "bn_apply")
+    _count()
+    return out
+
+
+def bn_backward(dout, act, y, st: BNState, gamma, dgamma, dbeta, dy, dz_out=None, eval_mode=False):
+    c = y.shape[-1]
+    m = y.numel() // c
+    ws = workspace(L().qt_bn_workspace_bytes(c), y.device, "bn")
+    check(L().qt_bn_backward(ptr(dout), ptr(act), ptr(y), ptr(st.mean), ptr(st.invstd), ptr(gamma), m, c, ptr(dgamma),
+                             ptr(dbeta), 0, 1 if eval_mode else 0, ptr(dy), ptr(dz_out), ptr(ws), ws.numel(), stream()),
+          "bn_backward")
+    _count(4)
+
+
+def colsum(x2d, out, accumulate=False):
+    m, c = x2d.shape
+    ws = workspace(L().qt_bn_workspace_bytes(c), x2d.device, "bn")
+    check(L().qt_colsum(ptr(x2d), m, c, ptr(out), 1 if accumulate else 0, ptr(ws), ws.numel(), stream()), "colsum")
+    _count(3)
+
+
+# ------------------------------------------------------------------------------------------------- misc
+def as_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor (any dtype / memory format) -> dense [N,H,W,C] bf16 buffer (no copy when it already
+    is a channels-last bf16 tensor produced by this package)."""
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    b = t.permute(0, 2, 3, 1)
+    return b if b.is_contiguous() else b.contiguous()
+
+
+def as_nchw_view(buf: torch.Tensor) -> torch.Tensor:
+    """Dense [N,H,W,C] buffer -> logical NCHW (channels_last) view."""
+    return buf.permute(0, 3, 1, 2)
+
+
+def new_seed() -> int:
+    """Dropout seed drawn from torch's CPU generator (so torch.manual_seed makes runs reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+# ------------------------------------------------------------------------------------------------- param grads
+_grad_views = _IdMap()
+
+
+def register_grad_view(p, view):
+    """parallel.DataParallelGrads: weight-gradient kernels write straight into the flat bucket buffers."""
+    _grad_views.set(p, view)
+
+
+def unregister_grad_view(p):
+    _grad_views.pop(p, None)
+
+
+def grad_out(p: torch.Tensor) -> torch.Tensor:
+    """Destination tensor for the gradient of parameter `p` (a bucket view under data parallelism)."""
+    v = _grad_views.get(p)
+    if v is not None:
+        return v
+    return torch.empty_like(p, memory_format=torch.contiguous_format)
+
+
+# ------------------------------------------------------------------------------------------------- profiling
+_prof = None
+
+
+def profile_begin():
+    """Start recording one CUDA-event pair per GEMM-family launch (bench.py's roofline pass)."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for fam, flops, e0, e1 in rec:
+        d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "n": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["n"] += 1
+    return out
+
+
+class gemm_scope:
+    """`with gemm_scope(family, flops): <launch>` — a no-op unless profiling is on."""
+    __slots__ = ("fam", "flops", "e0")
+
+    def __init__(self, fam, flops):
+        self.fam, self.flops, self.e0 = fam, flops, None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.fam, self.flops, self.e0, e1))
+        return False
+
+
+def conv_flops(d) -> float:
+    """Algorithmic FLOPs (2*MAC) of one convolution pass described by `d` (same for fprop, dgrad, wgrad)."""
+    od, oh, ow = conv_out_hw(d)
+    return 2.0 * d.groups * d.n * od * oh * ow * d.k_d * d.k_h * d.k_w * d.in_c * d.out_c

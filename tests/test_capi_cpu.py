@@ -1,0 +1,50 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/qtcnn.h
+declares, the ctypes signature table covers them all, the module mirror keeps the reference's constructor
+surface / state_dict keys, and the product path refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+
+import pytest
+import torch
+
+import qtcnn_b200.capi as capi
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.lib()
+    declared = capi.declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"libqtcnn.so does not export {name}"
+    assert set(declared) == set(capi._SIGNATURES), set(declared) ^ set(capi._SIGNATURES)
+    assert lib.qt_version() >= 100
+
+
+def test_conv_desc_matches_c_struct_layout():
+    d = capi.conv_desc(2, (1, 14, 14), 256, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    assert ctypes.sizeof(capi.ConvDesc) == 16 * 4 + 16 * 8
+    assert (d.x_stride[0], d.x_stride[2], d.x_stride[3]) == (14 * 14 * 256, 14 * 256, 256)
+    assert capi.lib().qt_conv_stat_rows(d) == (2 * 14 * 14 + 127) // 128
+    bad = capi.conv_desc(2, (1, 14, 14), 250, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    assert capi.lib().qt_conv_stat_rows(bad) == -1
+    assert b"multiples of 8" in capi.lib().qt_last_error()
+
+
+def test_module_mirror_surface_and_no_cpu_fallback():
+    from qtcnn_b200 import models as M
+    m = M.QuadtreeCNN(num_classes=8)
+    sd = m.state_dict()
+    assert len(sd) == 252
+    assert sum(p.numel() for p in m.parameters()) == 26_488_272
+    for key in ("base_cnn.conv1.weight", "features_extractor.0.weight", "features_extractor.6.0.downsample.1.running_var",
+                "global_processor.0.1.bn2.num_batches_tracked", "quadrant_processor.0.bias", "numerical_mlp.3.weight",
+                "classifier.0.weight", "classifier.3.bias", "base_cnn.fc.weight"):
+        assert key in sd, key
+    assert sd["classifier.0.weight"].shape == (2688, 5376)
+    assert sd["features_extractor.0.weight"].data_ptr() == sd["base_cnn.conv1.weight"].data_ptr()
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        m(torch.randn(1, 3, 224, 224), torch.randn(1, 47))
+    with pytest.raises(ValueError):
+        M.QuadtreeCNN(num_classes=8, mode="bogus")
+    frozen = M.get_model_resnet(8, "cpu", mode="image_only", print_num_params=False)
+    assert not any(p.requires_grad for p in frozen.base_cnn.parameters())
+    assert frozen.classifier[0].in_features == 5120

@@ -292,7 +292,7 @@ def test_batchnorm_train(C, m, c, residual, relu):
     dz = torch.empty_like(y)
     act = out if relu else None
     run(C, C.lib().qt_bn_backward(C.ptr(dout), C.ptr(act), C.ptr(y), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), m, c,
-                                  C.ptr(dgamma), C.ptr(dbeta), 0, C.ptr(dy), C.ptr(dz), C.ptr(ws), ws_bytes, C.stream()),
+                                  C.ptr(dgamma), C.ptr(dbeta), 0, 0, C.ptr(dy), C.ptr(dz), C.ptr(ws), ws_bytes, C.stream()),
         "bn_backward")
     # the reference mask comes from fp32 activations; ours from the bf16-rounded ones -> compare loosely on dy
     report("bn dgamma", dgamma, gref.grad, 2e-2)
@@ -424,3 +424,14 @@ def test_region_avgpool_and_misc(C):
     assert torch.equal(o, bf16(a.float() + b2.float()))
     run(C, C.lib().qt_relu_backward(C.ptr(a), C.ptr(b2), C.ptr(o), 4096, C.stream()), "relu_backward")
     assert torch.equal(o, torch.where(b2.float() > 0, a, torch.zeros_like(a)))
+
+
+def test_colsum_wide(C):
+    m, c = 300, 2688
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = bf16(torch.randn(m, c, device="cuda", generator=g))
+    ws_bytes = C.lib().qt_bn_workspace_bytes(c)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    out = torch.empty(c, device="cuda")
+    run(C, C.lib().qt_colsum(C.ptr(x), m, c, C.ptr(out), 0, C.ptr(ws), ws_bytes, C.stream()), "colsum wide")
+    report("colsum 2688", out, x.float().sum(0), 1e-5)
