@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -195,9 +196,12 @@ def run_ours(args):
         y = labels_h.to(dev, non_blocking=True)
         return float(step(x, nf, y))
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
-    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    if args.no_e2e:
+        ms_e2e, e2e = float("nan"), None
+    else:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = images_h.numel() * 4 + numerical_h.numel() * 4 + labels_h.numel() * 8
 
     roofline = None

@@ -52,6 +52,9 @@ int qt_version(void);
 const char* qt_last_error(void);
 /* 1 if any bounded barrier wait inside a kernel timed out since the last call (debug aid); resets it. */
 int qt_take_timeout_flag(void);
+/* Tuning/debug switch: 0 routes 3x3 stride-1 convolutions through the generic gather kernel instead of the
+ * persistent input-reuse kernel (both are tcgen05 paths). */
+void qt_set_conv3x3_enabled(int on);
 
 /* ---- layout / packing ------------------------------------------------------------------------- */
 /* images.to(device) feeding base_cnn.conv1 (QS/Quadtree_train.py:61, QS/models.py:222):

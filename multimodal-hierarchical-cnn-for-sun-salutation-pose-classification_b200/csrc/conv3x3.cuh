@@ -1,0 +1,336 @@
+// Persistent 3x3 / stride-1 / pad-1 convolution on tcgen05 with input reuse across the nine taps.
+//
+// The M index runs over the pixels of a *virtual* zero-padded map [N][H+2][W+2]; in that space a filter tap is
+// a constant row shift (dh*(W+2) + dw), so one "slab" — the BM + 2(W+3) consecutive virtual pixels around an
+// M tile, 64 channels wide — staged ONCE in shared memory serves all nine taps: the A descriptor of tap t just
+// starts (dh+1)*(W+2) + (dw+1) rows further down. This cuts the L2->SM traffic of the activation operand ~6x
+// against re-gathering every tap (the v1 kernel in igemm.cuh), which is what bounds 3x3 convs on B200.
+//
+// Shared-memory layouts
+//   A slab : no-swizzle K-major "planes": plane c (16-byte channel chunk) holds [rows][16 B]; an 8-row core
+//            matrix is 128 contiguous bytes, SBO = 128 B between 8-row groups, LBO = plane stride between the
+//            two 16-byte K chunks of one K=16 MMA. Any 16-byte-aligned start row is legal, so shifted windows
+//            need no swizzle-phase bookkeeping. Border / out-of-image rows are zero-filled by cp.async.
+//   B tile : [BN rows][128 B] with the 128-byte XOR swizzle (same as igemm.cuh), one tile per (tap, slab).
+//
+// Roles (288 threads, one CTA per SM, persistent over tiles): warps 0-3 epilogue (TMEM -> registers -> global,
+// BatchNorm partial sums), warps 4-7 producers (cp.async gathers, lag-published through mbarriers), warp 8
+// MMA issuer. Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
+// tile i+1; when the whole filter fits in the B ring (64->64 layers) it is loaded once and stays resident.
+#pragma once
+#include "igemm.cuh"
+
+namespace qt {
+
+constexpr int kC3Threads = 288;
+
+struct Conv3x3Params {
+  const __nv_bfloat16* a;   // dense NHWC input  [N][H][W][cin]
+  const __nv_bfloat16* b;   // weights [nout][wtaps][cin]
+  void* out;                // dense NHWC output [N][H][W][nout] (bf16)
+  const __nv_bfloat16* addend;
+  float* stats;             // [num_m_tiles * MT][2][nout]
+  int N, H, W, cin, nout, wtaps;
+  int flags;
+  int slabs;                // cin / 64
+  int V;                    // N * (H+2) * (W+2) virtual pixels
+  int num_m_tiles, num_n_tiles;
+  int R;                    // slab rows (multiple of 16)
+  int plane_stride;         // bytes, R*16 + 16
+  int b_resident;           // 1: all 9*slabs weight tiles stay in the B ring
+  signed char off_h[9], off_w[9];
+  short wtap[9];
+};
+
+template <int BN, int MT, int NSLAB, int NB>
+struct C3Smem {
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kBBytes = NB * kBTile;
+  static constexpr int kScratch = 2 * 4 * BN * 4;
+  static constexpr int kBarBytes = 512;
+  // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][barriers][slabs...]
+};
+
+template <int BN, int MT, int NSLAB, int NB>
+__global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p) {
+  using L = C3Smem<BN, MT, NSLAB, NB>;
+  constexpr uint32_t TCOLS = 2 * MT * BN;  // double-buffered accumulators
+  static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_ring = smem;
+  float* scratch = reinterpret_cast<float*>(smem + L::kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBBytes + L::kScratch);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + NSLAB;
+  uint64_t* b_full = a_empty + NSLAB;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* acc_full = b_empty + NB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* slab_base = smem + L::kBBytes + L::kScratch + L::kBarBytes;
+  const int slab_bytes = 8 * p.plane_stride;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLAB; ++s) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], 1); }
+      for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], kProducerThreads); mbar_init(&b_empty[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kProducerThreads); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<TCOLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ================================================================= producers
+    const int t = threadIdx.x - 128;
+    const int chunk = t & 7;
+    const int rbase = t >> 3;
+    const uint32_t b_sw = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
+    uint32_t a_cnt = 0, b_cnt = 0;   // items issued so far (ring positions)
+    uint32_t pend0 = 0, pend1 = 0;   // full-barrier addresses of the two most recent items (lag-2 publish)
+    uint32_t issued = 0;
+    auto publish = [&](uint32_t bar_addr) {
+      // called right after commit_group of a new item: the item issued two steps ago is complete
+      if (issued >= 2) {
+        cp_async_wait<2>();
+        fence_proxy_async_smem();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend0) : "memory");
+      }
+      pend0 = pend1;
+      pend1 = bar_addr;
+      ++issued;
+    };
+    bool first_tile = true;
+    const int adv_w = 16 % Wp, adv_h = 16 / Wp;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+      const int q0 = m_tile * (kBM * MT);
+      for (int c = 0; c < p.slabs; ++c) {
+        {  // ---- A slab: rows j <-> virtual pixel q0 - (W+3) + j
+          const int s = a_cnt % NSLAB;
+          if (a_cnt >= NSLAB) mbar_wait(&a_empty[s], ((a_cnt / NSLAB) - 1) & 1);
+          const uint32_t dst0 = smem_u32(slab_base + s * slab_bytes) + chunk * p.plane_stride;
+          const __nv_bfloat16* src_c = p.a + c * 64 + chunk * 8;
+          // first row of this thread: virtual pixel v0 (shifted by one image so the decomposition is non-negative),
+          // then advance 16 virtual pixels per iteration with carries instead of dividing per row
+          int n, hp, wp;
+          {
+            const int vv = q0 - (p.W + 3) + rbase + Wp * Hp;
+            wp = vv % Wp;
+            const int rest = vv / Wp;
+            hp = rest % Hp;
+            n = rest / Hp - 1;
+          }
+          for (int j = rbase; j < p.R; j += 16) {
+            const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(p.N)) && (wp >= 1) && (wp <= p.W) && (hp >= 1) &&
+                            (hp <= p.H);
+            const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
+            const __nv_bfloat16* src = ok ? (src_c + static_cast<long long>(pix) * p.cin) : p.a;
+            cp_async16(dst0 + j * 16, src, ok ? 16u : 0u);
+            wp += adv_w; hp += adv_h;
+            if (wp >= Wp) { wp -= Wp; ++hp; }
+            if (hp >= Hp) { hp -= Hp; ++n; }
+          }
+          cp_async_commit();
+          publish(smem_u32(&a_full[s]));
+          ++a_cnt;
+        }
+        if (!p.b_resident || first_tile) {
+          for (int tp = 0; tp < 9; ++tp) {
+            const int s = b_cnt % NB;
+            if (!p.b_resident && b_cnt >= NB) mbar_wait(&b_empty[s], ((b_cnt / NB) - 1) & 1);
+            const uint32_t dst0 = smem_u32(b_ring + s * L::kBTile) + rbase * 128 + b_sw;
+            const long long woff = static_cast<long long>(p.wtap[tp]) * p.cin + c * 64 + chunk * 8;
+#pragma unroll
+            for (int i = 0; i < BN / 16; ++i) {
+              const int n = n0 + rbase + 16 * i;
+              const bool ok = n < p.nout;
+              const __nv_bfloat16* src = ok ? (p.b + static_cast<long long>(n) * p.wtaps * p.cin + woff) : p.b;
+              cp_async16(dst0 + i * 16 * 128, src, ok ? 16u : 0u);
+            }
+            cp_async_commit();
+            publish(smem_u32(&b_full[s]));
+            ++b_cnt;
+          }
+        }
+      }
+      first_tile = false;
+    }
+    // drain the last (up to two) items
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    if (issued >= 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend0) : "memory");
+    if (issued >= 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend1) : "memory");
+  } else if (warp == 8) {
+    // ================================================================= MMA issuer
+    // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform
+    // datapath; one elected lane issues tcgen05.mma / tcgen05.commit.
+    {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      // descriptor high words are constant: SBO>>4 [0,14) | version 1 [14,16) | layout [29,32)
+      constexpr uint32_t a_hi = (128u >> 4) | (1u << 14) | (kLayoutNone << 29);
+      constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
+      const uint32_t a_lbo = (static_cast<uint32_t>(p.plane_stride >> 4) & 0x3FFFu) << 16;
+      constexpr uint32_t b_lbo = 1u << 16;
+      const uint32_t kstep = static_cast<uint32_t>(2 * p.plane_stride) >> 4;  // two 16-byte planes per K=16
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t a_cnt = 0, b_cnt = 0, tile_it = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        const uint32_t ab = tile_it & 1;
+        if (tile_it >= 2) mbar_wait(&acc_empty[ab], ((tile_it >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d_base = tbase + ab * (MT * BN);
+        for (int c = 0; c < p.slabs; ++c) {
+          const int sa = a_cnt % NSLAB;
+          mbar_wait(&a_full[sa], (a_cnt / NSLAB) & 1);
+          const uint32_t slab_lo = ((smem_u32(slab_base + sa * slab_bytes) >> 4) & 0x3FFFu) | a_lbo;
+#pragma unroll 1
+          for (int tp = 0; tp < 9; ++tp) {
+            int sb;
+            if (p.b_resident) {
+              sb = c * 9 + tp;
+              if (first_tile) mbar_wait(&b_full[sb], 0);
+            } else {
+              sb = b_cnt % NB;
+              mbar_wait(&b_full[sb], (b_cnt / NB) & 1);
+            }
+            tc_fence_after();
+            const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
+            const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
+            if (lane == 0) {
+#pragma unroll
+              for (int u = 0; u < MT; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
+                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
+                  umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
+                }
+              }
+              if (!p.b_resident) umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (!p.b_resident) ++b_cnt;
+          }
+          if (lane == 0) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          ++a_cnt;
+        }
+        if (lane == 0) umma_commit(&acc_full[ab]);
+        __syncwarp();
+        first_tile = false;
+      }
+    }
+  } else {
+    // ================================================================= epilogue (warps 0-3)
+    const int flags = p.flags;
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+      const uint32_t ab = tile_it & 1;
+      mbar_wait(&acc_full[ab], (tile_it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < MT; ++u) {
+        const int v = (m_tile * MT + u) * kBM + warp * 32 + lane;
+        bool row_ok = v < p.V;
+        long long orow = 0;
+        if (row_ok) {
+          const int wp = v % Wp;
+          const int rest = v / Wp;
+          const int hp = rest % Hp;
+          const int n = rest / Hp;
+          row_ok = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
+          orow = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.nout;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ab * (MT * BN) + u * BN + c0, r);
+          tmem_ld_wait();
+          const int ncol = n0 + c0;
+          if (ncol >= p.nout) break;
+          float vv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]);
+          if ((flags & EPI_ADDEND) && row_ok) {
+            const __nv_bfloat16* ad = p.addend + orow + ncol;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+              const uint4 q = *reinterpret_cast<const uint4*>(ad + j);
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
+                f[2 * e] = __low2float(h2);
+                f[2 * e + 1] = __high2float(h2);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) vv[j + e] += f[e];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[j] = bf16_round(vv[j]);
+          if (row_ok) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + ncol;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16x2(vv[j], vv[j + 1]);
+              q.y = pack_bf16x2(vv[j + 2], vv[j + 3]);
+              q.z = pack_bf16x2(vv[j + 4], vv[j + 5]);
+              q.w = pack_bf16x2(vv[j + 6], vv[j + 7]);
+              *reinterpret_cast<uint4*>(dst + j) = q;
+            }
+          }
+          if (flags & EPI_STATS) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              vv[j] = row_ok ? vv[j] : 0.f;
+              sq[j] = vv[j] * vv[j];
+            }
+            const float s1 = warp_transpose_reduce(vv);
+            const float s2 = warp_transpose_reduce(sq);
+            scratch[(0 * 4 + warp) * BN + c0 + lane] = s1;
+            scratch[(1 * 4 + warp) * BN + c0 + lane] = s2;
+          }
+        }
+        if (flags & EPI_STATS) {
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          const long long srow = static_cast<long long>(m_tile) * MT + u;
+          for (int i = threadIdx.x; i < 2 * BN; i += kProducerThreads) {
+            const int which = i / BN, col = i - which * BN;
+            if (n0 + col < p.nout) {
+              const float* sc = scratch + which * 4 * BN + col;
+              p.stats[(srow * 2 + which) * p.nout + n0 + col] = (sc[0] + sc[BN]) + (sc[2 * BN] + sc[3 * BN]);
+            }
+          }
+          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+}  // namespace qt

@@ -240,25 +240,32 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid
     for (int j = max(0, nit - kLag); j < nit; ++j) mbar_arrive(&full_bar[j % STAGES]);
   } else {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // warp-uniform control flow (descriptor math on the uniform datapath); lane 0 issues
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t d_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
+      constexpr uint32_t d_lbo = 1u << 16;
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
+        const uint32_t b_lo = a_lo + (L::kABytes >> 4);
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t ad = make_sdesc(a_addr + k * 32, 16, 1024, kLayoutSW128);
-          const uint64_t bd = make_sdesc(b_addr + k * 32, 16, 1024, kLayoutSW128);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (a_lo + k * 2);
+            const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (b_lo + k * 2);
+            umma_bf16(tbase, ad, bd, idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        __syncwarp();
       }
-      umma_commit(accum_bar);
+      if (lane == 0) umma_commit(accum_bar);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   if (warp < 4) {
@@ -514,25 +521,32 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
     fence_proxy_async_smem();
     for (int j = max(0, nit - kLag); j < nit; ++j) mbar_arrive(&full_bar[j % STAGES]);
   } else {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+      // MN-major SW128: LBO = 8192 B between 64-wide MN blocks, SBO = 1024 B between 8-pixel groups
+      constexpr uint32_t d_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
+      constexpr uint32_t d_lbo = (8192u >> 4) << 16;
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
+        const uint32_t b_lo = a_lo + (L::kABytes >> 4);
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixels (two 8-row swizzle atoms) per MMA
-          const uint64_t ad = make_sdesc(a_addr + k * 2048, 8192, 1024, kLayoutSW128);
-          const uint64_t bd = make_sdesc(b_addr + k * 2048, 8192, 1024, kLayoutSW128);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {  // 16 pixels (two 8-row swizzle atoms) per MMA
+            const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (a_lo + k * (2048 >> 4));
+            const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (b_lo + k * (2048 >> 4));
+            umma_bf16(tbase, ad, bd, idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        __syncwarp();
       }
-      umma_commit(accum_bar);
+      if (lane == 0) umma_commit(accum_bar);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   if (warp < 4) {

@@ -8,6 +8,7 @@
 
 #include "elementwise.cuh"
 #include "igemm.cuh"
+#include "conv3x3.cuh"
 
 using namespace qt;
 
@@ -215,12 +216,120 @@ int fill_forward(IgemmParams& p, const qt_conv_desc* d) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent 3x3/s1/p1 kernel dispatch (conv3x3.cuh)
+// ------------------------------------------------------------------------------------------------
+bool g_use_conv3x3 = true;
+
+bool dense_nhwc(const long long* st, int d, int h, int w, int c) {
+  (void)d;
+  return st[3] == c && st[2] == static_cast<long long>(w) * c && st[0] == static_cast<long long>(h) * w * c;
+}
+
+struct C3Plan {
+  bool ok;
+  int bn, mt, nslab, nb, R, plane_stride, resident;
+  int num_m_tiles, num_n_tiles, V;
+  size_t smem;
+};
+
+// cin/nout are the GEMM-side channel counts (swapped for dgrad).
+C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
+  C3Plan pl{};
+  pl.ok = false;
+  if (!g_use_conv3x3) return pl;
+  if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->pad_d != 0) return pl;
+  if (d->groups != 1) return pl;
+  if (cin % 64 || nout % 32) return pl;
+  if (flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32)) return pl;
+  if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
+  const long long V = static_cast<long long>(d->n) * (d->in_h + 2) * (d->in_w + 2);
+  if (V > (1ll << 30)) return pl;
+  pl.V = static_cast<int>(V);
+  pl.bn = nout <= 64 ? 64 : 128;
+  pl.mt = 2;
+  const int bm = kBM * pl.mt;
+  pl.R = ((bm + 2 * (d->in_w + 3)) + 15) / 16 * 16;
+  pl.plane_stride = pl.R * 16 + 16;
+  const int slab_bytes = 8 * pl.plane_stride;
+  const int slabs = cin / 64;
+  const int btile = pl.bn * 128;
+  const int fixed = 1024 + 2 * 4 * pl.bn * 4 + 512;
+  const int budget = 227 * 1024;
+  pl.num_m_tiles = static_cast<int>((V + bm - 1) / bm);
+  pl.num_n_tiles = (nout + pl.bn - 1) / pl.bn;
+  if (pl.bn == 64) {
+    // try the resident-filter configuration (NB = 9, 64->64 layers)
+    pl.nb = 9;
+    pl.resident = (slabs == 1 && pl.num_n_tiles == 1) ? 1 : 0;
+    pl.nslab = 3;
+    if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
+  } else {
+    pl.nb = 6;
+    pl.resident = 0;
+    pl.nslab = 3;
+    if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
+  }
+  pl.smem = static_cast<size_t>(fixed) + static_cast<size_t>(pl.nb) * btile + static_cast<size_t>(pl.nslab) * slab_bytes;
+  if (pl.smem > static_cast<size_t>(budget)) return pl;
+  pl.ok = true;
+  return pl;
+}
+
+template <int BN, int MT, int NSLAB, int NB>
+int launch_conv3x3(const Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(conv3x3_kernel<BN, MT, NSLAB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  conv3x3_kernel<BN, MT, NSLAB, NB><<<grid, kC3Threads, smem, st>>>(p);
+  return cuda_status("conv3x3_kernel");
+}
+
+// taps: per filter tap the input offset (dh, dw) and its index in the weight tensor.
+int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, const void* a, const void* b, void* out,
+                const void* addend, float* stats, int flags, bool dgrad, cudaStream_t st) {
+  Conv3x3Params p;
+  memset(&p, 0, sizeof(p));
+  p.a = static_cast<const __nv_bfloat16*>(a);
+  p.b = static_cast<const __nv_bfloat16*>(b);
+  p.out = out;
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.stats = stats;
+  p.N = d->n; p.H = d->in_h; p.W = d->in_w;
+  p.cin = cin; p.nout = nout; p.wtaps = 9;
+  p.flags = flags;
+  p.slabs = cin / 64;
+  p.V = pl.V;
+  p.num_m_tiles = pl.num_m_tiles; p.num_n_tiles = pl.num_n_tiles;
+  p.R = pl.R; p.plane_stride = pl.plane_stride; p.b_resident = pl.resident;
+  int t = 0;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw, ++t) {
+      p.off_h[t] = static_cast<signed char>(dgrad ? 1 - kh : kh - 1);
+      p.off_w[t] = static_cast<signed char>(dgrad ? 1 - kw : kw - 1);
+      p.wtap[t] = static_cast<short>(t);
+    }
+  const int tiles = pl.num_m_tiles * pl.num_n_tiles;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (pl.bn == 64) {
+    if (pl.nslab == 3) return launch_conv3x3<64, 2, 3, 9>(p, pl.smem, grid, st);
+    return launch_conv3x3<64, 2, 2, 9>(p, pl.smem, grid, st);
+  }
+  if (pl.nslab == 3) return launch_conv3x3<128, 2, 3, 6>(p, pl.smem, grid, st);
+  return launch_conv3x3<128, 2, 2, 6>(p, pl.smem, grid, st);
+}
+
 }  // namespace
 
 // ================================================================================================
 extern "C" {
 
-int qt_version(void) { return 100; }
+int qt_version(void) { return 101; }
+void qt_set_conv3x3_enabled(int on) { g_use_conv3x3 = on != 0; }
 const char* qt_last_error(void) { return g_err; }
 int qt_take_timeout_flag(void) {
   unsigned int v = 0, z = 0;
@@ -269,6 +378,8 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 // ---- convolutions -----------------------------------------------------------------------------------
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
+  const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
+  if (pl.ok) return pl.num_m_tiles * pl.mt;
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));
@@ -288,6 +399,8 @@ int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y,
   p.flags = flags & (EPI_BIAS | EPI_RELU | EPI_STATS | EPI_OUT_F32);
   if ((p.flags & EPI_BIAS) && !bias) return fail("conv_fprop: QT_EPI_BIAS without bias");
   if ((p.flags & EPI_STATS) && !stats) return fail("conv_fprop: QT_EPI_STATS without stats buffer");
+  const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, p.flags);
+  if (pl.ok) return run_conv3x3(pl, d, d->in_c, d->out_c, x, wf, y, nullptr, stats, p.flags, false, S(stream));
   return run_kmajor(p, S(stream), ws, ws_bytes, 0);
 }
 
@@ -297,6 +410,12 @@ int qt_conv_dgrad(const qt_conv_desc* d, const void* dy, const void* wd, void* d
   const OutDims o = conv_out_dims(d);
   const int sd = d->stride_d, sh = d->stride_h, sw = d->stride_w;
   if (ilog2_exact(d->out_c) < 0 && d->k_d * d->k_h * d->k_w > 1) return fail("conv_dgrad: out_c must be a power of two");
+  {
+    const C3Plan pl = plan_conv3x3(d, d->out_c, d->in_c, accumulate ? EPI_ADDEND : 0);
+    if (pl.ok)
+      return run_conv3x3(pl, d, d->out_c, d->in_c, dy, wd, dx, accumulate ? dx : nullptr, nullptr, accumulate ? EPI_ADDEND : 0,
+                         true, S(stream));
+  }
   bool any_empty = false;
   // One launch per stride-parity class; for stride 1 there is exactly one.
   for (int pd = 0; pd < sd; ++pd)

@@ -44,11 +44,33 @@ def workspace(nbytes: int, device, tag="gemm") -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------- weights
+# Fused / foreach optimizers update parameters without bumping Tensor._version, so packed bf16 weight copies
+# are also invalidated by a global optimizer-step counter (hooked once, covers every torch.optim optimizer).
+_generation = 0
+
+
+def _on_optimizer_step(*_args, **_kw):
+    global _generation
+    _generation += 1
+
+
+def invalidate_packed_weights():
+    """Call after modifying parameters through a path that neither bumps `_version` nor is a torch optimizer."""
+    _on_optimizer_step()
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(_on_optimizer_step)
+except Exception as _e:  # pragma: no cover
+    raise RuntimeError("this torch build lacks register_optimizer_step_post_hook; weight caches cannot be kept fresh") from _e
+
+
 class _Packed:
     __slots__ = ("version", "ptr", "wf", "wd", "w8")
 
     def __init__(self):
-        self.version = -1
+        self.version = None
         self.ptr = 0
         self.wf = self.wd = self.w8 = None
 
@@ -83,8 +105,9 @@ def _entry(w: torch.Tensor) -> _Packed:
     if e is None:
         e = _Packed()
         _packed.set(w, e)
-    if e.version != w._version or e.ptr != w.data_ptr():
-        e.version, e.ptr = w._version, w.data_ptr()
+    ver = (w._version, _generation)
+    if e.version != ver or e.ptr != w.data_ptr():
+        e.version, e.ptr = ver, w.data_ptr()
         e.wf = e.wd = e.w8 = None
     return e
 

@@ -195,3 +195,24 @@ def test_dropout_training_runs_and_is_seeded(env):
     loss = F.cross_entropy(model(images.cuda(), numerical.cuda()), labels.cuda())
     loss.backward()
     assert all(torch.isfinite(q.grad).all() for q in model.parameters() if q.grad is not None)
+
+
+def test_weights_refresh_after_fused_adam_step(env):
+    """Fused Adam does not bump Tensor._version; the packed bf16 weight copies must still follow the update."""
+    O, M = env
+    p = O.make_params("quadtree", 8, seed=0)
+    images, numerical, labels = O.synthetic_batch(4, 77)
+    model = M.QuadtreeCNN(num_classes=8, dropout_rate=0.0)
+    M.load_oracle_params(model, p)
+    model = model.cuda().train()
+    opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-2, fused=True)
+    x, nf, y = images.cuda(), numerical.cuda(), labels.cuda()
+    before = model(x, nf).detach().clone()
+    F.cross_entropy(model(x, nf), y).backward()
+    opt.step()
+    after = model(x, nf).detach()
+    assert float((after - before).abs().max()) > 1e-3, "forward ignored the optimizer update (stale packed weights)"
+    # and it matches the oracle evaluated with the updated fp32 parameters
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = O.quadtree_forward(sd, x, nf, training=True)
+    assert float((after - ref).abs().max()) <= 4e-2 * float(ref.abs().max())
