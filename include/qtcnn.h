@@ -55,6 +55,8 @@ int qt_take_timeout_flag(void);
 /* Tuning/debug switch: 0 routes 3x3 stride-1 convolutions through the generic gather kernel instead of the
  * persistent input-reuse kernel (both are tcgen05 paths). */
 void qt_set_conv3x3_enabled(int on);
+/* Experimental pipeline-shape selection (key 0: weight-gradient kernel, key 1: K-major kernel; value 0 = default). */
+void qt_set_tuning(int key, int value);
 
 /* ---- layout / packing ------------------------------------------------------------------------- */
 /* images.to(device) feeding base_cnn.conv1 (QS/Quadtree_train.py:61, QS/models.py:222):

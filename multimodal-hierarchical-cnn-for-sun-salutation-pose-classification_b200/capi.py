@@ -72,6 +72,7 @@ _SIGNATURES = {
     "qt_last_error": (c_char_p, []),
     "qt_take_timeout_flag": (c_int, []),
     "qt_set_conv3x3_enabled": (None, [c_int]),
+    "qt_set_tuning": (None, [c_int, c_int]),
     "qt_stem_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),

@@ -29,7 +29,7 @@ struct Conv3x3Params {
   const __nv_bfloat16* b;   // weights [nout][wtaps][cin]
   void* out;                // dense NHWC output [N][H][W][nout] (bf16)
   const __nv_bfloat16* addend;
-  float* stats;             // [num_m_tiles * MT][2][nout]
+  float* stats;             // [gridDim.x][2][nout]: one running partial per persistent CTA
   int N, H, W, cin, nout, wtaps;
   int flags;
   int slabs;                // cin / 64
@@ -46,7 +46,7 @@ template <int BN, int MT, int NSLAB, int NB>
 struct C3Smem {
   static constexpr int kBTile = BN * 128;
   static constexpr int kBBytes = NB * kBTile;
-  static constexpr int kScratch = 2 * 4 * BN * 4;
+  static constexpr int kScratch = 2 * 4 * BN * 4 + 4 * 2 * BN * 4;  // cross-warp combine + running sums (<= 4 n-tiles)
   static constexpr int kBarBytes = 512;
   // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][barriers][slabs...]
 };
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem;
   float* scratch = reinterpret_cast<float*>(smem + L::kBBytes);
+  float* running = scratch + 2 * 4 * BN;  // [n_tile][2][BN] per-CTA BatchNorm partial sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBBytes + L::kScratch);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NSLAB;
@@ -238,9 +239,14 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
     // ================================================================= epilogue (warps 0-3)
     const int flags = p.flags;
     uint32_t tile_it = 0;
+    if (flags & EPI_STATS) {
+      for (int i = threadIdx.x; i < p.num_n_tiles * 2 * BN; i += kProducerThreads) running[i] = 0.f;
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
       const int m_tile = tile / p.num_n_tiles;
-      const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int n0 = n_tile * BN;
       const uint32_t ab = tile_it & 1;
       mbar_wait(&acc_full[ab], (tile_it >> 1) & 1);
       tc_fence_after();
@@ -313,19 +319,25 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
         }
         if (flags & EPI_STATS) {
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          const long long srow = static_cast<long long>(m_tile) * MT + u;
           for (int i = threadIdx.x; i < 2 * BN; i += kProducerThreads) {
             const int which = i / BN, col = i - which * BN;
-            if (n0 + col < p.nout) {
-              const float* sc = scratch + which * 4 * BN + col;
-              p.stats[(srow * 2 + which) * p.nout + n0 + col] = (sc[0] + sc[BN]) + (sc[2 * BN] + sc[3 * BN]);
-            }
+            const float* sc = scratch + which * 4 * BN + col;
+            running[(n_tile * 2 + which) * BN + col] += (sc[0] + sc[BN]) + (sc[2 * BN] + sc[3 * BN]);
           }
           asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
+    }
+    if (flags & EPI_STATS) {
+      // one deterministic partial row per CTA: [2][nout]
+      for (int i = threadIdx.x; i < p.num_n_tiles * 2 * BN; i += kProducerThreads) {
+        const int nt = i / (2 * BN), rem = i - nt * 2 * BN;
+        const int which = rem / BN, col = rem - which * BN;
+        if (nt * BN + col < p.nout)
+          p.stats[(static_cast<long long>(blockIdx.x) * 2 + which) * p.nout + nt * BN + col] = running[i];
+      }
     }
   }
   tc_fence_before();

@@ -198,6 +198,49 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
+// Same, reducing a small number of fp32 partial rows [T][2][C] directly (persistent conv kernels emit one row per CTA).
+__global__ void bn_finalize_rows_kernel(const float* __restrict__ partial, int T, int C, double count,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                        float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < T; ++t) {
+    s1 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
+    s2 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  scale_out[c] = g * invstd;
+  shift_out[c] = b - static_cast<float>(mean) * g * invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+__global__ void bn_bwd_finalize_rows_kernel(const float* __restrict__ partial, int T, int C, double count,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                            int eval_mode, float* __restrict__ c1, float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < T; ++t) {
+    s1 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
+    s2 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
+  }
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s1) : static_cast<float>(s1);
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(s2) : static_cast<float>(s2);
+  c1[c] = eval_mode ? 0.f : static_cast<float>(s1 / count);
+  c2[c] = eval_mode ? 0.f : static_cast<float>(s2 / count);
+}
 // Eval mode: scale/shift from running statistics.
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,

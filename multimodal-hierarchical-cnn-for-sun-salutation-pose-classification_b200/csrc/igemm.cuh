@@ -22,9 +22,11 @@ namespace qt {
 constexpr int kMaxTaps = 32;
 constexpr int kBM = 128;   // UMMA M (TMEM lanes)
 constexpr int kBK = 64;    // bf16 per k-block = one 128-byte swizzle row
-constexpr int kProducerThreads = 128;
+constexpr int kProducerThreads = 128;   // epilogue threads (warps 0-3); they also produce
 constexpr int kGemmThreads = 160;
-constexpr int kLag = 2;    // cp.async groups in flight before a stage is published
+constexpr int kGemmThreadsWide = 288;   // + warps 5-8 as extra producers
+// kLag (template parameter of the kernels) = cp.async groups in flight before a stage is published; the ring
+// needs STAGES - kLag - 1 >= 1 stages of slack or producer and MMA issuer serialise.
 
 enum : int {
   EPI_BIAS = 1,
@@ -149,8 +151,8 @@ struct KMajorSmem {
 // =============================================================================================
 // K-major kernel: fprop / dgrad / linear
 // =============================================================================================
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+template <int BN, int STAGES, int kLag, int NPW>
+__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
   using L = KMajorSmem<BN, STAGES>;
   constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -170,10 +172,13 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
   const int nit = kb_end - kb_begin;
 
+  constexpr int kNP = NPW * 32;          // producer threads
+  constexpr int kRowStep = NPW * 4;      // rows covered per pass (8 chunks per row)
+  constexpr int kARows = kBM / kRowStep; // A rows per producer thread
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], kProducerThreads);
+        mbar_init(&full_bar[s], kNP);
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(accum_bar, 1);
@@ -187,15 +192,15 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp != 4) {
     // ------------------------------------------------------------------ producer
-    const int t = threadIdx.x;
+    const int t = warp < 4 ? threadIdx.x : threadIdx.x - 32;
     const int chunk = t & 7;
     const int rbase = t >> 3;
     const uint32_t sw_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
-    RowCoord rc[8];
+    RowCoord rc[kARows];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) rc[i] = decompose_row(p, m0 + rbase + 16 * i, p.a_goff[g]);
+    for (int i = 0; i < kARows; ++i) rc[i] = decompose_row(p, m0 + rbase + kRowStep * i, p.a_goff[g]);
     const __nv_bfloat16* bptr = p.b + p.b_goff[g];
     const long long brow_stride = static_cast<long long>(p.wtaps) * p.cin;
 
@@ -214,19 +219,19 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid
       const uint32_t a_dst = smem_u32(stage) + rbase * 128 + sw_off;
       const uint32_t b_dst = smem_u32(stage + L::kABytes) + rbase * 128 + sw_off;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kARows; ++i) {
         const bool ok = tap_ok && rc[i].base >= 0 && static_cast<unsigned>(rc[i].cd + td) < static_cast<unsigned>(p.id) &&
                         static_cast<unsigned>(rc[i].ch + th) < static_cast<unsigned>(p.ih) &&
                         static_cast<unsigned>(rc[i].cw + tw) < static_cast<unsigned>(p.iw);
         const __nv_bfloat16* src = ok ? (p.a + rc[i].base + toff) : p.a;
-        cp_async16(a_dst + i * 16 * 128, src, ok ? 16u : 0u);
+        cp_async16(a_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
       }
 #pragma unroll
-      for (int i = 0; i < BN / 16; ++i) {
-        const int n = n0 + rbase + 16 * i;
+      for (int i = 0; i < BN / kRowStep; ++i) {
+        const int n = n0 + rbase + kRowStep * i;
         const bool ok = tap_ok && n < p.nout;
         const __nv_bfloat16* src = ok ? (bptr + n * brow_stride + woff) : bptr;
-        cp_async16(b_dst + i * 16 * 128, src, ok ? 16u : 0u);
+        cp_async16(b_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
       }
       cp_async_commit();
       if (it >= kLag) {
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_kmajor_kernel(const __grid
     fence_proxy_async_smem();
     for (int j = max(0, nit - kLag); j < nit; ++j) mbar_arrive(&full_bar[j % STAGES]);
   } else {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
     // warp-uniform control flow (descriptor math on the uniform datapath); lane 0 issues
     {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
@@ -405,8 +410,8 @@ struct WgradSmem {
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmParams p) {
+template <int BN, int STAGES, int kLag, int NPW>
+__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmParams p) {
   using L = WgradSmem<BN, STAGES>;
   constexpr uint32_t TCOLS = BN;
   static_assert(BN % 64 == 0, "wgrad BN must be a multiple of 64");
@@ -428,10 +433,13 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
   const int nit = kb_end - kb_begin;
   const int F = p.ntaps * p.cin;
 
+  constexpr int kNP = NPW * 32;
+  constexpr int kRowStep = NPW * 4;
+  constexpr int kPRows = 64 / kRowStep;  // pixel rows per producer thread and k-block
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], kProducerThreads);
+        mbar_init(&full_bar[s], kNP);
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(accum_bar, 1);
@@ -445,10 +453,10 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    const int t = threadIdx.x;
+  if (warp != 4) {
+    const int t = warp < 4 ? threadIdx.x : threadIdx.x - 32;
     const int chunk = t & 7;
-    const int rbase = t >> 3;  // pixel rows rbase + 16*i, i = 0..3
+    const int rbase = t >> 3;  // pixel rows rbase + kRowStep*i
     const uint32_t sw_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
     // Feature decode for the two A blocks handled by this thread's chunk (fixed per CTA).
     bool f_ok[2];
@@ -466,10 +474,10 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
     }
     const __nv_bfloat16* bptr = p.b + p.b_goff[g];
     // Pixel coordinates of this thread's four rows, advanced incrementally by 64 pixels per k-block.
-    int rn[4], rd[4], rh[4], rw[4];
+    int rn[kPRows], rd[kPRows], rh[kPRows], rw[kPRows];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int idx = kb_begin * 64 + rbase + 16 * i;
+    for (int i = 0; i < kPRows; ++i) {
+      int idx = kb_begin * 64 + rbase + kRowStep * i;
       rw[i] = idx % p.ow; idx /= p.ow;
       rh[i] = idx % p.oh; idx /= p.oh;
       rd[i] = idx % p.od;
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
       const uint32_t a_dst = smem_u32(stage) + rbase * 128 + sw_off;
       const uint32_t b_dst = smem_u32(stage + L::kABytes) + rbase * 128 + sw_off;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kPRows; ++i) {
         const bool row_ok = rn[i] < p.nb;
         const int cd = rd[i] * p.mult_d, ch = rh[i] * p.mult_h, cw = rw[i] * p.mult_w;
         const long long abase = p.a_goff[g] + rn[i] * p.av.sn + cd * p.av.sd + ch * p.av.sh + cw * p.av.sw;
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
                           static_cast<unsigned>(ch + f_th[j]) < static_cast<unsigned>(p.ih) &&
                           static_cast<unsigned>(cw + f_tw[j]) < static_cast<unsigned>(p.iw);
           const __nv_bfloat16* src = ok ? (p.a + abase + f_off[j]) : p.a;
-          cp_async16(a_dst + j * 8192 + i * 16 * 128, src, ok ? 16u : 0u);
+          cp_async16(a_dst + j * 8192 + i * kRowStep * 128, src, ok ? 16u : 0u);
         }
         // dy rows through the output view
         const long long drow = rn[i] * p.ov.sn + rd[i] * p.ov.sd + rh[i] * p.ov.sh + rw[i] * p.ov.sw;
@@ -502,7 +510,7 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_wgrad_kernel(const __grid_
           const int n = n0 + j * 64 + chunk * 8;
           const bool ok = row_ok && (n < p.nout);
           const __nv_bfloat16* src = ok ? (bptr + drow + n) : bptr;
-          cp_async16(b_dst + j * 8192 + i * 16 * 128, src, ok ? 16u : 0u);
+          cp_async16(b_dst + j * 8192 + i * kRowStep * 128, src, ok ? 16u : 0u);
         }
         // advance by 64 pixels (mixed-radix add with single carries)
         rw[i] += p.adv_w; if (rw[i] >= p.ow) { rw[i] -= p.ow; rh[i] += 1; }

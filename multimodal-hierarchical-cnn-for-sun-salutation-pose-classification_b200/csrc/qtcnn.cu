@@ -50,26 +50,28 @@ constexpr int kNumSMs = 148;
 // ------------------------------------------------------------------------------------------------
 // GEMM launch helpers
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [0] wgrad pipeline variant, [1] kmajor pipeline variant
+
+template <int BN, int STAGES, int LAG, int NPW>
 int launch_kmajor(const IgemmParams& p, dim3 grid, cudaStream_t st) {
   using L = KMajorSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(igemm_kmajor_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaFuncSetAttribute(igemm_kmajor_kernel<BN, STAGES, LAG, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     configured = true;
   }
-  igemm_kmajor_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, st>>>(p);
+  igemm_kmajor_kernel<BN, STAGES, LAG, NPW><<<grid, NPW == 8 ? kGemmThreadsWide : kGemmThreads, L::kTotal, st>>>(p);
   return cuda_status("igemm_kmajor_kernel");
 }
-template <int BN, int STAGES>
+template <int BN, int STAGES, int LAG, int NPW>
 int launch_wgrad(const IgemmParams& p, dim3 grid, cudaStream_t st) {
   using L = WgradSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(igemm_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaFuncSetAttribute(igemm_wgrad_kernel<BN, STAGES, LAG, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     configured = true;
   }
-  igemm_wgrad_kernel<BN, STAGES><<<grid, kGemmThreads, L::kTotal, st>>>(p);
+  igemm_wgrad_kernel<BN, STAGES, LAG, NPW><<<grid, NPW == 8 ? kGemmThreadsWide : kGemmThreads, L::kTotal, st>>>(p);
   return cuda_status("igemm_wgrad_kernel");
 }
 
@@ -104,7 +106,11 @@ int run_kmajor(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, long l
     p.flags = EPI_SPLITK;
   }
   dim3 grid(gx, gy, p.groups * ksplit);
-  int rc = (BN == 64) ? launch_kmajor<64, 4>(p, grid, st) : launch_kmajor<128, 3>(p, grid, st);
+  int rc;
+  // default: 8 producer warps, two CTAs per SM (measured best on B200, profiles/r01_conv_tuning.md)
+  if (g_tune[1] == 1) rc = (BN == 64) ? launch_kmajor<64, 8, 3, 8>(p, grid, st) : launch_kmajor<128, 6, 3, 8>(p, grid, st);
+  else if (g_tune[1] == 2) rc = (BN == 64) ? launch_kmajor<64, 4, 1, 4>(p, grid, st) : launch_kmajor<128, 3, 1, 4>(p, grid, st);
+  else rc = (BN == 64) ? launch_kmajor<64, 4, 1, 8>(p, grid, st) : launch_kmajor<128, 3, 1, 8>(p, grid, st);
   if (rc) return rc;
   if (ksplit > 1) {
     const long long total = static_cast<long long>(p.M) * p.nout;
@@ -178,7 +184,10 @@ int run_wgrad(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, float* 
     p.adv_n = r;
   }
   dim3 grid(gx, gy, p.groups * ksplit);
-  int rc = (BN == 64) ? launch_wgrad<64, 4>(p, grid, st) : launch_wgrad<128, 3>(p, grid, st);
+  int rc;
+  if (g_tune[0] == 1) rc = (BN == 64) ? launch_wgrad<64, 8, 3, 8>(p, grid, st) : launch_wgrad<128, 6, 3, 8>(p, grid, st);
+  else if (g_tune[0] == 2) rc = (BN == 64) ? launch_wgrad<64, 4, 1, 4>(p, grid, st) : launch_wgrad<128, 3, 1, 4>(p, grid, st);
+  else rc = (BN == 64) ? launch_wgrad<64, 4, 1, 8>(p, grid, st) : launch_wgrad<128, 3, 1, 8>(p, grid, st);
   if (rc) return rc;
   const long long total = static_cast<long long>(F) * p.nout;
   splitk_reduce_wgrad_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, st>>>(
@@ -256,7 +265,8 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   const int slab_bytes = 8 * pl.plane_stride;
   const int slabs = cin / 64;
   const int btile = pl.bn * 128;
-  const int fixed = 1024 + 2 * 4 * pl.bn * 4 + 512;
+  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + 512;
+  if ((nout + pl.bn - 1) / pl.bn > 4) return pl;
   const int budget = 227 * 1024;
   pl.num_m_tiles = static_cast<int>((V + bm - 1) / bm);
   pl.num_n_tiles = (nout + pl.bn - 1) / pl.bn;
@@ -330,6 +340,7 @@ extern "C" {
 
 int qt_version(void) { return 101; }
 void qt_set_conv3x3_enabled(int on) { g_use_conv3x3 = on != 0; }
+void qt_set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tune[key] = value; }
 const char* qt_last_error(void) { return g_err; }
 int qt_take_timeout_flag(void) {
   unsigned int v = 0, z = 0;
@@ -379,7 +390,7 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
-  if (pl.ok) return pl.num_m_tiles * pl.mt;
+  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; return tiles < kNumSMs ? tiles : kNumSMs; }
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));
@@ -602,7 +613,8 @@ int rowlane_block(int c) {  // threads per block for the (C/8 groups) x lanes ke
   if (lanes < 1) lanes = 1;
   return groups * lanes;
 }
-constexpr int kBwdBlocks = 148 * 4;
+constexpr int kBwdBlocks = 148 * 2;
+constexpr int kDirectRows = 320;  // partial-row counts a single finalize kernel reduces by itself
 }  // namespace
 
 size_t qt_bn_workspace_bytes(int c) {
@@ -623,6 +635,11 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
                    float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
                    qt_stream_t stream) {
   if (ws_bytes < static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double)) return fail("bn_finalize: workspace too small");
+  if (partial_rows <= kDirectRows) {
+    bn_finalize_rows_kernel<<<(c + 63) / 64, 64, 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps, momentum,
+                                                                 running_mean, running_var, mean, invstd, scale, shift);
+    return cuda_status("bn_finalize_rows");
+  }
   double* sums = static_cast<double*>(ws);
   int slices = 0;
   if (int rc = reduce_partials(partial, partial_rows, 2 * c, sums, &slices, S(stream))) return rc;
@@ -663,10 +680,9 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
       static_cast<const __nv_bfloat16*>(y), mean, invstd, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
-  int slices = 0;
-  if (int rc = reduce_partials(partial, blocks, 2 * c, sums, &slices, S(stream))) return rc;
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, static_cast<double>(m), dgamma, dbeta,
-                                                                  accumulate, eval_mode, c1, c2);
+  (void)sums;
+  bn_bwd_finalize_rows_kernel<<<(c + 63) / 64, 64, 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), dgamma, dbeta,
+                                                                   accumulate, eval_mode, c1, c2);
   if (int rc = cuda_status("bn_bwd_finalize")) return rc;
   const long long total8 = m * c / 8;
   bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(

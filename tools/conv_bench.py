@@ -45,11 +45,15 @@ def main():
     ap.add_argument("--v1", action="store_true", help="disable the persistent 3x3 kernel")
     ap.add_argument("--layers", default="", help="substring filter on layer names")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--tune", default="", help="key=value,... passed to qt_set_tuning")
     a = ap.parse_args()
     global ITERS
     ITERS = a.iters
     lib = C.lib()
     lib.qt_set_conv3x3_enabled(0 if a.v1 else 1)
+    for kv in filter(None, a.tune.split(",")):
+        k, v = kv.split("=")
+        lib.qt_set_tuning(int(k), int(v))
     n = a.batch
     st = C.stream()
     for name, cin, cout, h, w, k, s, p in LAYERS:
