@@ -67,6 +67,8 @@ int qt_nhwc_bf16_to_nchw_f32(const void* x, float* out, int n, int c, long long 
 /* fp32 parameter [cout][cin][taps] -> bf16 GEMM operands (forward [cout][taps][cin], dgrad [cin][taps][cout]). */
 int qt_wpack_fprop(const float* w, void* wf, int cout, int cin, int taps, qt_stream_t stream);
 int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_stream_t stream);
+/* both GEMM layouts from one read of the parameter (wd may be NULL). */
+int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream);
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream);
 int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
 
@@ -145,6 +147,16 @@ int qt_region_avgpool_fwd(const void* x, void* out, long long regions, int p, in
 int qt_region_avgpool_bwd(const void* dout, const void* x, void* dx, long long regions, int p, int c, long long ldo,
                           int relu_mask, qt_stream_t stream);
 
+/* MaxPool3d with kernel == stride, no padding (3dcnn/models.py:111-135) on NDHWC bf16. */
+int qt_maxpool3d_fwd(const void* x, void* out, void* argmax, int n, int d, int h, int w, int c, int kd, int kh, int kw,
+                     qt_stream_t stream);
+int qt_maxpool3d_bwd(const void* dout, const void* argmax, void* dx, int n, int d, int h, int w, int c, int kd, int kh,
+                     int kw, qt_stream_t stream);
+/* softmax-weighted sum of the 16 sub-quadrant vectors (attention gate, QS/models.py:86-90); fp32. */
+int qt_attn_pool_fwd(const float* x, const float* scores, float* wts, float* out, int b, int r, int c, qt_stream_t stream);
+int qt_attn_pool_bwd(const float* x, const float* wts, const float* dout, float* dx, float* dscores, int b, int r, int c,
+                     qt_stream_t stream);
+
 /* ---- small fp32 linears of the fusion head (numerical_mlp, classifier.3; QS/models.py:255-271) ------ */
 int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float* w, const float* bias, int b, int n,
                         int k, int relu, float drop_p, unsigned long long seed, float* out, long long ldo,
@@ -157,6 +169,8 @@ int qt_small_linear_bwd_dw(const void* dy, int dy_is_bf16, long long ldy, const 
                            qt_stream_t stream);
 int qt_relu_dropout(float* h, void* h16, long long n, float drop_p, unsigned long long seed, int relu,
                     qt_stream_t stream);
+int qt_relu_dropout_bwd(const float* dout, const float* act, float* dz, void* dz16, long long n, float drop_p,
+                        unsigned long long seed, int relu, qt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "qt_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_wpack_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_wpack_both": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_stem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "qt_conv_stat_rows": (c_int, [ctypes.POINTER(ConvDesc)]),
@@ -123,6 +124,12 @@ _SIGNATURES = {
     "qt_region_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_void_p]),
     "qt_region_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_int,
                                       c_void_p]),
+    "qt_maxpool3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "qt_maxpool3d_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "qt_attn_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_attn_pool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_small_linear_fwd": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_float, c_ulonglong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
     "qt_small_linear_bwd_dx": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p,
@@ -131,6 +138,8 @@ _SIGNATURES = {
     "qt_small_linear_bwd_dw": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_int, c_void_p]),
     "qt_relu_dropout": (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_ulonglong, c_int, c_void_p]),
+    "qt_relu_dropout_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_ulonglong, c_int,
+                                    c_void_p]),
 }
 
 

@@ -130,6 +130,35 @@ __global__ void wpack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* _
       wd[(static_cast<long long>(ci) * T + t) * Cout + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
   }
 }
+// Both layouts from one read of w. grid (ceil(Cin/32), ceil(Cout/32)), block 256, dynamic smem 32*32*T floats.
+__global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T) {
+  extern __shared__ float tile[];  // [32 co][32 ci][T], odd pitches in both directions (bank-conflict free)
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int TP = T | 1;
+  const int CP = 32 * TP + 1;
+  const int run = 32 * T;
+  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+    const int co = i / run, r = i - co * run;  // r = ci_local*T + t, contiguous in w for a fixed co
+    const int cil = r / T, t = r - cil * T;
+    float v = 0.f;
+    if (co0 + co < Cout && ci0 + cil < Cin) v = w[(static_cast<long long>(co0 + co) * Cin + ci0) * T + r];
+    tile[co * CP + cil * TP + t] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+    {  // wf[co][t][ci]: ci fastest
+      const int cil = i & 31, t = (i >> 5) % T, co = i / (32 * T);
+      if (co0 + co < Cout && ci0 + cil < Cin)
+        wf[(static_cast<long long>(co0 + co) * T + t) * Cin + ci0 + cil] = __float2bfloat16_rn(tile[co * CP + cil * TP + t]);
+    }
+    if (wd) {  // wd[ci][t][co]: co fastest
+      const int col = i & 31, t = (i >> 5) % T, cil = i / (32 * T);
+      if (co0 + col < Cout && ci0 + cil < Cin)
+        wd[(static_cast<long long>(ci0 + cil) * T + t) * Cout + co0 + col] = __float2bfloat16_rn(tile[col * CP + cil * TP + t]);
+    }
+  }
+}
 // Stem 7x7x3 filter -> [Cout][8 row-taps][32 = (s, c4)] with zero padding (s == 7, c == 3, r == 7).
 __global__ void wpack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin,
                                   int R, int S) {
@@ -158,14 +187,30 @@ __global__ void stem_wgrad_unpack_kernel(const float* __restrict__ g8, float* __
 // accumulation, fixed order => deterministic). Stage 1 reduces T -> S slices, stage 2 finishes.
 // ---------------------------------------------------------------------------------------------
 __global__ void colreduce_stage1_kernel(const float* __restrict__ in, int T, int K, int S, double* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  // grid (ceil(K/32), S), block (32, 8): slice s of the rows, 8 row lanes, fp64 combine in fixed order
+  __shared__ double sh[8][32];
+  const int k = blockIdx.x * 32 + threadIdx.x;
   const int s = blockIdx.y;
-  if (k >= K) return;
   const int per = (T + S - 1) / S;
   const int t0 = s * per, t1 = min(T, t0 + per);
   double acc = 0.0;
-  for (int t = t0; t < t1; ++t) acc += static_cast<double>(in[static_cast<long long>(t) * K + k]);
-  out[static_cast<long long>(s) * K + k] = acc;
+  if (k < K) {
+    float f = 0.f;
+    int cnt = 0;
+    for (int t = t0 + threadIdx.y; t < t1; t += 8) {
+      f += in[static_cast<long long>(t) * K + k];
+      if (++cnt == 16) { acc += f; f = 0.f; cnt = 0; }
+    }
+    acc += f;
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += sh[j][threadIdx.x];
+    out[static_cast<long long>(s) * K + k] = tot;
+  }
 }
 
 // BatchNorm finalize (train mode): sums[S][2][C] (double) over `count` rows per channel.
@@ -198,19 +243,40 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
-// Same, reducing a small number of fp32 partial rows [T][2][C] directly (persistent conv kernels emit one row per CTA).
+// Block (32 channels x 8 row lanes): per-channel sums of partial[T][2][C] (fp32 rows, fp64 combine, fixed order).
+__device__ __forceinline__ void reduce_rows_2(const float* __restrict__ partial, int T, int C, int c, int ry,
+                                              double& s1, double& s2) {
+  __shared__ double sh[2][8][32];
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+    float f1 = 0.f, f2 = 0.f;
+    int cnt = 0;
+    for (int t = ry; t < T; t += 8) {
+      f1 += partial[(static_cast<long long>(t) * 2 + 0) * C + c];
+      f2 += partial[(static_cast<long long>(t) * 2 + 1) * C + c];
+      if (++cnt == 16) { a1 += f1; a2 += f2; f1 = f2 = 0.f; cnt = 0; }  // bound the fp32 run length
+    }
+    a1 += f1; a2 += f2;
+  }
+  sh[0][ry][threadIdx.x] = a1;
+  sh[1][ry][threadIdx.x] = a2;
+  __syncthreads();
+  s1 = 0.0; s2 = 0.0;
+  if (ry == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += sh[0][j][threadIdx.x]; s2 += sh[1][j][threadIdx.x]; }
+  }
+}
+// BatchNorm finalize straight from fp32 partial rows [T][2][C]. grid = ceil(C/32), block = (32, 8).
 __global__ void bn_finalize_rows_kernel(const float* __restrict__ partial, int T, int C, double count,
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                         float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                         float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < T; ++t) {
-    s1 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
-    s2 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s1, s2;
+  reduce_rows_2(partial, T, C, c, threadIdx.y, s1, s2);
+  if (threadIdx.y != 0 || c >= C) return;
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -226,20 +292,25 @@ __global__ void bn_finalize_rows_kernel(const float* __restrict__ partial, int T
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
+// Also folds everything pass 2 needs into three per-channel coefficients:
+//   dy = g*is*(dz - c1 - (y - mu)*is*c2) = A*dz + B*y + K,  A = g*is, B = -g*is^2*c2, K = g*is*(mu*is*c2 - c1).
 __global__ void bn_bwd_finalize_rows_kernel(const float* __restrict__ partial, int T, int C, double count,
-                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                            int eval_mode, float* __restrict__ c1, float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < T; ++t) {
-    s1 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
-    s2 += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
-  }
+                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                            const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int accumulate, int eval_mode,
+                                            float* __restrict__ coef) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s1, s2;
+  reduce_rows_2(partial, T, C, c, threadIdx.y, s1, s2);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s1) : static_cast<float>(s1);
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(s2) : static_cast<float>(s2);
-  c1[c] = eval_mode ? 0.f : static_cast<float>(s1 / count);
-  c2[c] = eval_mode ? 0.f : static_cast<float>(s2 / count);
+  const double c1 = eval_mode ? 0.0 : s1 / count;
+  const double c2 = eval_mode ? 0.0 : s2 / count;
+  const double g = gamma ? gamma[c] : 1.0, is = invstd[c], mu = mean[c];
+  coef[c] = static_cast<float>(g * is);
+  coef[C + c] = static_cast<float>(-g * is * is * c2);
+  coef[2 * C + c] = static_cast<float>(g * is * (mu * is * c2 - c1));
 }
 // Eval mode: scale/shift from running statistics.
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -327,16 +398,35 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
     float mu[8], is[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
-    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
+    const long long step = static_cast<long long>(gridDim.x) * lanes;
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += 2 * step) {
+      // two rows in flight per iteration (six independent 16-byte loads)
+      const long long r2 = r + step;
+      const bool has2 = r2 < M;
+      const uint4 qd = ld_nc16(dout + r * C + cg * 8), qv = ld_nc16(y + r * C + cg * 8);
+      uint4 qa = make_uint4(0, 0, 0, 0), qd2 = qa, qv2 = qa, qa2 = qa;
+      if (act) qa = ld_nc16(act + r * C + cg * 8);
+      if (has2) {
+        qd2 = ld_nc16(dout + r2 * C + cg * 8);
+        qv2 = ld_nc16(y + r2 * C + cg * 8);
+        if (act) qa2 = ld_nc16(act + r2 * C + cg * 8);
+      }
       float d[8], a[8], v[8];
-      unpack8(ld_nc16(dout + r * C + cg * 8), d);
-      unpack8(ld_nc16(y + r * C + cg * 8), v);
-      if (act) unpack8(ld_nc16(act + r * C + cg * 8), a);
+      unpack8(qd, d); unpack8(qv, v); unpack8(qa, a);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float dz = (act && !(a[e] > 0.f)) ? 0.f : d[e];
         s1[e] += dz;
         s2[e] += dz * (v[e] - mu[e]) * is[e];
+      }
+      if (has2) {
+        unpack8(qd2, d); unpack8(qv2, v); unpack8(qa2, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dz = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+          s1[e] += dz;
+          s2[e] += dz * (v[e] - mu[e]) * is[e];
+        }
       }
     }
 #pragma unroll
@@ -370,33 +460,34 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int S, i
   c1[c] = eval_mode ? 0.f : static_cast<float>(s1 / count);
   c2[c] = eval_mode ? 0.f : static_cast<float>(s2 / count);
 }
-// Pass 2: dy = gamma*invstd * (dz - c1 - xhat*c2); optionally also writes dz (gradient of the
-// residual/identity branch).
+// Pass 2: dy = A[c]*dz + B[c]*y + K[c] (coef = [A | B | K], see bn_bwd_finalize_rows_kernel); optionally also
+// writes dz (gradient of the residual/identity branch).
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
-                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ c1, const float* __restrict__ c2,
+                                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                     __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dz_out,
                                     long long total8, int C) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>((i * 8) % C);
-    float d[8], a[8], v[8], o[8], z[8];
+    float d[8], a[8], v[8], o[8];
     unpack8(ld_nc16(dout + i * 8), d);
     unpack8(ld_nc16(y + i * 8), v);
     if (act) unpack8(ld_nc16(act + i * 8), a);
+    float ca[8], cb[8], ck[8];
+    *reinterpret_cast<float4*>(ca) = __ldg(reinterpret_cast<const float4*>(coef + c0));
+    *reinterpret_cast<float4*>(ca + 4) = __ldg(reinterpret_cast<const float4*>(coef + c0 + 4));
+    *reinterpret_cast<float4*>(cb) = __ldg(reinterpret_cast<const float4*>(coef + C + c0));
+    *reinterpret_cast<float4*>(cb + 4) = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + 4));
+    *reinterpret_cast<float4*>(ck) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0));
+    *reinterpret_cast<float4*>(ck + 4) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
       const float dzv = (act && !(a[e] > 0.f)) ? 0.f : d[e];
-      const float is = __ldg(invstd + c);
-      const float xhat = (v[e] - __ldg(mean + c)) * is;
-      const float g = gamma ? __ldg(gamma + c) : 1.f;
-      o[e] = g * is * (dzv - __ldg(c1 + c) - xhat * __ldg(c2 + c));
-      z[e] = dzv;
+      o[e] = fmaf(ca[e], dzv, fmaf(cb[e], v[e], ck[e]));
+      d[e] = dzv;
     }
     *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
-    if (dz_out) *reinterpret_cast<uint4*>(dz_out + i * 8) = pack8(z);
+    if (dz_out) *reinterpret_cast<uint4*>(dz_out + i * 8) = pack8(d);
   }
 }
 
@@ -648,6 +739,119 @@ __global__ void region_avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout
 }
 
 // ---------------------------------------------------------------------------------------------
+// MaxPool3d with kernel == stride == (kd, kh, kw), no padding, floor mode (3dcnn/models.py:111-135) on NDHWC
+// bf16, int8 arg-max code = (dz*kh + dy)*kw + dx (first maximum in that order). C % 8 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool3d_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                     signed char* __restrict__ argmax, int N, int D, int H, int W, int C, int kd, int kh,
+                                     int kw) {
+  const int Do = D / kd, Ho = H / kh, Wo = W / kw, groups = C / 8;
+  const long long total = static_cast<long long>(N) * Do * Ho * Wo * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int cg = r % groups; r /= groups;
+    const int wo = r % Wo; r /= Wo;
+    const int ho = r % Ho; r /= Ho;
+    const int dd = r % Do;
+    const int n = r / Do;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    int code = 0;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < kh; ++b)
+        for (int c = 0; c < kw; ++c, ++code) {
+          float f[8];
+          unpack8(ld_nc16(x + ((((static_cast<long long>(n) * D + dd * kd + a) * H + ho * kh + b) * W + wo * kw + c) * C + cg * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (f[e] > best[e] || code == 0) { best[e] = f[e]; bi[e] = code; }
+        }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    if (argmax) {
+      uint2 pk;
+      pk.x = (bi[0] & 0xff) | ((bi[1] & 0xff) << 8) | ((bi[2] & 0xff) << 16) | ((bi[3] & 0xff) << 24);
+      pk.y = (bi[4] & 0xff) | ((bi[5] & 0xff) << 8) | ((bi[6] & 0xff) << 16) | ((bi[7] & 0xff) << 24);
+      *reinterpret_cast<uint2*>(argmax + i * 8) = pk;
+    }
+  }
+}
+__global__ void maxpool3d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const signed char* __restrict__ argmax,
+                                     __nv_bfloat16* __restrict__ dx, int N, int D, int H, int W, int C, int kd, int kh,
+                                     int kw) {
+  const int Do = D / kd, Ho = H / kh, Wo = W / kw, groups = C / 8;
+  const long long total = static_cast<long long>(N) * D * H * W * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int cg = r % groups; r /= groups;
+    const int w = r % W; r /= W;
+    const int h = r % H; r /= H;
+    const int d = r % D;
+    const int n = r / D;
+    float acc[8] = {0};
+    const int dd = d / kd, ho = h / kh, wo = w / kw;
+    if (dd < Do && ho < Ho && wo < Wo) {
+      const int code = ((d - dd * kd) * kh + (h - ho * kh)) * kw + (w - wo * kw);
+      const long long o = ((((static_cast<long long>(n) * Do + dd) * Ho + ho) * Wo + wo) * groups + cg) * 8;
+      const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
+      float g[8];
+      unpack8(ld_nc16(dout + o), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int a = (e < 4 ? (pk.x >> (8 * e)) : (pk.y >> (8 * (e - 4)))) & 0xff;
+        if (a == code) acc[e] = g[e];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention pooling over R region vectors (AttentionHierarchicalCNN, QS/models.py:86-90):
+//   w = softmax(scores[b, :]); out[b, :] = sum_i w_i * x[b, i, :].  x [B][R][C] fp32, scores [B][R] fp32.
+// One block per sample, C threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scores, float* __restrict__ wts,
+                                     float* __restrict__ out, int R, int C) {
+  const int b = blockIdx.x;
+  float m = -INFINITY;
+  for (int i = 0; i < R; ++i) m = fmaxf(m, scores[b * R + i]);
+  float den = 0.f;
+  for (int i = 0; i < R; ++i) den += expf(scores[b * R + i] - m);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < R; ++i) acc += (expf(scores[b * R + i] - m) / den) * x[(static_cast<long long>(b) * R + i) * C + c];
+    out[static_cast<long long>(b) * C + c] = acc;
+  }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) wts[b * R + i] = expf(scores[b * R + i] - m) / den;
+}
+// dx[b,i,c] = w_i*dout[c];  dscore_i = w_i * (t_i - sum_j w_j t_j), t_i = x_i . dout.  Block per sample, 32*k threads.
+__global__ void attn_pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wts, const float* __restrict__ dout,
+                                     float* __restrict__ dx, float* __restrict__ dscores, int R, int C) {
+  extern __shared__ float t[];  // [R]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wrp; i < R; i += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc += x[(static_cast<long long>(b) * R + i) * C + c] * dout[static_cast<long long>(b) * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) t[i] = acc;
+  }
+  __syncthreads();
+  float mean = 0.f;
+  for (int j = 0; j < R; ++j) mean += wts[b * R + j] * t[j];
+  for (int i = threadIdx.x; i < R; i += blockDim.x) dscores[b * R + i] = wts[b * R + i] * (t[i] - mean);
+  for (int k = threadIdx.x; k < R * C; k += blockDim.x) {
+    const int i = k / C, c = k - i * C;
+    dx[static_cast<long long>(b) * R * C + k] = wts[b * R + i] * dout[static_cast<long long>(b) * C + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small fp32 linear layers of the fusion head (numerical MLP 47->94->256, classifier.3 2688->nc).
 // One warp per output element; inputs fp32 or bf16, fp32 weights and accumulation.
 // ---------------------------------------------------------------------------------------------
@@ -701,23 +905,40 @@ __global__ void small_linear_bwd_dx_kernel(const TDy* __restrict__ dy, long long
   if (dx) dx[b * ldx + k] = acc;
   if (dx16) dx16[b * ldx16 + k] = __float2bfloat16_rn(acc);
 }
-// dw[n][k] (+)= sum_b dy[b][n] * x[b][k]; db[n] (+)= sum_b dy[b][n] (k == 0 thread).
+// dw[n][k] (+)= sum_b dy[b][n] * x[b][k]; db[n] (+)= sum_b dy[b][n]. Block (32 k, 8 batch lanes) per n:
+// loads of x are coalesced along k, the batch is split over 8 lanes and combined through shared memory.
 template <typename TDy, typename TX>
 __global__ void small_linear_bwd_dw_kernel(const TDy* __restrict__ dy, long long ldy, const TX* __restrict__ x,
                                            long long ldx, int B, int N, int K, float* __restrict__ dw,
                                            float* __restrict__ db, int accumulate) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(N) * K) return;
-  const int k = i % K;
-  const int n = i / K;
+  __shared__ float sh[8][33];
+  __shared__ float shb[8];
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f, accb = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = threadIdx.y; b < B; b += 8) {
     const float d = ld_as_float<TDy>(dy + b * ldy + n);
-    acc = fmaf(d, ld_as_float<TX>(x + b * ldx + k), acc);
+    if (k < K) acc = fmaf(d, ld_as_float<TX>(x + b * ldx + k), acc);
     accb += d;
   }
-  dw[i] = accumulate ? dw[i] + acc : acc;
-  if (db && k == 0) db[n] = accumulate ? db[n] + accb : accb;
+  sh[threadIdx.y][threadIdx.x] = acc;
+  if (threadIdx.x == 0) shb[threadIdx.y] = accb;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += sh[j][threadIdx.x];
+    if (k < K) {
+      const long long i = static_cast<long long>(n) * K + k;
+      dw[i] = accumulate ? dw[i] + tot : tot;
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+      float tb = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tb += shb[j];
+      db[n] = accumulate ? db[n] + tb : tb;
+    }
+  }
 }
 
 // Elementwise helpers on dense tensors.
@@ -748,6 +969,20 @@ __global__ void relu_dropout_kernel(float* __restrict__ h, __nv_bfloat16* __rest
     v *= dropout_scale(seed, static_cast<uint32_t>(i), drop_p);
     h[i] = v;
     if (h16) h16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dz = dout * 1[act > 0] * dropout_scale (act = stored relu/dropout output): backward of relu_dropout_kernel.
+__global__ void relu_dropout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ act, float* __restrict__ dz,
+                                        __nv_bfloat16* __restrict__ dz16, long long total, float drop_p,
+                                        unsigned long long seed, int relu) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = dout[i];
+    if (relu && !(act[i] > 0.f)) v = 0.f;
+    else v *= dropout_scale(seed, static_cast<uint32_t>(i), drop_p);
+    if (dz) dz[i] = v;
+    if (dz16) dz16[i] = __float2bfloat16_rn(v);
   }
 }
 

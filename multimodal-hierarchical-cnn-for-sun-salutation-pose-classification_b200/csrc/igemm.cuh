@@ -600,20 +600,34 @@ __global__ void splitk_reduce_rows_kernel(const float* __restrict__ ws, int nspl
   else reinterpret_cast<__nv_bfloat16*>(out)[m * ldo + n] = __float2bfloat16_rn(acc);
 }
 
-// Weight-gradient result: ws[z][f = tap*cin + c][n] -> grad[n][c_out_index][tap_out_index] in the
-// PyTorch parameter layout [nout][cin_real][ntaps_real]; taps/channels outside the real tensor
-// (padding used by the stem packing) are dropped through the two index maps. accumulate != 0 adds.
+// Weight-gradient result: ws[z][f = tap*cin + c][n] -> grad[n][c][tap] (PyTorch parameter layout
+// [nout][cin][ntaps]). The nsplit-fold read dominates, so it is what gets coalesced and parallelised:
+// grid (ceil(cin/32), ceil(N/32), ntaps), block 256 = 8 warps x 32 lanes; a warp owns 4 channel rows, lanes run
+// along n (128-byte rows of the workspace), four splits are in flight per thread. accumulate != 0 adds.
 __global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsplit, int F, int N, int Mpad, int Npad,
                                            int cin, int ntaps, float* __restrict__ grad, int accumulate) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(F) * N) return;
-  const int n = idx % N;
-  const int f = idx / N;
-  const int tap = f / cin, c = f - tap * cin;
-  float acc = 0.f;
-  for (int z = 0; z < nsplit; ++z) acc += ws[(static_cast<long long>(z) * Mpad + f) * Npad + n];
-  float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
-  *dst = accumulate ? (*dst + acc) : acc;
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int n = n0 + lane;
+  const long long zstride = static_cast<long long>(Mpad) * Npad;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + wrp * 4 + j;
+    if (c >= cin || n >= N) continue;
+    const float* src = ws + (static_cast<long long>(tap) * cin + c) * Npad + n;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= nsplit; z += 4) {
+      a0 += src[(z + 0) * zstride];
+      a1 += src[(z + 1) * zstride];
+      a2 += src[(z + 2) * zstride];
+      a3 += src[(z + 3) * zstride];
+    }
+    for (; z < nsplit; ++z) a0 += src[z * zstride];
+    const float acc = (a0 + a1) + (a2 + a3);
+    float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
+    *dst = accumulate ? (*dst + acc) : acc;
+  }
 }
 
 }  // namespace qt

@@ -189,9 +189,11 @@ int run_wgrad(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, float* 
   else if (g_tune[0] == 2) rc = (BN == 64) ? launch_wgrad<64, 4, 1, 4>(p, grid, st) : launch_wgrad<128, 3, 1, 4>(p, grid, st);
   else rc = (BN == 64) ? launch_wgrad<64, 4, 1, 8>(p, grid, st) : launch_wgrad<128, 3, 1, 8>(p, grid, st);
   if (rc) return rc;
-  const long long total = static_cast<long long>(F) * p.nout;
-  splitk_reduce_wgrad_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, st>>>(
-      p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad, cin_real, taps_real, dw, accumulate);
+  {
+    dim3 rgrid((cin_real + 31) / 32, (p.nout + 31) / 32, taps_real);
+    splitk_reduce_wgrad_kernel<<<rgrid, 256, 0, st>>>(p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad,
+                                                          cin_real, taps_real, dw, accumulate);
+  }
   return cuda_status("splitk_reduce_wgrad_kernel");
 }
 
@@ -375,6 +377,19 @@ int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_str
   dim3 grid((cin + 31) / 32, (cout + 31) / 32, taps), block(32, 8);
   wpack_dgrad_kernel<<<grid, block, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), cout, cin, taps);
   return cuda_status("wpack_dgrad");
+}
+int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream) {
+  if (taps > 32) return fail("wpack_both: too many taps");
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+  const size_t smem = static_cast<size_t>(32) * (32 * (taps | 1) + 1) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wpack_both_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 33 + 1) * 4);
+    configured = true;
+  }
+  wpack_both_kernel<<<grid, 256, smem, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), cout, cin,
+                                                  taps);
+  return cuda_status("wpack_both");
 }
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream) {
   if (cin > 4 || r > 8 || s > 8) return fail("wpack_stem: filter does not fit the 8x(8x4) packing");
@@ -602,8 +617,8 @@ constexpr int kRedSlices = 64;
 int reduce_partials(const float* partial, int rows, int K, double* sums, int* slices, cudaStream_t st) {
   int s = rows < kRedSlices ? rows : kRedSlices;
   if (s < 1) s = 1;
-  dim3 grid((K + 127) / 128, s);
-  colreduce_stage1_kernel<<<grid, 128, 0, st>>>(partial, rows, K, s, sums);
+  dim3 grid((K + 31) / 32, s);
+  colreduce_stage1_kernel<<<grid, dim3(32, 8), 0, st>>>(partial, rows, K, s, sums);
   *slices = s;
   return cuda_status("colreduce_stage1");
 }
@@ -613,14 +628,14 @@ int rowlane_block(int c) {  // threads per block for the (C/8 groups) x lanes ke
   if (lanes < 1) lanes = 1;
   return groups * lanes;
 }
-constexpr int kBwdBlocks = 148 * 2;
-constexpr int kDirectRows = 320;  // partial-row counts a single finalize kernel reduces by itself
+constexpr int kBwdBlocks = 148 * 4;
+constexpr int kDirectRows = 640;  // partial-row counts a single finalize kernel reduces by itself
 }  // namespace
 
 size_t qt_bn_workspace_bytes(int c) {
   // stage-1 sums (double) + per-block partials of the backward reduction + c1/c2
   return static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double) + static_cast<size_t>(kBwdBlocks) * 2 * c * sizeof(float) +
-         2 * static_cast<size_t>(c) * sizeof(float) + 256;
+         3 * static_cast<size_t>(c) * sizeof(float) + 256;
 }
 int qt_bn_stats(const void* y, long long m, int c, float* partial, int partial_rows, qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_stats: c must be a multiple of 8 and <= 2048");
@@ -636,8 +651,9 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
                    qt_stream_t stream) {
   if (ws_bytes < static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double)) return fail("bn_finalize: workspace too small");
   if (partial_rows <= kDirectRows) {
-    bn_finalize_rows_kernel<<<(c + 63) / 64, 64, 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps, momentum,
-                                                                 running_mean, running_var, mean, invstd, scale, shift);
+    bn_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 8), 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps,
+                                                                          momentum, running_mean, running_var, mean, invstd,
+                                                                          scale, shift);
     return cuda_status("bn_finalize_rows");
   }
   double* sums = static_cast<double*>(ws);
@@ -670,8 +686,7 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_backward: workspace too small");
   double* sums = static_cast<double*>(ws);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
-  float* c1 = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;
-  float* c2 = c1 + c;
+  float* coef = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;  // [A | B | K]
   const int block = rowlane_block(c);
   const int lanes = block / (c / 8);
   long long want = (m + lanes - 1) / lanes;
@@ -681,14 +696,15 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
       static_cast<const __nv_bfloat16*>(y), mean, invstd, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
   (void)sums;
-  bn_bwd_finalize_rows_kernel<<<(c + 63) / 64, 64, 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), dgamma, dbeta,
-                                                                   accumulate, eval_mode, c1, c2);
+  bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 8), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
+                                                                            invstd, gamma, dgamma, dbeta, accumulate, eval_mode,
+                                                                            coef);
   if (int rc = cuda_status("bn_bwd_finalize")) return rc;
   const long long total8 = m * c / 8;
   bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
-      static_cast<const __nv_bfloat16*>(y), mean, invstd, gamma, c1, c2, static_cast<__nv_bfloat16*>(dy),
-      static_cast<__nv_bfloat16*>(dz_out), total8, c);
+      static_cast<const __nv_bfloat16*>(y), coef, static_cast<__nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dz_out), total8,
+      c);
   return cuda_status("bn_bwd_apply");
 }
 int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream) {
@@ -788,6 +804,34 @@ int qt_region_avgpool_bwd(const void* dout, const void* x, void* dx, long long r
   return cuda_status("region_avgpool_bwd");
 }
 
+int qt_maxpool3d_fwd(const void* x, void* out, void* argmax, int n, int d, int h, int w, int c, int kd, int kh, int kw,
+                     qt_stream_t stream) {
+  if (c % 8) return fail("maxpool3d: c must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * (d / kd) * (h / kh) * (w / kw) * (c / 8);
+  maxpool3d_fwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                    static_cast<__nv_bfloat16*>(out),
+                                                                    static_cast<signed char*>(argmax), n, d, h, w, c, kd, kh, kw);
+  return cuda_status("maxpool3d_fwd");
+}
+int qt_maxpool3d_bwd(const void* dout, const void* argmax, void* dx, int n, int d, int h, int w, int c, int kd, int kh,
+                     int kw, qt_stream_t stream) {
+  if (c % 8) return fail("maxpool3d: c must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * d * h * w * (c / 8);
+  maxpool3d_bwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                                    static_cast<const signed char*>(argmax),
+                                                                    static_cast<__nv_bfloat16*>(dx), n, d, h, w, c, kd, kh, kw);
+  return cuda_status("maxpool3d_bwd");
+}
+int qt_attn_pool_fwd(const float* x, const float* scores, float* wts, float* out, int b, int r, int c, qt_stream_t stream) {
+  attn_pool_fwd_kernel<<<b, 64, 0, S(stream)>>>(x, scores, wts, out, r, c);
+  return cuda_status("attn_pool_fwd");
+}
+int qt_attn_pool_bwd(const float* x, const float* wts, const float* dout, float* dx, float* dscores, int b, int r, int c,
+                     qt_stream_t stream) {
+  attn_pool_bwd_kernel<<<b, 128, r * sizeof(float), S(stream)>>>(x, wts, dout, dx, dscores, r, c);
+  return cuda_status("attn_pool_bwd");
+}
+
 // ---- small linears ------------------------------------------------------------------------------------------
 int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float* w, const float* bias, int b, int n,
                         int k, int relu, float drop_p, unsigned long long seed, float* out, long long ldo,
@@ -822,22 +866,22 @@ int qt_small_linear_bwd_dx(const void* dy, int dy_is_bf16, long long ldy, const 
 int qt_small_linear_bwd_dw(const void* dy, int dy_is_bf16, long long ldy, const void* x, int x_is_bf16,
                            long long ldx, int b, int n, int k, float* dw, float* db, int accumulate,
                            qt_stream_t stream) {
-  const long long total = static_cast<long long>(n) * k;
-  const int grid = static_cast<int>((total + 255) / 256);
+  const dim3 grid((k + 31) / 32, n);
+  const dim3 blk(32, 8);
   cudaStream_t st = S(stream);
   if (dy_is_bf16 && x_is_bf16)
-    small_linear_bwd_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+    small_linear_bwd_dw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, blk, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dy), ldy, static_cast<const __nv_bfloat16*>(x), ldx, b, n, k, dw, db, accumulate);
   else if (dy_is_bf16)
-    small_linear_bwd_dw_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ldy,
+    small_linear_bwd_dw_kernel<__nv_bfloat16, float><<<grid, blk, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ldy,
                                                                           static_cast<const float*>(x), ldx, b, n, k, dw, db,
                                                                           accumulate);
   else if (x_is_bf16)
-    small_linear_bwd_dw_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), ldy,
+    small_linear_bwd_dw_kernel<float, __nv_bfloat16><<<grid, blk, 0, st>>>(static_cast<const float*>(dy), ldy,
                                                                           static_cast<const __nv_bfloat16*>(x), ldx, b, n, k,
                                                                           dw, db, accumulate);
   else
-    small_linear_bwd_dw_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), ldy,
+    small_linear_bwd_dw_kernel<float, float><<<grid, blk, 0, st>>>(static_cast<const float*>(dy), ldy,
                                                                   static_cast<const float*>(x), ldx, b, n, k, dw, db,
                                                                   accumulate);
   return cuda_status("small_linear_bwd_dw");
@@ -846,6 +890,13 @@ int qt_relu_dropout(float* h, void* h16, long long n, float drop_p, unsigned lon
                     qt_stream_t stream) {
   relu_dropout_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(h, static_cast<__nv_bfloat16*>(h16), n, drop_p, seed, relu);
   return cuda_status("relu_dropout");
+}
+
+int qt_relu_dropout_bwd(const float* dout, const float* act, float* dz, void* dz16, long long n, float drop_p,
+                        unsigned long long seed, int relu, qt_stream_t stream) {
+  relu_dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(dout, act, dz, static_cast<__nv_bfloat16*>(dz16), n, drop_p, seed,
+                                                                  relu);
+  return cuda_status("relu_dropout_bwd");
 }
 
 }  // extern "C"

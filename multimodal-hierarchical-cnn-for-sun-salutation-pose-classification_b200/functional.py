@@ -1,0 +1,344 @@
+"""Composable autograd Functions over the C ABI, used by the level-2 (hierarchical / attention), plain-ResNet and
+3-D model mirrors. Each Function is one reference operator group with its exact backward; tensors crossing
+Function boundaries are either channels-last bf16 maps or small fp32 / bf16 feature matrices."""
+from __future__ import annotations
+
+import torch
+
+from . import capi, ops
+from .capi import check, ptr, stream
+from .ops import BF16, L
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Region convolution + ReLU + AdaptiveAvgPool2d((1,1)) over the quadtree regions of a feature map
+# (Quadtree_from scratch/models.py:21-30, 60-79): level 1 = the 4 quadrants, level 2 = the 16 sub-quadrants
+# (quadrant-major, each TL,TR,BL,BR). Zero padding is per region, as in the reference (views are convolved
+# separately there).
+# ------------------------------------------------------------------------------------------------------------
+def _region_descs(n, H, W, cin, cout, level):
+    """One grouped (4-view) conv descriptor per parent region; outputs are region-major [G][n][qh][qw][cout]."""
+    key = ("regions", n, H, W, cin, cout, level)
+    cached = ops._desc_cache.get(key)
+    if cached is not None:
+        return cached
+    if H % (2 * level) or W % (2 * level):
+        raise RuntimeError("region conv: feature-map size must divide evenly into the quadtree level")
+    parents = [(0, 0, H, W)] if level == 1 else [(0, 0, H // 2, W // 2), (0, W // 2, H // 2, W // 2),
+                                                 (H // 2, 0, H // 2, W // 2), (H // 2, W // 2, H // 2, W // 2)]
+    descs = []
+    for ri, (h0, w0, hs, ws) in enumerate(parents):
+        qh, qw = hs // 2, ws // 2
+        xs = (H * W * cin, 0, W * cin, cin)
+        base = (h0 * W + w0) * cin
+        xoff = (base, base + qw * cin, base + qh * W * cin, base + qh * W * cin + qw * cin)
+        yoff = tuple((ri * 4 + q) * n * qh * qw * cout for q in range(4))
+        descs.append(capi.conv_desc(n, (1, qh, qw), cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1), x_stride=xs, groups=4,
+                                    x_group_off=xoff, y_group_off=yoff))
+    out = (descs, 4 * len(parents), parents[0][2] // 2, parents[0][3] // 2)
+    ops._desc_cache[key] = out
+    return out
+
+
+class RegionConvPool(torch.autograd.Function):
+    """pooled[g, b, :] = mean_{pixels}( relu(conv3x3(region_g(base)) + bias) ) -> bf16 [G, B, cout]."""
+
+    @staticmethod
+    def forward(ctx, base, w, b, level):
+        xb = ops.as_nhwc(base)
+        n, H, W, cin = xb.shape
+        cout = w.shape[0]
+        descs, G, qh, qw = _region_descs(n, H, W, cin, cout, level)
+        y = torch.empty(G, n, qh, qw, cout, device=xb.device, dtype=BF16)
+        wf = ops.packed_fprop(w)
+        for d in descs:
+            ops.conv_fprop(d, xb, wf, y, bias=b.detach(), relu=True)
+        pooled = torch.empty(G * n, cout, device=xb.device, dtype=BF16)
+        check(L().qt_region_avgpool_fwd(ptr(y), ptr(pooled), G * n, qh * qw, cout, cout, stream()), "region_avgpool_fwd")
+        ops._count()
+        if any(ctx.needs_input_grad):
+            ctx.saved = (xb, y, w, descs)
+            ctx.dims = (G, n, qh, qw, cout)
+        return pooled.view(G, n, cout)
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        xb, y, w, descs = ctx.saved
+        G, n, qh, qw, cout = ctx.dims
+        dp = dpooled.to(BF16).contiguous()
+        dy = torch.empty_like(y)
+        check(L().qt_region_avgpool_bwd(ptr(dp), ptr(y), ptr(dy), G * n, qh * qw, cout, cout, 1, stream()), "region_avgpool_bwd")
+        ops._count()
+        dw = db = dbase = None
+        if ctx.needs_input_grad[2]:
+            db = torch.empty(cout, device=xb.device)
+            ops.colsum(dy.view(-1, cout), db)
+        if ctx.needs_input_grad[1]:
+            dw = ops.grad_out(w)
+            for i, d in enumerate(descs):
+                ops.conv_wgrad(d, xb, dy, dw, accumulate=i > 0)
+        if ctx.needs_input_grad[0]:
+            dxb = torch.empty_like(xb)
+            wd = ops.packed_dgrad(w)
+            for d in descs:
+                ops.conv_dgrad(d, dy, wd, dxb)
+            dbase = ops.as_nchw_view(dxb)
+        return dbase, dw, db, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Linear layers
+# ------------------------------------------------------------------------------------------------------------
+class SmallLinear(torch.autograd.Function):
+    """fp32 nn.Linear (+ReLU, +Dropout) for the narrow layers: out = drop(relu(x W^T + b)), fp32 [M, N]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, p_drop, training):
+        lead = x.shape[:-1]
+        k = x.shape[-1]
+        x2 = x.detach().reshape(-1, k)
+        is16 = x2.dtype == BF16
+        if not is16:
+            x2 = x2.float()
+        x2 = x2.contiguous()
+        m, n = x2.shape[0], w.shape[0]
+        p = float(p_drop) if training else 0.0
+        seed = ops.new_seed() if p > 0 else 0
+        out = torch.empty(m, n, device=x2.device)
+        check(L().qt_small_linear_fwd(ptr(x2), 1 if is16 else 0, k, ptr(w.detach()), ptr(b.detach()) if b is not None else None, m, n,
+                                      k, 1 if relu else 0, p, seed, ptr(out), n, None, 0, stream()), "small_linear_fwd")
+        ops._count()
+        if any(ctx.needs_input_grad):
+            ctx.saved = (x2, w, out)
+            ctx.cfg = (is16, relu, p, seed, lead, k, b is not None)
+        return out.view(*lead, n)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w, out = ctx.saved
+        is16, relu, p, seed, lead, k, has_b = ctx.cfg
+        m, n = out.shape
+        dz = dout.detach().reshape(m, n).float().contiguous()
+        if relu or p > 0:
+            dz2 = torch.empty_like(dz)
+            check(L().qt_relu_dropout_bwd(ptr(dz), ptr(out), ptr(dz2), None, m * n, p, seed, 1 if relu else 0, stream()), "relu_dropout_bwd")
+            ops._count()
+            dz = dz2
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
+            dw = ops.grad_out(w)
+            db = torch.empty(n, device=dz.device) if has_b else None
+            check(L().qt_small_linear_bwd_dw(ptr(dz), 0, n, ptr(x2), 1 if is16 else 0, k, m, n, k, ptr(dw), ptr(db), 0, stream()),
+                  "small_linear_bwd_dw")
+            ops._count()
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(m, k, device=dz.device)
+            check(L().qt_small_linear_bwd_dx(ptr(dz), 0, n, ptr(w.detach()), m, n, k, None, 0, 0.0, 0, ptr(dx), k, None, 0, stream()),
+                  "small_linear_bwd_dx")
+            ops._count()
+            dx = dx.view(*lead, k)
+        return dx, dw, db, None, None, None
+
+
+class LinearTC(torch.autograd.Function):
+    """nn.Linear (+ReLU, +Dropout) on the tensor cores: x fp32/bf16 [B, K] (K % 8 == 0) -> fp32 [B, N]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, p_drop, training):
+        x16 = x.detach().to(BF16).contiguous()
+        bsz, k = x16.shape
+        n = w.shape[0]
+        p = float(p_drop) if training else 0.0
+        seed = ops.new_seed() if p > 0 else 0
+        out = torch.empty(bsz, n, device=x16.device)
+        ws = ops.workspace(L().qt_linear_workspace_bytes(bsz, n, k), x16.device)
+        wf = ops.packed_fprop(w)
+        with ops.gemm_scope("linear_fprop", 2.0 * bsz * n * k):
+            check(L().qt_linear_fprop(ptr(x16), k, ptr(wf), ptr(b.detach()), ptr(out), n, capi.QT_EPI_BIAS | capi.QT_EPI_OUT_F32, bsz, n,
+                                      k, ptr(ws), ws.numel(), stream()), "linear_fprop")
+        if relu or p > 0:
+            check(L().qt_relu_dropout(ptr(out), None, bsz * n, p, seed, 1 if relu else 0, stream()), "relu_dropout")
+        ops._count(2)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (x16, w, out)
+            ctx.cfg = (relu, p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x16, w, out = ctx.saved
+        relu, p, seed = ctx.cfg
+        bsz, k = x16.shape
+        n = w.shape[0]
+        d = dout.detach().float().contiguous()
+        dz16 = torch.empty(bsz, n, device=d.device, dtype=BF16)
+        check(L().qt_relu_dropout_bwd(ptr(d), ptr(out), None, ptr(dz16), bsz * n, p, seed, 1 if relu else 0, stream()), "relu_dropout_bwd")
+        ws = ops.workspace(L().qt_linear_workspace_bytes(bsz, n, k), d.device)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.grad_out(w)
+            with ops.gemm_scope("linear_wgrad", 2.0 * bsz * n * k):
+                check(L().qt_linear_wgrad(ptr(x16), k, ptr(dz16), n, ptr(dw), 0, bsz, n, k, ptr(ws), ws.numel(), stream()), "linear_wgrad")
+        if ctx.needs_input_grad[2]:
+            db = torch.empty(n, device=d.device)
+            ops.colsum(dz16, db)
+        if ctx.needs_input_grad[0]:
+            dx16 = torch.empty(bsz, k, device=d.device, dtype=BF16)
+            wd = ops.packed_dgrad(w)
+            with ops.gemm_scope("linear_dgrad", 2.0 * bsz * n * k):
+                check(L().qt_linear_dgrad(ptr(dz16), n, ptr(wd), ptr(dx16), k, bsz, n, k, ptr(ws), ws.numel(), stream()), "linear_dgrad")
+            dx = dx16.float()
+        ops._count(4)
+        return dx, dw, db, None, None, None
+
+
+class AttnPool(torch.autograd.Function):
+    """softmax(scores) weighted sum of R region vectors (QS/models.py:86-90): x fp32 [B,R,C], scores [B,R]."""
+
+    @staticmethod
+    def forward(ctx, x, scores):
+        xc = x.detach().float().contiguous()
+        sc = scores.detach().float().contiguous()
+        bsz, r, c = xc.shape
+        wts = torch.empty(bsz, r, device=xc.device)
+        out = torch.empty(bsz, c, device=xc.device)
+        check(L().qt_attn_pool_fwd(ptr(xc), ptr(sc), ptr(wts), ptr(out), bsz, r, c, stream()), "attn_pool_fwd")
+        ops._count()
+        ctx.save_for_backward(xc, wts)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, wts = ctx.saved_tensors
+        bsz, r, c = xc.shape
+        d = dout.detach().float().contiguous()
+        dx = torch.empty_like(xc)
+        ds = torch.empty(bsz, r, device=xc.device)
+        check(L().qt_attn_pool_bwd(ptr(xc), ptr(wts), ptr(d), ptr(dx), ptr(ds), bsz, r, c, stream()), "attn_pool_bwd")
+        ops._count()
+        return dx, ds
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Conv3d + BatchNorm3d + ReLU (+ MaxPool3d) block of Quadtree3DCNN (3dcnn/models.py:107-141)
+# ------------------------------------------------------------------------------------------------------------
+def _pad_cin(w, cin_pad):
+    """fp32 [cout, cin, taps...] -> [cout, cin_pad, taps] (zero channels) for cin = 3 -> 8."""
+    cout, cin = w.shape[:2]
+    taps = w[0, 0].numel()
+    if cin == cin_pad:
+        return w.detach().reshape(cout, cin, taps)
+    out = torch.zeros(cout, cin_pad, taps, device=w.device, dtype=w.dtype)
+    out[:, :cin] = w.detach().reshape(cout, cin, taps)
+    return out
+
+
+class Conv3dBnReluPool(torch.autograd.Function):
+    """x: NDHWC bf16 [N,D,H,W,Cin_pad] -> NDHWC bf16 after Conv3d(3x3x3, pad 1, bias) + BN3d(train/eval) + ReLU + pool."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, bn_mod, pool, training):
+        n, D, H, W, cin_pad = x.shape
+        cout = w.shape[0]
+        dev = x.device
+        d = capi.conv_desc(n, (D, H, W), cin_pad, cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        wp = _pad_cin(w, cin_pad)
+        wf = torch.empty(cout, 27, cin_pad, device=dev, dtype=BF16)
+        need_x_grad = ctx.needs_input_grad[0]
+        wd = torch.empty(cin_pad, 27, cout, device=dev, dtype=BF16) if need_x_grad else None
+        check(L().qt_wpack_both(ptr(wp), ptr(wf), ptr(wd), cout, cin_pad, 27, stream()), "wpack_both")
+        y = torch.empty(n, D, H, W, cout, device=dev, dtype=BF16)
+        stats = ops.conv_fprop(d, x, wf, y, bias=b.detach(), relu=False, want_stats=training)
+        m = n * D * H * W
+        st = ops.bn_finalize(stats, m, bn_mod, cout, dev, training)
+        a = torch.empty_like(y)
+        ops.bn_apply(y, st, a, None, True)
+        am = None
+        if pool is not None:
+            kd, kh, kw = pool
+            out = torch.empty(n, D // kd, H // kh, W // kw, cout, device=dev, dtype=BF16)
+            am = torch.empty(out.shape, device=dev, dtype=torch.int8) if any(ctx.needs_input_grad) else None
+            check(L().qt_maxpool3d_fwd(ptr(a), ptr(out), ptr(am), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_fwd")
+            ops._count(2)
+        else:
+            out = a
+        if any(ctx.needs_input_grad):
+            ctx.saved = (x, y, a, am, st, w, wd, gamma, d)
+            ctx.cfg = (pool, training, cin_pad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, a, am, st, w, wd, gamma, d = ctx.saved
+        pool, training, cin_pad = ctx.cfg
+        n, D, H, W, cout = y.shape
+        dev = y.device
+        dout = dout.to(BF16).contiguous()
+        if pool is not None:
+            kd, kh, kw = pool
+            da = torch.empty_like(y)
+            check(L().qt_maxpool3d_bwd(ptr(dout), ptr(am), ptr(da), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_bwd")
+            ops._count()
+        else:
+            da = dout
+        dgamma, dbeta = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+        dy = torch.empty_like(y)
+        ops.bn_backward(da, a, y, st, gamma.detach(), dgamma, dbeta, dy, None, eval_mode=not training)
+        db = torch.empty(cout, device=dev)
+        ops.colsum(dy.view(-1, cout), db)  # conv bias before train-mode BN: analytically ~0, computed faithfully
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty(cout, cin_pad, 27, device=dev)
+            ops.conv_wgrad(d, x, dy, dwp)
+            cin = w.shape[1]
+            dw = dwp[:, :cin].reshape(w.shape).contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.conv_dgrad(d, dy, wd, dx)
+        return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+class PackClip(torch.autograd.Function):
+    """[B,T,3,H,W] fp32 clip -> NDHWC bf16 [B,T,H,W,8] (channel padded); the permute(0,2,1,3,4) of
+    3dcnn/models.py:189 is only a change of logical axis order."""
+
+    @staticmethod
+    def forward(ctx, clips):
+        bsz, t, c, h, w = clips.shape
+        xf = clips.detach().float().contiguous()
+        out = torch.empty(bsz, t, h, w, 8, device=clips.device, dtype=BF16)
+        check(L().qt_nchw_f32_to_nhwc_bf16(ptr(xf), ptr(out), bsz * t, c, h * w, 8, stream()), "pack clip")
+        ops._count()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):  # inputs never require gradients in the reference scripts
+        return None
+
+
+class GlobalAvgPoolND(torch.autograd.Function):
+    """AdaptiveAvgPool over all spatial positions of a channels-last bf16 tensor [N, ..., C] -> fp32 [N, C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, c = x.shape[0], x.shape[-1]
+        p = x.numel() // (n * c)
+        out = torch.empty(n, c, device=x.device, dtype=BF16)
+        check(L().qt_region_avgpool_fwd(ptr(x), ptr(out), n, p, c, c, stream()), "avgpool")
+        ops._count()
+        ctx.shape = tuple(x.shape)
+        return out.float()
+
+    @staticmethod
+    def backward(ctx, dout):
+        shape = ctx.shape
+        n, c = shape[0], shape[-1]
+        p = 1
+        for s in shape[1:-1]:
+            p *= s
+        d = dout.to(BF16).contiguous()
+        dx = torch.empty(shape, device=d.device, dtype=BF16)
+        check(L().qt_region_avgpool_bwd(ptr(d), ptr(dx), ptr(dx), n, p, c, c, 0, stream()), "avgpool_bwd")
+        ops._count()
+        return dx

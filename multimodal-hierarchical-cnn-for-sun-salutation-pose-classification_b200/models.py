@@ -23,6 +23,7 @@ import torchvision
 from torchvision.models.resnet import BasicBlock
 
 from . import capi, ops
+from . import functional as Fn
 from .capi import check, ptr, stream
 from .ops import BF16, L
 
@@ -464,13 +465,205 @@ class QuadtreeCNN(nn.Module):
                                  self.dropout_rate, self.training)
 
 
+# =================================================================================================
+# Level-1 + level-2 models (Quadtree_from scratch/models.py:6-101, 105-210)
+# =================================================================================================
+class _HierBase(nn.Module):
+    """Shared trunk of AttentionHierarchicalCNN / HierarchicalQuadtreeCNN: layer2 map (128x28x28) as the quadtree
+    base, layer3->layer4->avgpool as the global branch, 3x3 convs + ReLU + AdaptiveAvgPool on the 4 quadrants
+    (14x14) and the 16 sub-quadrants (7x7). As in the reference the ResNet is NOT kept as an attribute, so the
+    state_dict has only features_extractor.* / global_processor.* keys for it."""
+
+    def _build_trunk(self, numerical_feature_dim, dropout_rate):
+        base_cnn = make_resnet18()
+        self.features_extractor = FusedFeatures(base_cnn.conv1, base_cnn.bn1, base_cnn.relu, base_cnn.maxpool,
+                                                base_cnn.layer1, base_cnn.layer2)
+        self.global_processor = nn.Sequential(base_cnn.layer3, base_cnn.layer4, base_cnn.avgpool)
+        self.quadrant_processor = nn.Sequential(nn.Conv2d(128, 128, kernel_size=3, padding=1), nn.ReLU(inplace=True),
+                                                nn.AdaptiveAvgPool2d((1, 1)))
+        self.sub_quadrant_processor = nn.Sequential(nn.Conv2d(128, 64, kernel_size=3, padding=1), nn.ReLU(inplace=True),
+                                                    nn.AdaptiveAvgPool2d((1, 1)))
+        self.dropout_rate = dropout_rate
+
+    def _regions(self, image_input):
+        base = self.features_extractor(image_input)                     # [B,128,28,28]
+        glob = self.global_processor(base).flatten(1).float()           # [B,512]
+        qp, sp = self.quadrant_processor[0], self.sub_quadrant_processor[0]
+        quad = Fn.RegionConvPool.apply(base, qp.weight, qp.bias, 1)     # [4,B,128]
+        sub = Fn.RegionConvPool.apply(base, sp.weight, sp.bias, 2)      # [16,B,64] quadrant-major
+        bsz = glob.shape[0]
+        quad = quad.permute(1, 0, 2).reshape(bsz, 4 * 128).float()
+        sub = sub.permute(1, 0, 2).float()                              # [B,16,64]
+        return glob, quad, sub
+
+    def _head(self, image_features, numerical_input):
+        mlp, cls = self.numerical_mlp, self.classifier
+        num = Fn.SmallLinear.apply(numerical_input, mlp[0].weight, mlp[0].bias, True, self.dropout_rate, self.training)
+        comb = torch.cat((image_features, num), dim=1)
+        h = Fn.LinearTC.apply(comb, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(h, cls[3].weight, cls[3].bias, False, 0.0, self.training)
+
+
+class AttentionHierarchicalCNN(_HierBase):
+    """Drop-in for Quadtree_from scratch/models.py:6-101."""
+
+    def __init__(self, num_classes, numerical_feature_dim=47, dropout_rate=0.5):
+        super().__init__()
+        self._build_trunk(numerical_feature_dim, dropout_rate)
+        self.attention_gate = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 1))
+        total_image_feature_dim = 512 + (4 * 128) + 64
+        self.numerical_mlp = nn.Sequential(nn.Linear(numerical_feature_dim, 128), nn.ReLU(inplace=True), nn.Dropout(dropout_rate))
+        self.classifier = nn.Sequential(nn.Linear(total_image_feature_dim + 128, 1024), nn.ReLU(inplace=True),
+                                        nn.Dropout(dropout_rate), nn.Linear(1024, num_classes))
+
+    def forward(self, image_input, numerical_input):
+        glob, quad, sub = self._regions(image_input)
+        g = self.attention_gate
+        hid = Fn.SmallLinear.apply(sub, g[0].weight, g[0].bias, True, 0.0, self.training)         # [B,16,32]
+        scores = Fn.SmallLinear.apply(hid, g[2].weight, g[2].bias, False, 0.0, self.training)     # [B,16,1]
+        attended = Fn.AttnPool.apply(sub, scores.squeeze(-1))                                      # [B,64]
+        return self._head(torch.cat((glob, quad, attended), dim=1), numerical_input)
+
+
+class HierarchicalQuadtreeCNN(_HierBase):
+    """Quadtree_from scratch/models.py:105-210 with the evidently intended bottom-right slices (the reference's
+    `w:` / `qw:` slices are empty and its forward raises — SURVEY.md §0.2); constructor and state_dict are
+    the reference's."""
+
+    def __init__(self, num_classes, numerical_feature_dim=47, dropout_rate=0.5):
+        super().__init__()
+        self._build_trunk(numerical_feature_dim, dropout_rate)
+        total_image_feature_dim = 512 + (4 * 128) + (16 * 64)
+        self.numerical_mlp = nn.Sequential(nn.Linear(numerical_feature_dim, 128), nn.ReLU(inplace=True), nn.Dropout(dropout_rate))
+        self.classifier = nn.Sequential(nn.Linear(total_image_feature_dim + 128, 1024), nn.ReLU(inplace=True),
+                                        nn.Dropout(dropout_rate), nn.Linear(1024, num_classes))
+
+    def forward(self, image_input, numerical_input):
+        glob, quad, sub = self._regions(image_input)
+        return self._head(torch.cat((glob, quad, sub.reshape(sub.shape[0], -1)), dim=1), numerical_input)
+
+
+# =================================================================================================
+# StandardResNetCNN (resnet/models.py:7-65)
+# =================================================================================================
+class StandardResNetCNN(nn.Module):
+    def __init__(self, num_classes, dropout_rate=0.5):
+        super().__init__()
+        self.base_cnn = make_resnet18()
+        for param in self.base_cnn.parameters():
+            param.requires_grad = False
+        b = self.base_cnn
+        self.features_extractor = FusedFeatures(b.conv1, b.bn1, b.relu, b.maxpool, b.layer1, b.layer2, b.layer3, b.layer4)
+        self.avgpool = b.avgpool
+        self.classifier = nn.Sequential(nn.Linear(512, 256), nn.ReLU(inplace=True), nn.Dropout(dropout_rate),
+                                        nn.Linear(256, num_classes))
+        self.dropout_rate = dropout_rate
+        self.gradients = None
+        self.activations = None
+
+    def save_gradient_hook(self, module, grad_input, grad_output):
+        self.gradients = grad_output[0]
+
+    def save_activation_hook(self, module, input, output):
+        self.activations = output
+
+    def forward(self, image_input, numerical_input=None):
+        feats = self.features_extractor(image_input)
+        f = self.avgpool(feats).flatten(1).float()
+        cls = self.classifier
+        h = Fn.SmallLinear.apply(f, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(h, cls[3].weight, cls[3].bias, False, 0.0, self.training)
+
+
+# =================================================================================================
+# Quadtree3DCNN (3dcnn/models.py:96-214): Conv3d stack on the tensor cores; the LSTM stays torch (SURVEY §8f.2)
+# =================================================================================================
+class Quadtree3DCNN(nn.Module):
+    _POOLS = {"conv3d_block1": (1, 2, 2), "conv3d_block2": (2, 2, 2), "conv3d_block3": (2, 2, 2),
+              "conv3d_block4_new": (1, 2, 2), "conv3d_final_features": None}
+
+    def __init__(self, num_classes, sequence_length=8, cnn_3d_feature_dim=1024, numerical_feature_dim=47, dropout_rate=0.6,
+                 mode="quadtree_3d_fusion"):
+        super().__init__()
+        self.mode = mode
+        self.sequence_length = sequence_length
+        self.cnn_3d_feature_dim = cnn_3d_feature_dim
+        self.numerical_feature_dim = numerical_feature_dim
+
+        def block(cin, cout, pool):
+            layers = [nn.Conv3d(cin, cout, kernel_size=(3, 3, 3), padding=(1, 1, 1)), nn.BatchNorm3d(cout), nn.ReLU(inplace=True)]
+            if pool is not None:
+                layers.append(nn.MaxPool3d(kernel_size=pool, stride=pool))
+            return nn.Sequential(*layers)
+
+        self.conv3d_block1 = block(3, 32, (1, 2, 2))
+        self.conv3d_block2 = block(32, 64, (2, 2, 2))
+        self.conv3d_block3 = block(64, 128, (2, 2, 2))
+        self.conv3d_block4_new = block(128, 256, (1, 2, 2))
+        self.conv3d_final_features = block(256, cnn_3d_feature_dim, None)
+        self.global_avg_pool_3d = nn.AdaptiveAvgPool3d((1, 1, 1))
+        self.numerical_lstm = nn.LSTM(input_size=numerical_feature_dim, hidden_size=numerical_feature_dim * 4, num_layers=2,
+                                      batch_first=True, dropout=dropout_rate)
+        self.numerical_lstm_output_dim = numerical_feature_dim * 4
+        self.numerical_projection = nn.Sequential(nn.Linear(self.numerical_lstm_output_dim, cnn_3d_feature_dim // 2),
+                                                  nn.ReLU(inplace=True), nn.Dropout(dropout_rate))
+        self.numerical_final_dim = cnn_3d_feature_dim // 2
+        if mode == "quadtree_3d_fusion":
+            self.final_classifier_input_dim = cnn_3d_feature_dim + self.numerical_final_dim
+        elif mode == "quadtree_3d_image_only":
+            self.final_classifier_input_dim = cnn_3d_feature_dim
+        else:
+            raise ValueError(f"Invalid mode for Quadtree3DCNN: {mode}. Choose from 'quadtree_3d_fusion', 'quadtree_3d_image_only'.")
+        d = self.final_classifier_input_dim
+        self.classifier = nn.Sequential(nn.Linear(d, d // 2), nn.ReLU(inplace=True), nn.Dropout(dropout_rate),
+                                        nn.Linear(d // 2, num_classes))
+        self.dropout_rate = dropout_rate
+        self.gradients = None
+        self.activations = None
+
+    def save_gradient_hook(self, module, grad_input, grad_output):
+        self.gradients = grad_output[0]
+
+    def save_activation_hook(self, module, input, output):
+        self.activations = output
+
+    def conv_stack(self, image_sequence_input):
+        """[B,T,3,H,W] fp32 -> pooled conv features fp32 [B, cnn_3d_feature_dim]."""
+        _require_cuda(image_sequence_input, "Quadtree3DCNN")
+        x = Fn.PackClip.apply(image_sequence_input)
+        for name, pool in self._POOLS.items():
+            seq = getattr(self, name)
+            conv, bn = seq[0], seq[1]
+            x = Fn.Conv3dBnReluPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn, pool, bn.training)
+        return Fn.GlobalAvgPoolND.apply(x)
+
+    def forward(self, image_sequence_input, numerical_sequence_input):
+        image_features = self.conv_stack(image_sequence_input)
+        if self.mode == "quadtree_3d_fusion":
+            lstm_out, _ = self.numerical_lstm(numerical_sequence_input.to(image_features.device).float())
+            proj = self.numerical_projection[0]
+            num = Fn.SmallLinear.apply(lstm_out[:, -1, :], proj.weight, proj.bias, True, self.dropout_rate, self.training)
+            combined = torch.cat((image_features, num), dim=1)
+        else:
+            combined = image_features
+        cls = self.classifier
+        h = Fn.LinearTC.apply(combined, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(h, cls[3].weight, cls[3].bias, False, 0.0, self.training)
+
+
 def get_model(model_name="quadtree", num_classes=8, device="cuda", print_num_params=True):
     """`get_model` of Quadtree_from scratch/models.py:309-325 (same argument names and printout)."""
     name = model_name.lower()
     if name == "quadtree":
         model = QuadtreeCNN(num_classes=num_classes).to(device)
+    elif name == "hierarchical_quadtree":
+        model = HierarchicalQuadtreeCNN(num_classes=num_classes).to(device)
+    elif name == "attention_hierarchical":
+        model = AttentionHierarchicalCNN(num_classes=num_classes).to(device)
     else:
-        raise ValueError(f"get_model: '{model_name}' is outside the B200 hot path (SURVEY.md §8); supported: 'quadtree'")
+        # the reference's StandardMultimodalCNN is a `pass` stub there and raises TypeError (SURVEY §0.3)
+        raise ValueError(f"get_model: backbone '{model_name}' is outside the B200 hot path (SURVEY.md §8); supported: "
+                         "'quadtree', 'hierarchical_quadtree', 'attention_hierarchical'")
     if print_num_params:
         num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
         print(f"Model: '{name.upper()}' | Trainable Parameters: {num_params / 1e6:.2f} Million")
@@ -480,9 +673,28 @@ def get_model(model_name="quadtree", num_classes=8, device="cuda", print_num_par
 def get_model_resnet(num_classes, device, numerical_feature_dim=47, mode="fusion", print_num_params=True):
     """`get_model` of resnet/models.py:183-194 (frozen backbone + mode switch)."""
     if mode == "standard_resnet_only":
-        raise ValueError("standard_resnet_only is outside the accelerated path for now")
-    model = QuadtreeCNN(num_classes=num_classes, numerical_feature_dim=numerical_feature_dim, mode=mode,
-                        freeze_backbone=True).to(device)
+        model = StandardResNetCNN(num_classes=num_classes).to(device)
+    else:
+        model = QuadtreeCNN(num_classes=num_classes, numerical_feature_dim=numerical_feature_dim, mode=mode,
+                            freeze_backbone=True).to(device)
+    if print_num_params:
+        num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        print(f"Number of trainable parameters: {num_params / 1e6:.2f} Million (Mode: {mode})")
+    return model
+
+
+def get_model_3d(num_classes, device, numerical_feature_dim=47, mode="fusion", sequence_length=8, print_num_params=True):
+    """`get_model` of 3dcnn/models.py:493-522 for the modes on the accelerated path."""
+    if mode == "standard_resnet_only":
+        model = StandardResNetCNN(num_classes=num_classes).to(device)
+    elif mode in ("quadtree_3d_fusion", "quadtree_3d_image_only"):
+        model = Quadtree3DCNN(num_classes=num_classes, sequence_length=sequence_length,
+                              numerical_feature_dim=numerical_feature_dim, mode=mode, cnn_3d_feature_dim=1024).to(device)
+    elif mode in ("resnet_3d_video_only", "hybrid_quadtree_3d_fusion", "hybrid_quadtree_3d_image_only"):
+        raise ValueError(f"get_model: mode '{mode}' (torchvision r3d_18 backbone) is SURVEY.md §8f 'next', not built yet")
+    else:
+        model = QuadtreeCNN(num_classes=num_classes, numerical_feature_dim=numerical_feature_dim, mode=mode,
+                            freeze_backbone=True).to(device)
     if print_num_params:
         num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
         print(f"Number of trainable parameters: {num_params / 1e6:.2f} Million (Mode: {mode})")
@@ -490,11 +702,30 @@ def get_model_resnet(num_classes, device, numerical_feature_dim=47, mode="fusion
 
 
 def load_oracle_params(model: nn.Module, params: dict) -> None:
-    """Load a parameter dict in the oracle's naming (oracle/quadtree_oracle.make_params) — the names ARE the
-    reference's state_dict keys, aliases resolve through the shared tensors."""
+    """Load a parameter dict in the oracle's naming (oracle/quadtree_oracle.make_params). For QuadtreeCNN /
+    StandardResNetCNN the names ARE the reference's state_dict keys; the hierarchical classes hold the ResNet
+    only through features_extractor / global_processor, so `base_cnn.*` names are mapped onto those."""
     own = model.state_dict()
-    sd = {k: v for k, v in params.items() if k in own}
+    alias = {}
+    if not hasattr(model, "base_cnn") and any(k.startswith("base_cnn.") for k in params):
+        fe = {"conv1": "features_extractor.0", "bn1": "features_extractor.1", "layer1": "features_extractor.4",
+              "layer2": "features_extractor.5", "layer3": "global_processor.0", "layer4": "global_processor.1"}
+        for k, v in params.items():
+            if k.startswith("base_cnn."):
+                rest = k[len("base_cnn."):]
+                head = rest.split(".")[0]
+                if head in fe:
+                    alias[fe[head] + rest[len(head):]] = v
+            else:
+                alias[k] = v
+    else:
+        alias = params
+    sd = {k: v for k, v in alias.items() if k in own}
     res = model.load_state_dict(sd, strict=False)
     missing = [k for k in res.missing_keys if not k.startswith(("features_extractor.", "global_processor."))]
-    if missing:
+    if missing and hasattr(model, "base_cnn"):
         raise RuntimeError(f"load_oracle_params: missing {missing[:5]}")
+    if not hasattr(model, "base_cnn"):
+        really_missing = [k for k in own if k not in sd]
+        if really_missing:
+            raise RuntimeError(f"load_oracle_params: missing {really_missing[:5]}")

@@ -121,13 +121,16 @@ def _w_dims(w: torch.Tensor) -> Tuple[int, int, int]:
 
 
 def packed_fprop(w: torch.Tensor) -> torch.Tensor:
-    """bf16 [cout][taps][cin] copy of an fp32 parameter, refreshed when the parameter changes."""
+    """bf16 [cout][taps][cin] copy of an fp32 parameter, refreshed when the parameter changes. When autograd is
+    recording, the data-gradient layout [cin][taps][cout] is produced by the same kernel (one read of w)."""
     e = _entry(w)
     if e.wf is None:
         cout, cin, taps = _w_dims(w)
         e.wf = torch.empty(cout, taps, cin, device=w.device, dtype=BF16)
         wc = w.detach().contiguous()
-        check(L().qt_wpack_fprop(ptr(wc), ptr(e.wf), cout, cin, taps, stream()), "wpack_fprop")
+        if torch.is_grad_enabled() or w.requires_grad:
+            e.wd = torch.empty(cin, taps, cout, device=w.device, dtype=BF16)
+        check(L().qt_wpack_both(ptr(wc), ptr(e.wf), ptr(e.wd), cout, cin, taps, stream()), "wpack_both")
         _count()
     return e.wf
 

@@ -435,3 +435,14 @@ def test_colsum_wide(C):
     out = torch.empty(c, device="cuda")
     run(C, C.lib().qt_colsum(C.ptr(x), m, c, C.ptr(out), 0, C.ptr(ws), ws_bytes, C.stream()), "colsum wide")
     report("colsum 2688", out, x.float().sum(0), 1e-5)
+
+
+@pytest.mark.parametrize("cout,cin,taps", [(64, 64, 9), (128, 64, 1), (2688, 5376, 1), (96, 40, 27)])
+def test_wpack_both(C, cout, cin, taps):
+    g = torch.Generator(device="cuda").manual_seed(13)
+    w = torch.randn(cout, cin, taps, device="cuda", generator=g)
+    wf = torch.empty(cout, taps, cin, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(cin, taps, cout, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_both(C.ptr(w), C.ptr(wf), C.ptr(wd), cout, cin, taps, C.stream()), "wpack_both")
+    assert torch.equal(wf, bf16(w).permute(0, 2, 1).contiguous())
+    assert torch.equal(wd, bf16(w).permute(1, 2, 0).contiguous())
