@@ -9,6 +9,7 @@
 #include "elementwise.cuh"
 #include "igemm.cuh"
 #include "conv3x3.cuh"
+#include "stem.cuh"
 
 using namespace qt;
 
@@ -528,9 +529,41 @@ static int fill_stem(IgemmParams& p, int n, int h, int w, int cout) {
   p.groups = 1;
   return 0;
 }
-int qt_stem_stat_rows(int n, int h, int w) { return (n * (h / 2) * (w / 2) + kBM - 1) / kBM; }
+// Dedicated overlapping-row stem kernels (stem.cuh) when the shape allows; g_tune[2] = 1 forces the generic path.
+static bool stem_fast_ok(int h, int w, int cout) { return g_tune[2] == 0 && cout == 64 && h % 2 == 0 && w % 2 == 0 && w <= 248; }
+static bool stem_wgrad_fast_ok(int h, int w, int cout, int cin) {
+  return stem_fast_ok(h, w, cout) && cin <= 4 && ((w / 2) % 16 == 0);
+}
+static int stem_tiles(int n, int h, int rows) { return n * (((h / 2) + rows - 1) / rows); }
+
+int qt_stem_stat_rows(int n, int h, int w) {
+  if (stem_fast_ok(h, w, 64)) { const int t = stem_tiles(n, h, kStemRows); return t < kNumSMs ? t : kNumSMs; }
+  return (n * (h / 2) * (w / 2) + kBM - 1) / kBM;
+}
 int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, int h, int w, int cout,
                   qt_stream_t stream) {
+  if (stem_fast_ok(h, w, cout)) {
+    StemParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.xp = static_cast<const __nv_bfloat16*>(xp);
+    sp.w8 = static_cast<const __nv_bfloat16*>(w8);
+    sp.y = static_cast<__nv_bfloat16*>(y);
+    sp.stats = stats;
+    sp.N = n; sp.H = h; sp.W = w; sp.Ho = h / 2; sp.Wo = w / 2; sp.Hp = h + 7; sp.Wp = w + 8;
+    sp.strips = (sp.Ho + kStemRows - 1) / kStemRows;
+    sp.num_tiles = n * sp.strips;
+    sp.row_bytes = sp.Wp * 8;
+    sp.stage_bytes = ((2 * kStemRows + 5) * sp.row_bytes + 2304 + 127) / 128 * 128;  // slack: MMA rows up to 127 read 2096 B past the last row start
+    const size_t smem = 1024 + 28 * 1024 + 4096 + 256 + static_cast<size_t>(kStemStages) * sp.stage_bytes;
+    static size_t configured = 0;
+    if (configured < smem) {
+      cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      configured = smem;
+    }
+    const int grid = sp.num_tiles < kNumSMs ? sp.num_tiles : kNumSMs;
+    stem_fprop_kernel<<<grid, kStemThreads, smem, S(stream)>>>(sp);
+    return cuda_status("stem_fprop_kernel");
+  }
   IgemmParams p;
   if (int rc = fill_stem(p, n, h, w, cout)) return rc;
   p.a = static_cast<const __nv_bfloat16*>(xp);
@@ -541,11 +574,40 @@ int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, 
   return run_kmajor(p, S(stream), nullptr, 0, 0);
 }
 size_t qt_stem_wgrad_workspace_bytes(int n, int h, int w, int cout) {
-  return wgrad_ws_bytes(256, cout, 1, static_cast<long long>(n) * (h / 2) * (w / 2), nullptr) +
-         static_cast<size_t>(cout) * 256 * sizeof(float);
+  const size_t generic = wgrad_ws_bytes(256, cout, 1, static_cast<long long>(n) * (h / 2) * (w / 2), nullptr) +
+                         static_cast<size_t>(cout) * 256 * sizeof(float);
+  const size_t fast = static_cast<size_t>(kNumSMs) * 64 * 224 * sizeof(float);
+  return generic > fast ? generic : fast;
 }
 int qt_stem_wgrad(const void* xp, const void* dy, float* dw, int accumulate, int n, int h, int w, int cout, int cin,
                   void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (stem_wgrad_fast_ok(h, w, cout, cin)) {
+    StemWgradParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.xp = static_cast<const __nv_bfloat16*>(xp);
+    sp.dy = static_cast<const __nv_bfloat16*>(dy);
+    sp.partial = static_cast<float*>(ws);
+    sp.N = n; sp.Ho = h / 2; sp.Wo = w / 2; sp.Hp = h + 7; sp.Wp = w + 8;
+    sp.strips = (sp.Ho + kSWRows - 1) / kSWRows;
+    sp.num_tiles = n * sp.strips;
+    sp.row_bytes = sp.Wp * 8;
+    sp.x_bytes = ((2 * kSWRows + 5) * sp.row_bytes + 512 + 1023) / 1024 * 1024;
+    sp.dy_bytes = sp.Wo * 128;
+    if (sp.dy_bytes % 1024) return fail("stem_wgrad: Wo must be a multiple of 8");
+    const int grid = sp.num_tiles < kNumSMs ? sp.num_tiles : kNumSMs;
+    if (ws_bytes < static_cast<size_t>(grid) * 64 * 224 * sizeof(float)) return fail("stem_wgrad: workspace too small");
+    const size_t smem = 1024 + static_cast<size_t>(kSWStages) * (kSWRows * sp.dy_bytes + sp.x_bytes) + sp.dy_bytes + 256;
+    if (smem > 227 * 1024) return fail("stem_wgrad: image too wide for the dedicated kernel");
+    static size_t configured = 0;
+    if (configured < smem) {
+      cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      configured = smem;
+    }
+    stem_wgrad_kernel<<<grid, kSWThreads, smem, S(stream)>>>(sp);
+    if (int rc = cuda_status("stem_wgrad_kernel")) return rc;
+    stem_wgrad_reduce_kernel<<<(cout * cin * 49 + 255) / 256, 256, 0, S(stream)>>>(sp.partial, grid, dw, cout, cin, accumulate);
+    return cuda_status("stem_wgrad_reduce");
+  }
   IgemmParams p;
   if (int rc = fill_stem(p, n, h, w, cout)) return rc;
   const size_t g8_bytes = static_cast<size_t>(cout) * 256 * sizeof(float);

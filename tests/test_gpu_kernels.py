@@ -222,8 +222,10 @@ def test_quadrant_conv_groups(C):
     report("quadrant conv fprop", y.permute(0, 1, 4, 2, 3), ref, BF16_REL_L2, True)
 
 
-def test_stem(C):
-    n, h, w, cout = 3, 64, 96, 64
+@pytest.mark.parametrize("n,h,w", [(3, 64, 96), (2, 224, 224), (1, 38, 50)])
+def test_stem(C, n, h, w):
+    """(64x96, 224x224): dedicated overlapping-row kernels; 38x50 (Wo % 16 != 0): generic weight-gradient path."""
+    cout = 64
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(n, 3, h, w, device="cuda", generator=g)
     wt = torch.randn(cout, 3, 7, 7, device="cuda", generator=g) / math.sqrt(147)
