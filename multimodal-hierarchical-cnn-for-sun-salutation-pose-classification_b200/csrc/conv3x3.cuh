@@ -22,7 +22,7 @@
 
 namespace qt {
 
-constexpr int kC3Threads = 288;
+constexpr int kC3Threads = 320;  // 4 epilogue + 4 producer + 2 MMA-issuer warps
 
 struct Conv3x3Params {
   const __nv_bfloat16* a;   // dense NHWC input  [N][H][W][cin]
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
   using L = C3Smem<BN, MT, NSLAB, NB>;
   constexpr uint32_t TCOLS = 2 * MT * BN;  // double-buffered accumulators
   static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
+  static_assert(MT == 2, "one MMA-issuer warp per sub-tile: warps 8 and 9");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem;
@@ -79,9 +80,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
 
   if (warp == 8) {
     if (lane == 0) {
-      for (int s = 0; s < NSLAB; ++s) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], 1); }
-      for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], kProducerThreads); mbar_init(&b_empty[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kProducerThreads); }
+      // two MMA-issuer warps (one per 128-row sub-tile) release every operand / accumulator stage together
+      for (int s = 0; s < NSLAB; ++s) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], MT); }
+      for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], kProducerThreads); mbar_init(&b_empty[s], MT); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], MT); mbar_init(&acc_empty[s], kProducerThreads); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -174,8 +176,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
     fence_proxy_async_smem();
     if (issued >= 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend0) : "memory");
     if (issued >= 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend1) : "memory");
-  } else if (warp == 8) {
-    // ================================================================= MMA issuer
+  } else if (warp >= 8) {
+    // ================================================================= MMA issuers (warp 8 + u owns sub-tile u)
     // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform
     // datapath; one elected lane issues tcgen05.mma / tcgen05.commit.
     {
@@ -212,14 +214,12 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
             const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
             const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
             if (lane == 0) {
+              const int u = warp - 8;
 #pragma unroll
-              for (int u = 0; u < MT; ++u) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
-                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
-                  umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
-                }
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
+                const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
+                umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
               }
               if (!p.b_resident) umma_commit(&b_empty[sb]);
             }

@@ -80,6 +80,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// Make the mbarrier track completion of all cp.async issued so far by this thread: the arrive happens
+// asynchronously when they land (counts as one of the barrier's expected arrivals), so a producer never has to
+// block in cp.async.wait_group (CUTLASS: cutlass::arch::cpasync_barrier_arrive_noinc).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // Generic-proxy writes (cp.async / st.shared) -> async-proxy readers (tcgen05.mma, TMA).
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

@@ -10,6 +10,7 @@
 #include "igemm.cuh"
 #include "conv3x3.cuh"
 #include "stem.cuh"
+#include "wgrad3x3.cuh"
 
 using namespace qt;
 
@@ -336,6 +337,86 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
   return launch_conv3x3<128, 2, 2, 6>(p, pl.smem, grid, st);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Slab weight-gradient kernel dispatch (wgrad3x3.cuh); g_tune[3] = 1 forces the generic gather kernel.
+// ------------------------------------------------------------------------------------------------
+struct W3Plan {
+  bool ok;
+  int cfg;  // 0: 64->64 (NSLAB 1, 5 taps, 3 stages), 1: 128-multiples (NSLAB 2, 3 taps, 2 stages)
+  int V, num_kt, splits, kt_per_split, R, plane_stride, cout_tiles, cin_groups, tap_groups;
+  size_t smem, ws_bytes;
+};
+W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
+  W3Plan pl{};
+  pl.ok = false;
+  if (g_tune[3] != 0) return pl;
+  if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->groups != 1) return pl;
+  if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
+  if (d->in_c == 64 && d->out_c == 64) pl.cfg = 0;
+  else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
+  else return pl;
+  const long long V = static_cast<long long>(d->n) * (d->in_h + 2) * (d->in_w + 2);
+  if (V > (1ll << 30)) return pl;
+  pl.V = static_cast<int>(V);
+  pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);
+  pl.R = (kW3KP + 2 * (d->in_w + 3) + 15) / 16 * 16;
+  pl.plane_stride = pl.R * 16 + 16;
+  const int nslab = pl.cfg == 0 ? 1 : 2, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 3 : 2, taps = pl.cfg == 0 ? 5 : 3;
+  pl.cout_tiles = d->out_c / (64 * cb);
+  pl.cin_groups = d->in_c / (64 * nslab);
+  pl.tap_groups = (9 + taps - 1) / taps;
+  const int types = pl.cout_tiles * pl.cin_groups * pl.tap_groups;
+  int splits = kNumSMs / types;
+  if (splits < 1) splits = 1;
+  if (splits > pl.num_kt / 4) splits = pl.num_kt / 4;
+  if (splits < 1) splits = 1;
+  pl.kt_per_split = (pl.num_kt + splits - 1) / splits;
+  pl.splits = (pl.num_kt + pl.kt_per_split - 1) / pl.kt_per_split;
+  const size_t slab_bytes = (static_cast<size_t>(8) * nslab * pl.plane_stride + 1023) / 1024 * 1024;
+  pl.smem = 1024 + stages * (static_cast<size_t>(cb) * kW3KP * 128 + slab_bytes) + (cb == 1 ? kW3KP * 128 : 0) + 256;
+  if (pl.smem > 227 * 1024) return pl;
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * 9 * d->in_c * d->out_c * sizeof(float);
+  pl.ok = true;
+  return pl;
+}
+
+template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
+int launch_wgrad3x3(const Wgrad3x3Params& p, const W3Plan& pl, cudaStream_t st) {
+  static size_t configured = 0;
+  if (configured < pl.smem) {
+    cudaFuncSetAttribute(wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+    configured = pl.smem;
+  }
+  dim3 grid(pl.cout_tiles * pl.cin_groups * pl.tap_groups, pl.splits);
+  wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA><<<grid, 192, pl.smem, st>>>(p);
+  return cuda_status("wgrad3x3_kernel");
+}
+
+int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  if (ws == nullptr || ws_bytes < pl.ws_bytes) return fail("wgrad3x3: workspace too small (%zu < %zu)", ws_bytes, pl.ws_bytes);
+  Wgrad3x3Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.ws = static_cast<float*>(ws);
+  p.N = d->n; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
+  p.V = pl.V; p.num_kt = pl.num_kt; p.kt_per_split = pl.kt_per_split;
+  p.R = pl.R; p.plane_stride = pl.plane_stride;
+  p.cout_tiles = pl.cout_tiles; p.cin_groups = pl.cin_groups; p.tap_groups = pl.tap_groups;
+  int t = 0;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw, ++t) { p.off_h[t] = static_cast<signed char>(kh - 1); p.off_w[t] = static_cast<signed char>(kw - 1); }
+  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 5, 1, 3, 1>(p, pl, st) : launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st);
+  if (rc) return rc;
+  dim3 rgrid((d->in_c + 31) / 32, (d->out_c + 31) / 32, 9);
+  splitk_reduce_wgrad_kernel<<<rgrid, 256, 0, st>>>(p.ws, pl.splits, 9 * d->in_c, d->out_c, 9 * d->in_c, d->out_c, d->in_c, 9, dw,
+                                                    accumulate);
+  return cuda_status("splitk_reduce_wgrad_kernel");
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -498,11 +579,17 @@ size_t qt_conv_wgrad_workspace_bytes(const qt_conv_desc* d) {
   if (check_desc(d)) return 0;
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
-  return wgrad_ws_bytes(d->k_d * d->k_h * d->k_w * d->in_c, d->out_c, d->groups, M, nullptr);
+  const size_t generic = wgrad_ws_bytes(d->k_d * d->k_h * d->k_w * d->in_c, d->out_c, d->groups, M, nullptr);
+  const W3Plan pl = plan_wgrad3x3(d);
+  return (pl.ok && pl.ws_bytes > generic) ? pl.ws_bytes : generic;
 }
 int qt_conv_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
                   size_t ws_bytes, qt_stream_t stream) {
   if (int rc = check_desc(d)) return rc;
+  {
+    const W3Plan pl = plan_wgrad3x3(d);
+    if (pl.ok) return run_wgrad3x3(pl, d, x, dy, dw, accumulate, ws, ws_bytes, S(stream));
+  }
   IgemmParams p;
   if (int rc = fill_forward(p, d)) return rc;
   p.a = static_cast<const __nv_bfloat16*>(x);

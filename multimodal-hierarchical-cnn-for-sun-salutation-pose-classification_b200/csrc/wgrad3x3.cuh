@@ -1,0 +1,226 @@
+// Weight gradient of 3x3 / stride-1 / pad-1 convolutions with input reuse across the taps (the backward twin of
+// conv3x3.cuh):   dW[tap][cin][cout] = sum over pixels  x[pixel + shift(tap)][cin] * dy[pixel][cout].
+//
+// The reduction (GEMM K) runs over the virtual zero-padded pixel space [N][H+2][W+2] in tiles of 128 pixels. Per
+// tile the producers stage
+//   * the x "slab" (128 + 2(W+3) virtual pixels x 64*NSLAB channels) as no-swizzle planes [8-channel chunk][pixel][16 B]
+//     — used as the MN-major B operand (N = channels): chunk stride = SBO, 16 B between the pixels of a core
+//     matrix, LBO = 128 B between 8-pixel groups; a tap is just a different start pixel, so ONE slab feeds all taps;
+//   * the dy tile (128 virtual pixels x 64*CB couts, zero rows for border pixels) in the 128B-swizzled MN-major
+//     layout — the A operand (M = cout; for 64-cout layers the upper 64 rows point at a zero block).
+// Each CTA owns TAPS accumulators [128 cout x 64*NSLAB cin] in TMEM for its whole pixel range (split-K over
+// pixel ranges), then writes fp32 partials in the workspace layout of splitk_reduce_wgrad_kernel.
+// Roles (192 threads): warps 0-3 producers (and final epilogue), warps 4 and 5 MMA issuers (even / odd taps of the
+// CTA's tap group: distinct accumulators, so two threads feed the tensor core's queue and the single-thread
+// issue rate stops being the limiter).
+#pragma once
+#include "igemm.cuh"
+
+namespace qt {
+
+constexpr int kW3KP = 128;  // virtual pixels per k-tile
+
+struct Wgrad3x3Params {
+  const __nv_bfloat16* x;    // dense NHWC [N][H][W][cin]
+  const __nv_bfloat16* dy;   // dense NHWC [N][H][W][cout]
+  float* ws;                 // [splits][Mpad = 9*cin][Npad = cout]
+  int N, H, W, cin, cout;
+  int V, num_kt, kt_per_split;
+  int R, plane_stride;       // slab rows (multiple of 16), bytes per plane (R*16 + 16)
+  int cout_tiles, cin_groups, tap_groups;
+  signed char off_h[9], off_w[9];
+};
+
+template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
+__global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant__ Wgrad3x3Params p) {
+  constexpr int NCH = 64 * NSLAB;          // channels (GEMM N) per CTA
+  constexpr uint32_t TCOLS = 512;
+  static_assert(TAPS * NCH <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int dy_bytes = CB * kW3KP * 128;                        // CB blocks of [128 pixels][128 B]
+  const int slab_bytes = (8 * NSLAB * p.plane_stride + 1023) / 1024 * 1024;
+  const int stage_bytes = dy_bytes + slab_bytes;
+  uint8_t* zero_blk = smem + STAGES * stage_bytes;              // 16 KB of zeros (cout rows 64..127 when CB == 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + (CB == 1 ? kW3KP * 128 : 0));
+  uint64_t* full = bars;
+  uint64_t* empty = full + STAGES;
+  uint64_t* done = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Wp = p.W + 2, Hp = p.H + 2;
+  // CTA coordinates
+  int type = blockIdx.x;
+  const int tap_group = type % p.tap_groups; type /= p.tap_groups;
+  const int cin_group = type % p.cin_groups;
+  const int cout_tile = type / p.cin_groups;
+  const int tap0 = tap_group * TAPS;
+  const int ntap = min(TAPS, 9 - tap0);
+  const int cin0 = cin_group * NCH;
+  const int cout0 = cout_tile * (64 * CB);
+  const int kt0 = blockIdx.y * p.kt_per_split;
+  const int kt1 = min(p.num_kt, kt0 + p.kt_per_split);
+  const int nit = max(0, kt1 - kt0);
+
+  if (CB == 1) {
+    for (int i = threadIdx.x * 16; i < kW3KP * 128; i += 192 * 16) *reinterpret_cast<uint4*>(zero_blk + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], NMMA); }
+      mbar_init(done, NMMA);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<TCOLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 + NMMA) {
+    // spare warp (single-issuer configuration)
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int t = threadIdx.x;
+    const int chunk = t & 7;
+    const int rbase = t >> 3;
+    const uint32_t dsw = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
+    const int adv_w = 16 % Wp, adv_h = 16 / Wp;
+    for (int it = 0; it < nit; ++it) {
+      const int s = it % STAGES;
+      if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+      uint8_t* st = smem + s * stage_bytes;
+      const int q0 = (kt0 + it) * kW3KP;
+      {  // ---- dy tile: row i <-> virtual pixel q0 + i (zero for border / out-of-range pixels)
+        int n, hp, wp;
+        {
+          const int vv = q0 + rbase;
+          wp = vv % Wp;
+          const int rest = vv / Wp;
+          hp = rest % Hp;
+          n = rest / Hp;
+        }
+        const uint32_t dst0 = smem_u32(st) + dsw;
+#pragma unroll
+        for (int i = 0; i < kW3KP / 16; ++i) {
+          const bool ok = (n < p.N) && (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
+          const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
+          const __nv_bfloat16* src = ok ? (p.dy + static_cast<long long>(pix) * p.cout + cout0 + chunk * 8) : p.dy;
+#pragma unroll
+          for (int b = 0; b < CB; ++b)
+            cp_async16(dst0 + b * (kW3KP * 128) + (rbase + 16 * i) * 128, ok ? src + b * 64 : p.dy, ok ? 16u : 0u);
+          wp += adv_w; hp += adv_h;
+          if (wp >= Wp) { wp -= Wp; ++hp; }
+          if (hp >= Hp) { hp -= Hp; ++n; }
+        }
+      }
+      {  // ---- x slab: row j <-> virtual pixel q0 - (W+3) + j
+        int n, hp, wp;
+        {
+          const int vv = q0 - (p.W + 3) + rbase + Wp * Hp;
+          wp = vv % Wp;
+          const int rest = vv / Wp;
+          hp = rest % Hp;
+          n = rest / Hp - 1;
+        }
+        const uint32_t dst0 = smem_u32(st + dy_bytes) + chunk * p.plane_stride;
+        const __nv_bfloat16* src_c = p.x + cin0 + chunk * 8;
+        for (int j = rbase; j < p.R; j += 16) {
+          const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(p.N)) && (wp >= 1) && (wp <= p.W) && (hp >= 1) &&
+                          (hp <= p.H);
+          const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
+          const __nv_bfloat16* src = ok ? (src_c + static_cast<long long>(pix) * p.cin) : p.x;
+#pragma unroll
+          for (int sl = 0; sl < NSLAB; ++sl)
+            cp_async16(dst0 + sl * 8 * p.plane_stride + j * 16, ok ? src + sl * 64 : p.x, ok ? 16u : 0u);
+          wp += adv_w; hp += adv_h;
+          if (wp >= Wp) { wp -= Wp; ++hp; }
+          if (hp >= Hp) { hp -= Hp; ++n; }
+        }
+      }
+      // completion is tracked by the mbarrier itself (no wait_group): the producers run ahead by up to STAGES
+      // tiles; the consumer issues the generic->async proxy fence after its barrier wait.
+      cp_async_mbar_arrive_noinc(&full[s]);
+    }
+    cp_async_wait<0>();  // nothing may be in flight when the CTA retires
+  } else {
+    // ------------------------------------------------------------------ MMA issuers (warp 4: even taps, warp 5: odd taps)
+    const int tpar = warp - 4;
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, NCH, 1, 1);
+    constexpr uint32_t a_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);   // SBO: next 8 pixels of dy
+    const uint32_t b_hi = (static_cast<uint32_t>(p.plane_stride >> 4) & 0x3FFFu) | (1u << 14) | (kLayoutNone << 29);  // SBO: next chunk plane
+    constexpr uint32_t b_lbo = (128u >> 4) << 16;                                 // LBO: next 8 pixels of the slab
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // per-tap start rows (in 16-byte units) kept in registers; the 8 x TAPS MMAs of a k-tile are fully unrolled
+    uint32_t row0[TAPS];
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp) {
+      const int tsel = min(tap0 + tp, 8);
+      row0[tp] = static_cast<uint32_t>((p.off_h[tsel] + 1) * Wp + (p.off_w[tsel] + 1));
+    }
+    for (int it = 0; it < nit; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&full[s], (it / STAGES) & 1);
+      fence_proxy_async_smem();
+      tc_fence_after();
+      uint8_t* st = smem + s * stage_bytes;
+      const uint32_t a_addr = smem_u32(st);
+      const uint32_t a_lbo_bytes = (CB == 2) ? static_cast<uint32_t>(kW3KP * 128) : (smem_u32(zero_blk) - a_addr);
+      const uint32_t a_lo = ((a_addr >> 4) & 0x3FFFu) | (((a_lbo_bytes >> 4) & 0x3FFFu) << 16);
+      const uint32_t x_lo = ((smem_u32(st + dy_bytes) >> 4) & 0x3FFFu) | b_lbo;
+      const uint32_t acc = it ? 1u : 0u;
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < kW3KP / 16; ++ks) {
+#pragma unroll
+          for (int tp = 0; tp < TAPS; ++tp) {
+            if ((NMMA == 1 || (tp & 1) == tpar) && tp < ntap) {
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + ks * (2048 >> 4));
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (x_lo + row0[tp] + ks * 16);
+              umma_bf16(tbase + tp * NCH, ad, bd, idesc, ks ? 1u : acc);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(done);
+    __syncwarp();
+  }
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ final epilogue: TMEM -> workspace partials
+    if (nit > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
+    const int crow = warp * 32 + lane;            // cout within the 128-row accumulator
+    const bool row_ok = crow < 64 * CB && (cout0 + crow) < p.cout;
+    const long long Mpad = 9LL * p.cin;
+    for (int tp = 0; tp < ntap; ++tp) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NCH; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tp * NCH + c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap0 + tp) * p.cin + cin0 + c0) * p.cout +
+                       cout0 + crow;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.cout] = nit > 0 ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+}  // namespace qt
