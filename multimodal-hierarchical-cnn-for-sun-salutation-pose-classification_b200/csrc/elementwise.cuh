@@ -130,15 +130,16 @@ __global__ void wpack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* _
       wd[(static_cast<long long>(ci) * T + t) * Cout + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
   }
 }
-// Both layouts from one read of w. grid (ceil(Cin/32), ceil(Cout/32)), block 256, dynamic smem 32*32*T floats.
+// Both layouts from one read of w. grid (ceil(Cin/32), ceil(Cout/8)), block 256, dynamic smem 8*(32*(T|1)+1) floats.
+// (8 x 32 tiles keep even the 64x64 layers at 16+ blocks; the 16-byte runs of wd[ci][t][co0..co0+7] are one sector.)
 __global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T) {
-  extern __shared__ float tile[];  // [32 co][32 ci][T], odd pitches in both directions (bank-conflict free)
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  extern __shared__ float tile[];  // [8 co][32 ci][T], odd pitches in both directions (bank-conflict free)
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 8;
   const int TP = T | 1;
   const int CP = 32 * TP + 1;
   const int run = 32 * T;
-  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
     const int co = i / run, r = i - co * run;  // r = ci_local*T + t, contiguous in w for a fixed co
     const int cil = r / T, t = r - cil * T;
     float v = 0.f;
@@ -146,14 +147,14 @@ __global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __
     tile[co * CP + cil * TP + t] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * run; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
     {  // wf[co][t][ci]: ci fastest
       const int cil = i & 31, t = (i >> 5) % T, co = i / (32 * T);
       if (co0 + co < Cout && ci0 + cil < Cin)
         wf[(static_cast<long long>(co0 + co) * T + t) * Cin + ci0 + cil] = __float2bfloat16_rn(tile[co * CP + cil * TP + t]);
     }
-    if (wd) {  // wd[ci][t][co]: co fastest
-      const int col = i & 31, t = (i >> 5) % T, cil = i / (32 * T);
+    if (wd) {  // wd[ci][t][co]: co fastest (8 per block)
+      const int col = i & 7, t = (i >> 3) % T, cil = i / (8 * T);
       if (co0 + col < Cout && ci0 + cil < Cin)
         wd[(static_cast<long long>(ci0 + cil) * T + t) * Cout + co0 + col] = __float2bfloat16_rn(tile[col * CP + cil * TP + t]);
     }
@@ -243,31 +244,39 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
-// Block (32 channels x 8 row lanes): per-channel sums of partial[T][2][C] (fp32 rows, fp64 combine, fixed order).
+// Block (32 channels x 32 row lanes): per-channel sums of partial[T][2][C] (fp32 rows, fp64 combine, fixed order).
+// Each thread sums every 32nd row with four independent loads in flight, so T ~ 600 rows take ~5 iterations.
 __device__ __forceinline__ void reduce_rows_2(const float* __restrict__ partial, int T, int C, int c, int ry,
                                               double& s1, double& s2) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][32][33];
   double a1 = 0.0, a2 = 0.0;
   if (c < C) {
-    float f1 = 0.f, f2 = 0.f;
-    int cnt = 0;
-    for (int t = ry; t < T; t += 8) {
-      f1 += partial[(static_cast<long long>(t) * 2 + 0) * C + c];
-      f2 += partial[(static_cast<long long>(t) * 2 + 1) * C + c];
-      if (++cnt == 16) { a1 += f1; a2 += f2; f1 = f2 = 0.f; cnt = 0; }  // bound the fp32 run length
+    const long long stride = 2LL * C;
+    const float* base = partial + c;
+    int t = ry;
+    for (; t + 96 < T; t += 128) {
+      const float x0 = base[t * stride], y0 = base[t * stride + C];
+      const float x1 = base[(t + 32) * stride], y1 = base[(t + 32) * stride + C];
+      const float x2 = base[(t + 64) * stride], y2 = base[(t + 64) * stride + C];
+      const float x3 = base[(t + 96) * stride], y3 = base[(t + 96) * stride + C];
+      a1 += static_cast<double>((x0 + x1) + (x2 + x3));
+      a2 += static_cast<double>((y0 + y1) + (y2 + y3));
     }
-    a1 += f1; a2 += f2;
+    for (; t < T; t += 32) {
+      a1 += static_cast<double>(base[t * stride]);
+      a2 += static_cast<double>(base[t * stride + C]);
+    }
   }
   sh[0][ry][threadIdx.x] = a1;
   sh[1][ry][threadIdx.x] = a2;
   __syncthreads();
   s1 = 0.0; s2 = 0.0;
   if (ry == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1 += sh[0][j][threadIdx.x]; s2 += sh[1][j][threadIdx.x]; }
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) { s1 += sh[0][j][threadIdx.x]; s2 += sh[1][j][threadIdx.x]; }
   }
 }
-// BatchNorm finalize straight from fp32 partial rows [T][2][C]. grid = ceil(C/32), block = (32, 8).
+// BatchNorm finalize straight from fp32 partial rows [T][2][C]. grid = ceil(C/32), block = (32, 32).
 __global__ void bn_finalize_rows_kernel(const float* __restrict__ partial, int T, int C, double count,
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,

@@ -601,32 +601,46 @@ __global__ void splitk_reduce_rows_kernel(const float* __restrict__ ws, int nspl
 }
 
 // Weight-gradient result: ws[z][f = tap*cin + c][n] -> grad[n][c][tap] (PyTorch parameter layout
-// [nout][cin][ntaps]). The nsplit-fold read dominates, so it is what gets coalesced and parallelised:
-// grid (ceil(cin/32), ceil(N/32), ntaps), block 256 = 8 warps x 32 lanes; a warp owns 4 channel rows, lanes run
-// along n (128-byte rows of the workspace), four splits are in flight per thread. accumulate != 0 adds.
+// [nout][cin][ntaps]). grid (ceil(cin/32), ceil(N/32), ntaps), block 256 = 8 warps x 32 lanes. Reads: a warp owns 4
+// channel rows, lanes run along n (128-byte rows of the workspace), four splits in flight per thread. The 32x32
+// tile is transposed through shared memory so the gradient is written with lanes along c (contiguous for
+// linear layers, stride ntaps for convs). accumulate != 0 adds.
 __global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsplit, int F, int N, int Mpad, int Npad,
                                            int cin, int ntaps, float* __restrict__ grad, int accumulate) {
+  __shared__ float tile[32][33];  // [c][n]
   const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tap = blockIdx.z;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int n = n0 + lane;
   const long long zstride = static_cast<long long>(Mpad) * Npad;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int c = c0 + wrp * 4 + j;
-    if (c >= cin || n >= N) continue;
-    const float* src = ws + (static_cast<long long>(tap) * cin + c) * Npad + n;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int z = 0;
-    for (; z + 4 <= nsplit; z += 4) {
-      a0 += src[(z + 0) * zstride];
-      a1 += src[(z + 1) * zstride];
-      a2 += src[(z + 2) * zstride];
-      a3 += src[(z + 3) * zstride];
+    const int cl = wrp * 4 + j;
+    const int c = c0 + cl, n = n0 + lane;
+    float acc = 0.f;
+    if (c < cin && n < N) {
+      const float* src = ws + (static_cast<long long>(tap) * cin + c) * Npad + n;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int z = 0;
+      for (; z + 4 <= nsplit; z += 4) {
+        a0 += src[(z + 0) * zstride];
+        a1 += src[(z + 1) * zstride];
+        a2 += src[(z + 2) * zstride];
+        a3 += src[(z + 3) * zstride];
+      }
+      for (; z < nsplit; ++z) a0 += src[z * zstride];
+      acc = (a0 + a1) + (a2 + a3);
     }
-    for (; z < nsplit; ++z) a0 += src[z * zstride];
-    const float acc = (a0 + a1) + (a2 + a3);
-    float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
-    *dst = accumulate ? (*dst + acc) : acc;
+    tile[cl][lane] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int nl = wrp * 4 + j;
+    const int n = n0 + nl, c = c0 + lane;
+    if (c < cin && n < N) {
+      float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
+      const float v = tile[lane][nl];
+      *dst = accumulate ? (*dst + v) : v;
+    }
   }
 }
 

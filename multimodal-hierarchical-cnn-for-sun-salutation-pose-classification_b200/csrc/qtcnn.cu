@@ -462,13 +462,8 @@ int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_str
 }
 int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream) {
   if (taps > 32) return fail("wpack_both: too many taps");
-  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
-  const size_t smem = static_cast<size_t>(32) * (32 * (taps | 1) + 1) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(wpack_both_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (32 * 33 + 1) * 4);
-    configured = true;
-  }
+  dim3 grid((cin + 31) / 32, (cout + 7) / 8);
+  const size_t smem = static_cast<size_t>(8) * (32 * (taps | 1) + 1) * sizeof(float);
   wpack_both_kernel<<<grid, 256, smem, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), cout, cin,
                                                   taps);
   return cuda_status("wpack_both");
@@ -800,7 +795,7 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
                    qt_stream_t stream) {
   if (ws_bytes < static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double)) return fail("bn_finalize: workspace too small");
   if (partial_rows <= kDirectRows) {
-    bn_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 8), 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps,
+    bn_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps,
                                                                           momentum, running_mean, running_var, mean, invstd,
                                                                           scale, shift);
     return cuda_status("bn_finalize_rows");
@@ -845,7 +840,7 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
       static_cast<const __nv_bfloat16*>(y), mean, invstd, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
   (void)sums;
-  bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 8), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
+  bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
                                                                             invstd, gamma, dgamma, dbeta, accumulate, eval_mode,
                                                                             coef);
   if (int rc = cuda_status("bn_bwd_finalize")) return rc;
