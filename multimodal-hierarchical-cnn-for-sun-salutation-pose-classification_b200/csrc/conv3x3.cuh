@@ -101,19 +101,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
     const int rbase = t >> 3;
     const uint32_t b_sw = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
     uint32_t a_cnt = 0, b_cnt = 0;   // items issued so far (ring positions)
-    uint32_t pend0 = 0, pend1 = 0;   // full-barrier addresses of the two most recent items (lag-2 publish)
-    uint32_t issued = 0;
-    auto publish = [&](uint32_t bar_addr) {
-      // called right after commit_group of a new item: the item issued two steps ago is complete
-      if (issued >= 2) {
-        cp_async_wait<2>();
-        fence_proxy_async_smem();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend0) : "memory");
-      }
-      pend0 = pend1;
-      pend1 = bar_addr;
-      ++issued;
-    };
+    // cp.async completion is tracked by the mbarriers themselves (cp.async.mbarrier.arrive.noinc): producers run
+    // ahead by the full depth of the rings and never block in wait_group; the issuers fence after their waits.
     bool first_tile = true;
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -146,8 +135,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
             if (wp >= Wp) { wp -= Wp; ++hp; }
             if (hp >= Hp) { hp -= Hp; ++n; }
           }
-          cp_async_commit();
-          publish(smem_u32(&a_full[s]));
+          cp_async_mbar_arrive_noinc(&a_full[s]);
           ++a_cnt;
         }
         if (!p.b_resident || first_tile) {
@@ -163,19 +151,14 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
               const __nv_bfloat16* src = ok ? (p.b + static_cast<long long>(n) * p.wtaps * p.cin + woff) : p.b;
               cp_async16(dst0 + i * 16 * 128, src, ok ? 16u : 0u);
             }
-            cp_async_commit();
-            publish(smem_u32(&b_full[s]));
+            cp_async_mbar_arrive_noinc(&b_full[s]);
             ++b_cnt;
           }
         }
       }
       first_tile = false;
     }
-    // drain the last (up to two) items
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    if (issued >= 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend0) : "memory");
-    if (issued >= 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(pend1) : "memory");
+    cp_async_wait<0>();  // nothing may be in flight when the CTA retires
   } else if (warp >= 8) {
     // ================================================================= MMA issuers (warp 8 + u owns sub-tile u)
     // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform
@@ -199,6 +182,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
         for (int c = 0; c < p.slabs; ++c) {
           const int sa = a_cnt % NSLAB;
           mbar_wait(&a_full[sa], (a_cnt / NSLAB) & 1);
+          fence_proxy_async_smem();
           const uint32_t slab_lo = ((smem_u32(slab_base + sa * slab_bytes) >> 4) & 0x3FFFu) | a_lbo;
 #pragma unroll 1
           for (int tp = 0; tp < 9; ++tp) {
@@ -210,6 +194,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
               sb = b_cnt % NB;
               mbar_wait(&b_full[sb], (b_cnt / NB) & 1);
             }
+            fence_proxy_async_smem();
             tc_fence_after();
             const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
             const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));

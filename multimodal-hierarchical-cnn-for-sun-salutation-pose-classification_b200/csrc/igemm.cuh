@@ -233,16 +233,10 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
         const __nv_bfloat16* src = ok ? (bptr + n * brow_stride + woff) : bptr;
         cp_async16(b_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[(it - kLag) % STAGES]);
-      }
+      // completion tracked by the mbarrier (no wait_group); the issuer fences after its wait
+      cp_async_mbar_arrive_noinc(&full_bar[s]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int j = max(0, nit - kLag); j < nit; ++j) mbar_arrive(&full_bar[j % STAGES]);
+    cp_async_wait<0>();  // nothing may be in flight when the CTA retires
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
     // warp-uniform control flow (descriptor math on the uniform datapath); lane 0 issues
@@ -254,6 +248,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
       for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        fence_proxy_async_smem();
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
         const uint32_t b_lo = a_lo + (L::kABytes >> 4);
@@ -518,16 +513,10 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
         rd[i] += p.adv_d; if (rd[i] >= p.od) { rd[i] -= p.od; rn[i] += 1; }
         rn[i] += p.adv_n;
       }
-      cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[(it - kLag) % STAGES]);
-      }
+      // completion tracked by the mbarrier (no wait_group); the issuer fences after its wait
+      cp_async_mbar_arrive_noinc(&full_bar[s]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int j = max(0, nit - kLag); j < nit; ++j) mbar_arrive(&full_bar[j % STAGES]);
+    cp_async_wait<0>();  // nothing may be in flight when the CTA retires
   } else {
     {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
@@ -538,6 +527,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
       for (int it = 0; it < nit; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        fence_proxy_async_smem();
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
         const uint32_t b_lo = a_lo + (L::kABytes >> 4);
