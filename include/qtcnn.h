@@ -120,10 +120,22 @@ int qt_bn_apply(const void* y, const float* scale, const float* shift, const voi
                 int c, int relu, qt_stream_t stream);
 /* native_batch_norm_backward fused with the ReLU mask: dz = dout*(act>0) when act != NULL;
  * dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); optionally stores dz (identity-branch gradient).
- * eval_mode != 0: statistics were constants (model.eval(), e.g. Grad-CAM), dy = gamma*invstd*dz. */
+ * eval_mode != 0: statistics were constants (model.eval(), e.g. Grad-CAM), dy = gamma*invstd*dz.
+ * act == NULL with mask_scale/mask_shift: the ReLU mask is recomputed as y*mask_scale + mask_shift > 0 (the forward's
+ * own expression), so the activation tensor is not read. */
 int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
-                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, int eval_mode,
-                   void* dy, void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream);
+                   const float* gamma, const float* mask_scale, const float* mask_shift, long long m, int c, float* dgamma,
+                   float* dbeta, int accumulate, int eval_mode, void* dy, void* dz_out, void* ws, size_t ws_bytes,
+                   qt_stream_t stream);
+/* Stem tail fused (bn1 -> relu -> maxpool 3x3/s2/p1, torchvision resnet.py:198-200): one pass forward; backward =
+ * max-pool gather + ReLU mask recomputed from y + BatchNorm backward, never materialising the full-resolution
+ * activated map or its gradient. */
+int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, int n, int h,
+                           int w, int c, qt_stream_t stream);
+int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
+                           float* dgamma, float* dbeta, int eval_mode, void* dy, void* ws, size_t ws_bytes,
+                           qt_stream_t stream);
 int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream);
 int qt_colsum(const void* x, long long m, int c, float* out, int accumulate, void* ws, size_t ws_bytes,
               qt_stream_t stream);

@@ -52,11 +52,11 @@ struct C3Smem {
 };
 
 template <int BN, int MT, int NSLAB, int NB>
-__global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p) {
+__global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p) {
   using L = C3Smem<BN, MT, NSLAB, NB>;
   constexpr uint32_t TCOLS = 2 * MT * BN;  // double-buffered accumulators
   static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
-  static_assert(MT == 2, "one MMA-issuer warp per sub-tile: warps 8 and 9");
+  static_assert(MT == 1 || MT == 2, "one MMA-issuer warp per sub-tile: warps 8 and 9 (warp 9 idles when MT == 1)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_ring = smem;
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_kernel(const __grid_con
       first_tile = false;
     }
     cp_async_wait<0>();  // nothing may be in flight when the CTA retires
+  } else if (warp >= 8 + MT) {
+    // idle issuer warp (MT == 1)
   } else if (warp >= 8) {
     // ================================================================= MMA issuers (warp 8 + u owns sub-tile u)
     // The whole warp runs the (warp-uniform) control flow so descriptor arithmetic stays on the uniform

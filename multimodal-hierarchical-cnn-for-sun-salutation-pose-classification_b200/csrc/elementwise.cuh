@@ -394,9 +394,13 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
 
 // BatchNorm backward, pass 1: dz = dout * (act > 0) (mask only when act != nullptr);
 // partial[blocks][2][C] = { sum dz, sum dz * xhat }, xhat = (y - mean) * invstd.
+// ReLU mask: from the stored activation (act > 0) or, when act == nullptr and msc != nullptr, recomputed from
+// the raw conv output (y*msc + msh > 0 — the forward's own expression, so the mask is identical and the
+// activation tensor need not be read).
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, long long M, int C,
+                                     const float* __restrict__ invstd, const float* __restrict__ msc,
+                                     const float* __restrict__ msh, long long M, int C,
                                      float* __restrict__ partial) {
   extern __shared__ float sm[];
   const int groups = C / 8;
@@ -404,9 +408,13 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   float s1[8] = {0}, s2[8] = {0};
   if (rl < lanes) {
-    float mu[8], is[8];
+    float mu[8], is[8], ms[8], mh[8];
+    const bool ymask = (act == nullptr) && (msc != nullptr);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
+    for (int e = 0; e < 8; ++e) {
+      mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e];
+      ms[e] = ymask ? msc[cg * 8 + e] : 0.f; mh[e] = ymask ? msh[cg * 8 + e] : 1.f;
+    }
     const long long step = static_cast<long long>(gridDim.x) * lanes;
     for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += 2 * step) {
       // two rows in flight per iteration (six independent 16-byte loads)
@@ -424,7 +432,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
       unpack8(qd, d); unpack8(qv, v); unpack8(qa, a);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float dz = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+        const bool off = act ? !(a[e] > 0.f) : !(fmaf(v[e], ms[e], mh[e]) > 0.f);
+        const float dz = off ? 0.f : d[e];
         s1[e] += dz;
         s2[e] += dz * (v[e] - mu[e]) * is[e];
       }
@@ -432,7 +441,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
         unpack8(qd2, d); unpack8(qv2, v); unpack8(qa2, a);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float dz = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+          const bool off = act ? !(a[e] > 0.f) : !(fmaf(v[e], ms[e], mh[e]) > 0.f);
+          const float dz = off ? 0.f : d[e];
           s1[e] += dz;
           s2[e] += dz * (v[e] - mu[e]) * is[e];
         }
@@ -473,8 +483,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int S, i
 // writes dz (gradient of the residual/identity branch).
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
+                                    const float* __restrict__ msc, const float* __restrict__ msh,
                                     __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dz_out,
                                     long long total8, int C) {
+  const bool ymask = (act == nullptr) && (msc != nullptr);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>((i * 8) % C);
@@ -489,9 +501,17 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
     *reinterpret_cast<float4*>(cb + 4) = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + 4));
     *reinterpret_cast<float4*>(ck) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0));
     *reinterpret_cast<float4*>(ck + 4) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4));
+    float ms[8], mh[8];
+    if (ymask) {
+      *reinterpret_cast<float4*>(ms) = __ldg(reinterpret_cast<const float4*>(msc + c0));
+      *reinterpret_cast<float4*>(ms + 4) = __ldg(reinterpret_cast<const float4*>(msc + c0 + 4));
+      *reinterpret_cast<float4*>(mh) = __ldg(reinterpret_cast<const float4*>(msh + c0));
+      *reinterpret_cast<float4*>(mh + 4) = __ldg(reinterpret_cast<const float4*>(msh + c0 + 4));
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float dzv = (act && !(a[e] > 0.f)) ? 0.f : d[e];
+      const bool off = act ? !(a[e] > 0.f) : (ymask && !(fmaf(v[e], ms[e], mh[e]) > 0.f));
+      const float dzv = off ? 0.f : d[e];
       o[e] = fmaf(ca[e], dzv, fmaf(cb[e], v[e], ck[e]));
       d[e] = dzv;
     }
@@ -628,6 +648,158 @@ __global__ void maxpool2d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, con
       }
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem tail fused: BatchNorm-apply + ReLU + MaxPool2d(3,2,1) in one pass over the raw conv output, and its
+// backward (max-pool gather + ReLU mask recomputed from y + BatchNorm backward) without ever materialising the
+// 112x112 activated map or its gradient (torchvision resnet.py:198-200).
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                           signed char* __restrict__ argmax, int N, int H, int W, int C, int Ho, int Wo) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = i % groups;
+    const int wo = (i / groups) % Wo;
+    const int ho = (i / (static_cast<long long>(groups) * Wo)) % Ho;
+    const int n = i / (static_cast<long long>(groups) * Wo * Ho);
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = -1; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int w = wo * 2 - 1 + q;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + ((static_cast<long long>(n) * H + h) * W + w) * C + cg * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // same rounding as the unfused path: the activated value is a bf16
+          const float a = bf16_round(fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f));
+          if (a > best[e] || bi[e] < 0) { best[e] = a; bi[e] = r * 3 + q; }
+        }
+      }
+    }
+    const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
+    *reinterpret_cast<uint4*>(out + o) = pack8(best);
+    if (argmax) {
+      uint2 pk;
+      pk.x = (bi[0] & 0xff) | ((bi[1] & 0xff) << 8) | ((bi[2] & 0xff) << 16) | ((bi[3] & 0xff) << 24);
+      pk.y = (bi[4] & 0xff) | ((bi[5] & 0xff) << 8) | ((bi[6] & 0xff) << 16) | ((bi[7] & 0xff) << 24);
+      *reinterpret_cast<uint2*>(argmax + o) = pk;
+    }
+  }
+}
+// dz at conv-output pixel (n,h,w), 8 channels: gather the pooled gradient through the arg-max plane and apply the
+// ReLU mask recomputed from y.
+__device__ __forceinline__ void stem_dz8(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                                         const float (&yv)[8], const float (&sc)[8], const float (&sh)[8], int n, int h,
+                                         int w, int cg, int C, int Ho, int Wo, float (&dz)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dz[e] = 0.f;
+  const int ho_lo = max(0, h / 2), ho_hi = min(Ho - 1, (h + 1) / 2);
+  const int wo_lo = max(0, w / 2), wo_hi = min(Wo - 1, (w + 1) / 2);
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    const int r = h - (ho * 2 - 1);
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      const int q = w - (wo * 2 - 1);
+      const int code = r * 3 + q;
+      const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
+      const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
+      float d[8];
+      unpack8(*reinterpret_cast<const uint4*>(dpool + o), d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int a = (e < 4 ? (pk.x >> (8 * e)) : (pk.y >> (8 * (e - 4)))) & 0xff;
+        if (a == code) dz[e] += d[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (!(fmaf(yv[e], sc[e], sh[e]) > 0.f)) dz[e] = 0.f;
+}
+// pass 1: partial[blocks][2][C] = { sum dz, sum dz*xhat }
+__global__ void stem_bn_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                                               const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                               const float* __restrict__ shift, const float* __restrict__ mean,
+                                               const float* __restrict__ invstd, int N, int H, int W, int C, int Ho, int Wo,
+                                               float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int groups = C / 8;
+  const int lanes = blockDim.x / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float s1[8] = {0}, s2[8] = {0};
+  if (rl < lanes) {
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = scale[cg * 8 + e]; sh[e] = shift[cg * 8 + e]; mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
+    const long long M = static_cast<long long>(N) * H * W;
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
+      const int w = r % W;
+      const int h = (r / W) % H;
+      const int n = r / (static_cast<long long>(W) * H);
+      float yv[8], dz[8];
+      unpack8(ld_nc16(y + r * C + cg * 8), yv);
+      stem_dz8(dpool, argmax, yv, sc, sh, n, h, w, cg, C, Ho, Wo, dz);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1[e] += dz[e]; s2[e] += dz[e] * (yv[e] - mu[e]) * is[e]; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sm[(rl * 2 + 0) * C + cg * 8 + e] = s1[e];
+      sm[(rl * 2 + 1) * C + cg * 8 + e] = s2[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * 2 * C + i];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C + i] = acc;
+  }
+}
+// pass 2: dy = A*dz + B*y + K (coef = [A | B | K])
+__global__ void stem_bn_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                                              const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                              const float* __restrict__ shift, const float* __restrict__ coef,
+                                              __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int Ho, int Wo) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(N) * H * W * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = i % groups;
+    const int w = (i / groups) % W;
+    const int h = (i / (static_cast<long long>(groups) * W)) % H;
+    const int n = i / (static_cast<long long>(groups) * W * H);
+    float sc[8], sh[8], ca[8], cb[8], ck[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      *reinterpret_cast<float4*>(sc + e) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + e));
+      *reinterpret_cast<float4*>(sh + e) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + e));
+      *reinterpret_cast<float4*>(ca + e) = __ldg(reinterpret_cast<const float4*>(coef + cg * 8 + e));
+      *reinterpret_cast<float4*>(cb + e) = __ldg(reinterpret_cast<const float4*>(coef + C + cg * 8 + e));
+      *reinterpret_cast<float4*>(ck + e) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + cg * 8 + e));
+    }
+    float yv[8], dz[8], o[8];
+    unpack8(ld_nc16(y + i * 8), yv);
+    stem_dz8(dpool, argmax, yv, sc, sh, n, h, w, cg, C, Ho, Wo, dz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = fmaf(ca[e], dz[e], fmaf(cb[e], yv[e], ck[e]));
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
   }
 }
 

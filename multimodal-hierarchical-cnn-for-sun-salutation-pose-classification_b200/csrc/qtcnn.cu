@@ -255,6 +255,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->pad_d != 0) return pl;
   if (d->groups != 1) return pl;
+  if (d->in_w < 10 && g_tune[4] == 0) return pl;  // 7x7 maps: 65 % border overhead, the gather kernel is faster (profiles/r01_conv_tuning.md)
   if (cin % 64 || nout % 32) return pl;
   if (flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32)) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
@@ -262,7 +263,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.bn = nout <= 64 ? 64 : 128;
-  pl.mt = 2;
+  pl.mt = (g_tune[5] == 1 && pl.bn == 128) ? 1 : 2;  // experimental: 128-pixel tiles, two CTAs per SM
   const int bm = kBM * pl.mt;
   pl.R = ((bm + 2 * (d->in_w + 3)) + 15) / 16 * 16;
   pl.plane_stride = pl.R * 16 + 16;
@@ -280,6 +281,10 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
     pl.resident = (slabs == 1 && pl.num_n_tiles == 1) ? 1 : 0;
     pl.nslab = 3;
     if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
+  } else if (pl.mt == 1) {
+    pl.nb = 3;
+    pl.resident = 0;
+    pl.nslab = 2;
   } else {
     pl.nb = 6;
     pl.resident = 0;
@@ -328,6 +333,10 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
       p.wtap[t] = static_cast<short>(t);
     }
   const int tiles = pl.num_m_tiles * pl.num_n_tiles;
+  if (pl.mt == 1) {
+    const int g2 = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+    return launch_conv3x3<128, 1, 2, 3>(p, pl.smem, g2, st);
+  }
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (pl.bn == 64) {
     if (pl.nslab == 3) return launch_conv3x3<64, 2, 3, 9>(p, pl.smem, grid, st);
@@ -354,6 +363,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->groups != 1) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
+  if (d->in_w < 10 && g_tune[4] == 0) return pl;
   if (d->in_c == 64 && d->out_c == 64) pl.cfg = 0;
   else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
   else return pl;
@@ -482,7 +492,7 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
-  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; return tiles < kNumSMs ? tiles : kNumSMs; }
+  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; const int cap = pl.mt == 1 ? 2 * kNumSMs : kNumSMs; return tiles < cap ? tiles : cap; }
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));
@@ -824,8 +834,9 @@ int qt_bn_apply(const void* y, const float* scale, const float* shift, const voi
   return cuda_status("bn_apply");
 }
 int qt_bn_backward(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
-                   const float* gamma, long long m, int c, float* dgamma, float* dbeta, int accumulate, int eval_mode,
-                   void* dy, void* dz_out, void* ws, size_t ws_bytes, qt_stream_t stream) {
+                   const float* gamma, const float* mask_scale, const float* mask_shift, long long m, int c, float* dgamma,
+                   float* dbeta, int accumulate, int eval_mode, void* dy, void* dz_out, void* ws, size_t ws_bytes,
+                   qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_backward: c must be a multiple of 8 and <= 2048");
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_backward: workspace too small");
   double* sums = static_cast<double*>(ws);
@@ -837,7 +848,7 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
   bn_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
-      static_cast<const __nv_bfloat16*>(y), mean, invstd, m, c, partial);
+      static_cast<const __nv_bfloat16*>(y), mean, invstd, mask_scale, mask_shift, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
   (void)sums;
   bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
@@ -847,9 +858,46 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
   const long long total8 = m * c / 8;
   bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
-      static_cast<const __nv_bfloat16*>(y), coef, static_cast<__nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dz_out), total8,
-      c);
+      static_cast<const __nv_bfloat16*>(y), coef, mask_scale, mask_shift, static_cast<__nv_bfloat16*>(dy),
+      static_cast<__nv_bfloat16*>(dz_out), total8, c);
   return cuda_status("bn_bwd_apply");
+}
+int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, int n, int h,
+                           int w, int c, qt_stream_t stream) {
+  if (c % 8) return fail("bn_relu_maxpool: c must be a multiple of 8");
+  const int ho = out_dim(h, 3, 2, 1), wo = out_dim(w, 3, 2, 1);
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
+  bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(y), scale, shift,
+                                                                          static_cast<__nv_bfloat16*>(out),
+                                                                          static_cast<signed char*>(argmax), n, h, w, c, ho, wo);
+  return cuda_status("bn_relu_maxpool_fwd");
+}
+int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
+                           float* dgamma, float* dbeta, int eval_mode, void* dy, void* ws, size_t ws_bytes,
+                           qt_stream_t stream) {
+  if (c % 8 || c > 2048) return fail("bn_relu_maxpool_bwd: c must be a multiple of 8 and <= 2048");
+  if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_relu_maxpool_bwd: workspace too small");
+  const int ho = out_dim(h, 3, 2, 1), wo = out_dim(w, 3, 2, 1);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
+  float* coef = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;
+  const int block = rowlane_block(c);
+  const int lanes = block / (c / 8);
+  const long long m = static_cast<long long>(n) * h * w;
+  long long want = (m + lanes - 1) / lanes;
+  const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
+  stem_bn_pool_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
+      shift, mean, invstd, n, h, w, c, ho, wo, partial);
+  if (int rc = cuda_status("stem_bn_pool_bwd_reduce")) return rc;
+  bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
+                                                                             invstd, gamma, dgamma, dbeta, 0, eval_mode, coef);
+  if (int rc = cuda_status("bn_bwd_finalize")) return rc;
+  const long long total = m * (c / 8);
+  stem_bn_pool_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
+      shift, coef, static_cast<__nv_bfloat16*>(dy), n, h, w, c, ho, wo);
+  return cuda_status("stem_bn_pool_bwd_apply");
 }
 int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream) {
   if (n % 8) return fail("relu_backward: n must be a multiple of 8");

@@ -63,33 +63,36 @@ class _StemFn(torch.autograd.Function):
             check(L().qt_stem_fprop(ptr(xp), ptr(w8), ptr(y), ptr(stats), n, h, w, cout, stream()), "stem_fprop")
         ops._count(2)
         st = ops.bn_finalize(stats, n * ho * wo, bn_mod, cout, dev, training)
-        a = torch.empty_like(y)
-        ops.bn_apply(y, st, a, None, True)
         po, qo = capi.out_size(ho, 3, 2, 1), capi.out_size(wo, 3, 2, 1)
         out = torch.empty(n, po, qo, cout, device=dev, dtype=BF16)
         need_bwd = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
         am = torch.empty(n, po, qo, cout, device=dev, dtype=torch.int8) if need_bwd else None
-        check(L().qt_maxpool2d_fwd(ptr(a), ptr(out), ptr(am), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_fwd")
+        # bn1 + relu + maxpool in one pass: the 112x112 activated map is never written
+        check(L().qt_bn_relu_maxpool_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(am), n, ho, wo, cout, stream()),
+              "bn_relu_maxpool_fwd")
         ops._count()
         if need_bwd:
-            ctx.saved = (xp, y, a, am, st, conv_w, bn_w)
+            ctx.saved = (xp, y, am, st, conv_w, bn_w)
             ctx.dims = (n, h, w, cout, ho, wo)
             ctx.training = training
         return ops.as_nchw_view(out)
 
     @staticmethod
     def backward(ctx, dout):
-        xp, y, a, am, st, conv_w, bn_w = ctx.saved
+        xp, y, am, st, conv_w, bn_w = ctx.saved
         n, h, w, cout, ho, wo = ctx.dims
         dev = y.device
         dout = ops.as_nhwc(dout)
+        dgamma = torch.empty(cout, device=dev)
+        dbeta = torch.empty(cout, device=dev)
+        # max-pool gather, then BatchNorm backward with the ReLU mask recomputed from y (the activated 112x112 map
+        # was never stored). The fully fused backward (qt_bn_relu_maxpool_bwd) measured slower than these two
+        # streaming passes (profiles/r01_conv_tuning.md).
         da = torch.empty_like(y)
         check(L().qt_maxpool2d_bwd(ptr(dout), ptr(am), ptr(da), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_bwd")
         ops._count()
-        dgamma = torch.empty(cout, device=dev)
-        dbeta = torch.empty(cout, device=dev)
         dy = torch.empty_like(y)
-        ops.bn_backward(da, a, y, st, bn_w.detach(), dgamma, dbeta, dy, None, eval_mode=not ctx.training)
+        ops.bn_backward(da, None, y, st, bn_w.detach(), dgamma, dbeta, dy, None, eval_mode=not ctx.training, mask_from_y=True)
         dw = None
         if ctx.needs_input_grad[1]:
             dw = _zeros_like_param(conv_w)
@@ -171,7 +174,7 @@ class _BlockFn(torch.autograd.Function):
         # bn1 + ReLU
         dg1, db1 = vec(), vec()
         dy1 = torch.empty_like(y1)
-        ops.bn_backward(da1, a1, y1, st1, g1.detach(), dg1, db1, dy1, None, eval_mode=ev)
+        ops.bn_backward(da1, None, y1, st1, g1.detach(), dg1, db1, dy1, None, eval_mode=ev, mask_from_y=True)
         dw1 = None
         if need[1]:
             dw1 = _zeros_like_param(w1)

@@ -266,11 +266,14 @@ def bn_apply(y, st: BNState, out, residual=None, relu=True):
     return out
 
 
-def bn_backward(dout, act, y, st: BNState, gamma, dgamma, dbeta, dy, dz_out=None, eval_mode=False):
+def bn_backward(dout, act, y, st: BNState, gamma, dgamma, dbeta, dy, dz_out=None, eval_mode=False, mask_from_y=False):
+    """act: stored post-ReLU output (mask act > 0), or None. mask_from_y=True (with act=None) recomputes the ReLU mask
+    from y with this BatchNorm's own scale/shift — valid when the layer is BN -> ReLU with no residual add."""
     c = y.shape[-1]
     m = y.numel() // c
     ws = workspace(L().qt_bn_workspace_bytes(c), y.device, "bn")
-    check(L().qt_bn_backward(ptr(dout), ptr(act), ptr(y), ptr(st.mean), ptr(st.invstd), ptr(gamma), m, c, ptr(dgamma),
+    msc, msh = (ptr(st.scale), ptr(st.shift)) if (mask_from_y and act is None) else (None, None)
+    check(L().qt_bn_backward(ptr(dout), ptr(act), ptr(y), ptr(st.mean), ptr(st.invstd), ptr(gamma), msc, msh, m, c, ptr(dgamma),
                              ptr(dbeta), 0, 1 if eval_mode else 0, ptr(dy), ptr(dz_out), ptr(ws), ws.numel(), stream()),
           "bn_backward")
     _count(4)

@@ -293,7 +293,7 @@ def test_batchnorm_train(C, m, c, residual, relu):
     dy = torch.empty_like(y)
     dz = torch.empty_like(y)
     act = out if relu else None
-    run(C, C.lib().qt_bn_backward(C.ptr(dout), C.ptr(act), C.ptr(y), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), m, c,
+    run(C, C.lib().qt_bn_backward(C.ptr(dout), C.ptr(act), C.ptr(y), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), None, None, m, c,
                                   C.ptr(dgamma), C.ptr(dbeta), 0, 0, C.ptr(dy), C.ptr(dz), C.ptr(ws), ws_bytes, C.stream()),
         "bn_backward")
     # the reference mask comes from fp32 activations; ours from the bf16-rounded ones -> compare loosely on dy
@@ -448,3 +448,45 @@ def test_wpack_both(C, cout, cin, taps):
     run(C, C.lib().qt_wpack_both(C.ptr(w), C.ptr(wf), C.ptr(wd), cout, cin, taps, C.stream()), "wpack_both")
     assert torch.equal(wf, bf16(w).permute(0, 2, 1).contiguous())
     assert torch.equal(wd, bf16(w).permute(1, 2, 0).contiguous())
+
+
+def test_fused_stem_tail(C):
+    """bn1 + relu + maxpool(3,2,1) fused forward / backward vs torch autograd on the same bf16 conv output."""
+    n, h, w, c = 3, 22, 26, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    y = bf16(torch.randn(n, c, h, w, device="cuda", generator=g) * 1.5 + 0.3)
+    gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+    beta = 0.3 * torch.randn(c, device="cuda", generator=g)
+    yf = y.float().requires_grad_(True)
+    gref, bref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(yf, None, None, gref, bref, True, 0.1, 1e-5)
+    act = z.relu()
+    act = act + (bf16(act).float() - act).detach()  # the product stores bf16 activations: ties break on the rounded values
+    pooled = F.max_pool2d(act, 3, 2, 1)
+    dpool = bf16(torch.randn_like(pooled))
+    pooled.backward(dpool.float())
+    # our statistics
+    y_nhwc = y.permute(0, 2, 3, 1).contiguous()
+    m = n * h * w
+    rows = 29
+    partial = torch.zeros(rows, 2, c, device="cuda")
+    run(C, C.lib().qt_bn_stats(C.ptr(y_nhwc), m, c, C.ptr(partial), rows, C.stream()), "bn_stats")
+    ws_bytes = C.lib().qt_bn_workspace_bytes(c)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    mean, invstd, scale, shift = (torch.empty(c, device="cuda") for _ in range(4))
+    run(C, C.lib().qt_bn_finalize(C.ptr(partial), rows, c, float(m), C.ptr(gamma), C.ptr(beta), 1e-5, 0.1, None, None, C.ptr(mean),
+                                  C.ptr(invstd), C.ptr(scale), C.ptr(shift), C.ptr(ws), ws_bytes, C.stream()), "bn_finalize")
+    ho, wo = pooled.shape[2], pooled.shape[3]
+    out = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.bfloat16)
+    am = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.int8)
+    run(C, C.lib().qt_bn_relu_maxpool_fwd(C.ptr(y_nhwc), C.ptr(scale), C.ptr(shift), C.ptr(out), C.ptr(am), n, h, w, c, C.stream()),
+        "bn_relu_maxpool_fwd")
+    report("fused stem tail fwd", out.permute(0, 3, 1, 2), pooled.detach(), BF16_REL_L2, True)
+    dy = torch.empty_like(y_nhwc)
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    run(C, C.lib().qt_bn_relu_maxpool_bwd(C.ptr(dpool.permute(0, 2, 3, 1).contiguous()), C.ptr(am), C.ptr(y_nhwc), C.ptr(scale),
+                                          C.ptr(shift), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), n, h, w, c, C.ptr(dgamma),
+                                          C.ptr(dbeta), 0, C.ptr(dy), C.ptr(ws), ws_bytes, C.stream()), "bn_relu_maxpool_bwd")
+    report("fused stem tail dgamma", dgamma, gref.grad, 2e-2)
+    report("fused stem tail dbeta", dbeta, bref.grad, 2e-2)
+    report("fused stem tail dy", dy.permute(0, 3, 1, 2), yf.grad, 2e-2)
