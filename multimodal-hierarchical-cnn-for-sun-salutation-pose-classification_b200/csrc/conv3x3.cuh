@@ -18,11 +18,13 @@
 // MMA issuer. Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
 // tile i+1; when the whole filter fits in the B ring (64->64 layers) it is loaded once and stays resident.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "igemm.cuh"
 
 namespace qt {
 
-constexpr int kC3Threads = 320;  // 4 epilogue + 4 producer + 2 MMA-issuer warps
+constexpr int kC3Threads = 352;  // 4 epilogue + 4 A-slab producer + 2 MMA-issuer warps + 1 TMA (weights) warp
 
 struct Conv3x3Params {
   const __nv_bfloat16* a;   // dense NHWC input  [N][H][W][cin]
@@ -38,6 +40,7 @@ struct Conv3x3Params {
   int R;                    // slab rows (multiple of 16)
   int plane_stride;         // bytes, R*16 + 16
   int b_resident;           // 1: all 9*slabs weight tiles stay in the B ring
+  int b_tma;                // 1: weight tiles arrive by TMA (cp.async.bulk.tensor.2d through `wmap`), else cp.async
   signed char off_h[9], off_w[9];
   short wtap[9];
 };
@@ -52,7 +55,8 @@ struct C3Smem {
 };
 
 template <int BN, int MT, int NSLAB, int NB>
-__global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p) {
+__global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p,
+                                                                                const __grid_constant__ CUtensorMap wmap) {
   using L = C3Smem<BN, MT, NSLAB, NB>;
   constexpr uint32_t TCOLS = 2 * MT * BN;  // double-buffered accumulators
   static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     if (lane == 0) {
       // two MMA-issuer warps (one per 128-row sub-tile) release every operand / accumulator stage together
       for (int s = 0; s < NSLAB; ++s) { mbar_init(&a_full[s], kProducerThreads); mbar_init(&a_empty[s], MT); }
-      for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], kProducerThreads); mbar_init(&b_empty[s], MT); }
+      for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], p.b_tma ? 1 : kProducerThreads); mbar_init(&b_empty[s], MT); }
       for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], MT); mbar_init(&acc_empty[s], kProducerThreads); }
       fence_mbar_init();
     }
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           cp_async_mbar_arrive_noinc(&a_full[s]);
           ++a_cnt;
         }
-        if (!p.b_resident || first_tile) {
+        if (!p.b_tma && (!p.b_resident || first_tile)) {
           for (int tp = 0; tp < 9; ++tp) {
             const int s = b_cnt % NB;
             if (!p.b_resident && b_cnt >= NB) mbar_wait(&b_empty[s], ((b_cnt / NB) - 1) & 1);
@@ -159,6 +163,36 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       first_tile = false;
     }
     cp_async_wait<0>();  // nothing may be in flight when the CTA retires
+  } else if (warp == 10) {
+    // ================================================================= TMA producer for the weight tiles
+    // box = [BN rows][64 K-elements] of the 2-D weight matrix [nout][9*cin], 128B-swizzled by the TMA unit —
+    // byte-identical to what the cp.async path writes. One instruction per (tap, slab) tile.
+    if (p.b_tma && lane == 0) {
+      uint32_t b_cnt = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+        if (!p.b_resident || first_tile) {
+          for (int c = 0; c < p.slabs; ++c) {
+            for (int tp = 0; tp < 9; ++tp) {
+              const int s = b_cnt % NB;
+              if (!p.b_resident && b_cnt >= NB) mbar_wait(&b_empty[s], ((b_cnt / NB) - 1) & 1);
+              mbar_arrive_expect_tx(&b_full[s], L::kBTile);
+              const int kx = p.wtap[tp] * p.cin + c * 64;
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                      smem_u32(b_ring + s * L::kBTile)),
+                  "l"(reinterpret_cast<uint64_t>(&wmap)), "r"(kx), "r"(n0), "r"(smem_u32(&b_full[s]))
+                  : "memory");
+              ++b_cnt;
+            }
+          }
+        }
+        first_tile = false;
+      }
+    }
+    __syncwarp();
   } else if (warp >= 8 + MT) {
     // idle issuer warp (MT == 1)
   } else if (warp >= 8) {

@@ -297,14 +297,48 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   return pl;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// 2-D bf16 matrix [rows][cols] (cols contiguous), box [box_rows][64 cols], 128B swizzle, zero OOB fill.
+bool make_weight_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, int MT, int NSLAB, int NB>
-int launch_conv3x3(const Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
+int launch_conv3x3(Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
   static size_t configured = 0;
   if (configured < smem) {
     cudaFuncSetAttribute(conv3x3_kernel<BN, MT, NSLAB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  conv3x3_kernel<BN, MT, NSLAB, NB><<<grid, kC3Threads, smem, st>>>(p);
+  alignas(64) CUtensorMap wmap;
+  memset(&wmap, 0, sizeof(wmap));
+  p.b_tma = (g_tune[6] == 0 && (reinterpret_cast<uintptr_t>(p.b) & 15) == 0 &&
+             make_weight_tmap(&wmap, p.b, p.nout, static_cast<long long>(p.wtaps) * p.cin, BN))
+                ? 1 : 0;
+  conv3x3_kernel<BN, MT, NSLAB, NB><<<grid, kC3Threads, smem, st>>>(p, wmap);
   return cuda_status("conv3x3_kernel");
 }
 
