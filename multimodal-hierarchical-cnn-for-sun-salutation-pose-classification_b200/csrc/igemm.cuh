@@ -15,6 +15,8 @@
 // dgrad (off = pad - r, flipped taps), parity-decomposed stride-2 dgrad, the four quadrant
 // views of the quadtree split (group offsets) and plain linear layers (one tap, 1x1 grid).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only)
+
 #include "ptx.cuh"
 
 namespace qt {
@@ -66,6 +68,7 @@ struct IgemmParams {
   int M, num_kb, kb_per_split;
   int Mpad, Npad;
   int adv_n, adv_d, adv_h, adv_w;  // wgrad: 64 pixels decomposed over (n, od, oh, ow)
+  int b_tma;  // K-major kernel: 0 = weights by cp.async, 1 = by TMA (k-block inside one tap), 2 = by TMA (natural tap order)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -152,7 +155,8 @@ struct KMajorSmem {
 // K-major kernel: fprop / dgrad / linear
 // =============================================================================================
 template <int BN, int STAGES, int kLag, int NPW>
-__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p,
+                                                                                       const __grid_constant__ CUtensorMap bmap) {
   using L = KMajorSmem<BN, STAGES>;
   constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(&full_bar[s], kNP);
+        mbar_init(&full_bar[s], kNP + (p.b_tma ? 1 : 0));  // + the expect_tx arrive of the TMA weight tile
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(accum_bar, 1);
@@ -218,6 +222,22 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
       uint8_t* stage = smem + s * L::kStageBytes;
       const uint32_t a_dst = smem_u32(stage) + rbase * 128 + sw_off;
       const uint32_t b_dst = smem_u32(stage + L::kABytes) + rbase * 128 + sw_off;
+      if (p.b_tma && t == 0) {
+        // weight tile [BN rows][64 K] by one TMA instruction (128B-swizzled by the copy engine, zero OOB fill)
+        const int kbase = (kb_begin + it) * kBK;
+        int kx = kbase;
+        if (p.b_tma == 1) {
+          const int tp1 = p.ntaps > 1 ? (kbase >> p.cin_log2) : 0;
+          const int c1 = p.ntaps > 1 ? (kbase & (p.cin - 1)) : kbase;
+          kx = p.wtap[tp1] * p.cin + c1;
+        }
+        mbar_arrive_expect_tx(&full_bar[s], BN * 128);
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                smem_u32(stage + L::kABytes)),
+            "l"(reinterpret_cast<uint64_t>(&bmap)), "r"(kx), "r"(n0), "r"(smem_u32(&full_bar[s]))
+            : "memory");
+      }
 #pragma unroll
       for (int i = 0; i < kARows; ++i) {
         const bool ok = tap_ok && rc[i].base >= 0 && static_cast<unsigned>(rc[i].cd + td) < static_cast<unsigned>(p.id) &&
@@ -226,12 +246,14 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
         const __nv_bfloat16* src = ok ? (p.a + rc[i].base + toff) : p.a;
         cp_async16(a_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
       }
+      if (!p.b_tma) {
 #pragma unroll
-      for (int i = 0; i < BN / kRowStep; ++i) {
-        const int n = n0 + rbase + kRowStep * i;
-        const bool ok = tap_ok && n < p.nout;
-        const __nv_bfloat16* src = ok ? (bptr + n * brow_stride + woff) : bptr;
-        cp_async16(b_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
+        for (int i = 0; i < BN / kRowStep; ++i) {
+          const int n = n0 + rbase + kRowStep * i;
+          const bool ok = tap_ok && n < p.nout;
+          const __nv_bfloat16* src = ok ? (bptr + n * brow_stride + woff) : bptr;
+          cp_async16(b_dst + i * kRowStep * 128, src, ok ? 16u : 0u);
+        }
       }
       // completion tracked by the mbarrier (no wait_group); the issuer fences after its wait
       cp_async_mbar_arrive_noinc(&full_bar[s]);

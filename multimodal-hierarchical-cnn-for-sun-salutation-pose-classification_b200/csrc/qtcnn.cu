@@ -53,16 +53,30 @@ constexpr int kNumSMs = 148;
 // GEMM launch helpers
 // ------------------------------------------------------------------------------------------------
 int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [0] wgrad pipeline variant, [1] kmajor pipeline variant
+bool make_weight_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows);
 
 template <int BN, int STAGES, int LAG, int NPW>
-int launch_kmajor(const IgemmParams& p, dim3 grid, cudaStream_t st) {
+int launch_kmajor(IgemmParams& p, dim3 grid, cudaStream_t st) {
   using L = KMajorSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(igemm_kmajor_kernel<BN, STAGES, LAG, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     configured = true;
   }
-  igemm_kmajor_kernel<BN, STAGES, LAG, NPW><<<grid, NPW == 8 ? kGemmThreadsWide : kGemmThreads, L::kTotal, st>>>(p);
+  // Weight tiles by TMA when a 64-wide k-block maps onto 64 contiguous columns of the [nout][wtaps*cin] matrix.
+  alignas(64) CUtensorMap bmap;
+  memset(&bmap, 0, sizeof(bmap));
+  p.b_tma = 0;
+  const long long cols = static_cast<long long>(p.wtaps) * p.cin;
+  bool natural = true;
+  for (int t = 0; t < p.ntaps; ++t) natural = natural && (p.wtap[t] == t);
+  int mode = 0;
+  if (p.ntaps == 1 || p.cin % 64 == 0) mode = 1;
+  else if (natural) mode = 2;
+  if (g_tune[6] == 0 && mode && p.groups >= 1 && p.b_goff[0] == 0 && p.b_goff[1] == 0 && p.b_goff[2] == 0 && p.b_goff[3] == 0 &&
+      (reinterpret_cast<uintptr_t>(p.b) & 15) == 0 && (cols % 8) == 0 && make_weight_tmap(&bmap, p.b, p.nout, cols, BN))
+    p.b_tma = mode;
+  igemm_kmajor_kernel<BN, STAGES, LAG, NPW><<<grid, NPW == 8 ? kGemmThreadsWide : kGemmThreads, L::kTotal, st>>>(p, bmap);
   return cuda_status("igemm_kmajor_kernel");
 }
 template <int BN, int STAGES, int LAG, int NPW>
@@ -82,7 +96,7 @@ inline int pick_bn(int nout) { return nout <= 64 ? 64 : 128; }
 // Chooses split-K and launches the K-major kernel (+ the split-K reduction when used).
 // `dense_out_ld` > 0 means the output is a dense row-major [M][nout] matrix with that row stride
 // (required for split-K).
-int run_kmajor(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, long long dense_out_ld) {
+int run_kmajor(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, long long dense_out_ld) {  // p by value: launch_kmajor edits it
   const int BN = pick_bn(p.nout);
   const int gx = (p.M + kBM - 1) / kBM, gy = (p.nout + BN - 1) / BN;
   p.num_kb = (p.ntaps * p.cin + kBK - 1) / kBK;
