@@ -72,19 +72,19 @@ class _StemFn(torch.autograd.Function):
               "bn_relu_maxpool_fwd")
         ops._count()
         if need_bwd:
-            ctx.saved = (xp, y, am, st, conv_w, bn_w)
+            ctx.saved = (xp, y, am, st, conv_w, bn_w, bn_b)
             ctx.dims = (n, h, w, cout, ho, wo)
             ctx.training = training
         return ops.as_nchw_view(out)
 
     @staticmethod
     def backward(ctx, dout):
-        xp, y, am, st, conv_w, bn_w = ctx.saved
+        xp, y, am, st, conv_w, bn_w, bn_b = ctx.saved
         n, h, w, cout, ho, wo = ctx.dims
         dev = y.device
         dout = ops.as_nhwc(dout)
-        dgamma = torch.empty(cout, device=dev)
-        dbeta = torch.empty(cout, device=dev)
+        dgamma = ops.grad_out(bn_w)
+        dbeta = ops.grad_out(bn_b)
         # max-pool gather, then BatchNorm backward with the ReLU mask recomputed from y (the activated 112x112 map
         # was never stored). The fully fused backward (qt_bn_relu_maxpool_bwd) measured slower than these two
         # streaming passes (profiles/r01_conv_tuning.md).
@@ -142,14 +142,14 @@ class _BlockFn(torch.autograd.Function):
         out = torch.empty_like(y1)
         ops.bn_apply(y2, st2, out, idn, True)
         if any(ctx.needs_input_grad):
-            ctx.saved = (xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd)
+            ctx.saved = (xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd, b1, b2, bd)
             ctx.descs = (d1, d2, dd)
             ctx.training = training
         return ops.as_nchw_view(out)
 
     @staticmethod
     def backward(ctx, dout):
-        xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd = ctx.saved
+        xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd, b1, b2, bd = ctx.saved
         d1, d2, dd = ctx.descs
         ev = not ctx.training
         dev = xb.device
@@ -161,7 +161,7 @@ class _BlockFn(torch.autograd.Function):
             return torch.empty(cout, device=dev)
 
         # bn2 + residual ReLU
-        dg2, db2 = vec(), vec()
+        dg2, db2 = ops.grad_out(g2), ops.grad_out(b2)
         dy2 = torch.empty_like(y2)
         dz = torch.empty_like(y2)
         ops.bn_backward(dout, out, y2, st2, g2.detach(), dg2, db2, dy2, dz, eval_mode=ev)
@@ -172,7 +172,7 @@ class _BlockFn(torch.autograd.Function):
         da1 = torch.empty_like(a1)
         ops.conv_dgrad(d2, dy2, ops.packed_dgrad(w2), da1)
         # bn1 + ReLU
-        dg1, db1 = vec(), vec()
+        dg1, db1 = ops.grad_out(g1), ops.grad_out(b1)
         dy1 = torch.empty_like(y1)
         ops.bn_backward(da1, None, y1, st1, g1.detach(), dg1, db1, dy1, None, eval_mode=ev, mask_from_y=True)
         dw1 = None
@@ -182,7 +182,7 @@ class _BlockFn(torch.autograd.Function):
         dwd = dgd = dbd = None
         dx = None
         if wd is not None:
-            dgd, dbd = vec(), vec()
+            dgd, dbd = ops.grad_out(gd), ops.grad_out(bd)
             dyd = torch.empty_like(yd)
             ops.bn_backward(dz, None, yd, std, gd.detach(), dgd, dbd, dyd, None, eval_mode=ev)
             if need[7]:
@@ -336,13 +336,13 @@ class _QuadHeadFn(torch.autograd.Function):
                                       None, 0, stream()), "classifier.3")
         ops._count(4)
         if any(ctx.needs_input_grad):
-            ctx.saved = (bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w)
+            ctx.saved = (bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b)
             ctx.cfg = (mode, p, seed1, seed2, n, ldf, nimg, nnum, dq)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w = ctx.saved
+        bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b = ctx.saved
         mode, p, seed1, seed2, n, ldf, nimg, nnum, dq = ctx.cfg
         need = ctx.needs_input_grad
         dev = feat.device
@@ -350,7 +350,7 @@ class _QuadHeadFn(torch.autograd.Function):
         nc, nhid = c3w.shape
         # classifier.3
         dc3w = ops.grad_out(c3w)
-        dc3b = torch.empty(nc, device=dev)
+        dc3b = ops.grad_out(c3b)
         check(L().qt_small_linear_bwd_dw(ptr(dl), 0, nc, ptr(hbuf), 0, nhid, n, nc, nhid, ptr(dc3w), ptr(dc3b), 0, stream()), "classifier.3 dW")
         dh16 = torch.empty(n, nhid, device=dev, dtype=BF16)
         check(L().qt_small_linear_bwd_dx(ptr(dl), 0, nc, ptr(c3w.detach()), n, nc, nhid, ptr(hbuf), nhid, p, seed2, None, 0,
@@ -361,7 +361,7 @@ class _QuadHeadFn(torch.autograd.Function):
         dc0w = ops.grad_out(c0w)
         with ops.gemm_scope("linear_wgrad", 2.0 * n * nhid * ldf):
             check(L().qt_linear_wgrad(ptr(feat), ldf, ptr(dh16), nhid, ptr(dc0w), 0, n, nhid, ldf, ptr(ws), ws.numel(), stream()), "classifier.0 dW")
-        dc0b = torch.empty(nhid, device=dev)
+        dc0b = ops.grad_out(c0b)
         ops.colsum(dh16, dc0b)
         dfeat = torch.empty(n, ldf, device=dev, dtype=BF16)
         wd0 = ops.packed_dgrad(c0w)
@@ -374,13 +374,13 @@ class _QuadHeadFn(torch.autograd.Function):
             nh, k0 = m0w.shape
             dnum = dfeat.data_ptr() + 2 * nimg
             dm3w = ops.grad_out(m3w)
-            dm3b = torch.empty(nnum, device=dev)
+            dm3b = ops.grad_out(m3b)
             check(L().qt_small_linear_bwd_dw(dnum, 1, ldf, ptr(h1), 0, nh, n, nnum, nh, ptr(dm3w), ptr(dm3b), 0, stream()), "numerical_mlp.3 dW")
             dh1 = torch.empty(n, nh, device=dev)
             check(L().qt_small_linear_bwd_dx(dnum, 1, ldf, ptr(m3w.detach()), n, nnum, nh, ptr(h1), nh, p, seed1, ptr(dh1), nh, None, 0,
                                              stream()), "numerical_mlp.3 dX")
             dm0w = ops.grad_out(m0w)
-            dm0b = torch.empty(nh, device=dev)
+            dm0b = ops.grad_out(m0b)
             check(L().qt_small_linear_bwd_dw(ptr(dh1), 0, nh, ptr(numf), 0, k0, n, nh, k0, ptr(dm0w), ptr(dm0b), 0, stream()), "numerical_mlp.0 dW")
             ops._count(3)
         dbase = dl4 = dqw = dqb = None
@@ -394,7 +394,7 @@ class _QuadHeadFn(torch.autograd.Function):
                 dqw = _zeros_like_param(qw)
                 ops.conv_wgrad(dq, bb, dqt, dqw)
             if need[4]:
-                dqb = torch.empty(qw.shape[0], device=dev)
+                dqb = ops.grad_out(qb)
                 ops.colsum(dqt.view(-1, qw.shape[0]), dqb)
             if need[0]:
                 dbb = torch.empty_like(bb)
