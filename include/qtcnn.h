@@ -77,6 +77,8 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
  * quadrant_processor.0 QS/models.py:234-238 & 284-287, 3dcnn/models.py:107-139).
  * y = conv(x, wf) [+ bias] [ReLU]; with QT_EPI_STATS also writes per-tile column sum / sum-of-squares
  * partials [qt_conv_stat_rows][2][out_c] for the train-mode BatchNorm that follows. */
+/* kernel selection of a pass (0 = fprop, 1 = dgrad, 2 = wgrad): 0 generic gather GEMM, 1 persistent slab kernel. */
+int qt_conv_plan(const qt_conv_desc* d, int pass);
 int qt_conv_stat_rows(const qt_conv_desc* d);
 size_t qt_conv_fprop_workspace_bytes(const qt_conv_desc* d);
 int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y, const float* bias, float* stats,

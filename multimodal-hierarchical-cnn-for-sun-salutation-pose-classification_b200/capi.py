@@ -81,6 +81,7 @@ _SIGNATURES = {
     "qt_wpack_both": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_stem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "qt_conv_plan": (c_int, [ctypes.POINTER(ConvDesc), c_int]),
     "qt_conv_stat_rows": (c_int, [ctypes.POINTER(ConvDesc)]),
     "qt_conv_fprop_workspace_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
     "qt_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

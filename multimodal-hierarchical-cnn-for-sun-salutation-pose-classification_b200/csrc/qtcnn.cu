@@ -537,6 +537,13 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 }
 
 // ---- convolutions -----------------------------------------------------------------------------------
+/* which kernel a pass will use: 0 generic gather GEMM, 1 persistent slab kernel (conv3x3 / wgrad3x3) */
+int qt_conv_plan(const qt_conv_desc* d, int pass) {
+  if (check_desc(d)) return -1;
+  if (pass == 0) return plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS).ok ? 1 : 0;
+  if (pass == 1) return plan_conv3x3(d, d->out_c, d->in_c, 0).ok ? 1 : 0;
+  return plan_wgrad3x3(d).ok ? 1 : 0;
+}
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);

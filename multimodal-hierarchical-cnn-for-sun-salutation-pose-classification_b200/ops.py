@@ -189,6 +189,15 @@ def quadrant_desc(n, h, w, cin, cout, k, pad):
     return d
 
 
+def _fam(d, which, name):
+    """Profiling family: the kernel the C dispatch will pick for this pass + the pass name."""
+    if _prof is None:
+        return name
+    slab = L().qt_conv_plan(d, which) == 1
+    kern = ("wgrad3x3_kernel" if which == 2 else "conv3x3_kernel") if slab else ("igemm_wgrad_kernel" if which == 2 else "igemm_kmajor_kernel")
+    return f"{kern}:{name}"
+
+
 def conv_out_hw(d) -> Tuple[int, int, int]:
     return (capi.out_size(d.in_d, d.k_d, d.stride_d, d.pad_d), capi.out_size(d.in_h, d.k_h, d.stride_h, d.pad_h),
             capi.out_size(d.in_w, d.k_w, d.stride_w, d.pad_w))
@@ -202,14 +211,14 @@ def conv_fprop(d, x, wf, y, bias=None, relu=False, want_stats=False):
         rows = L().qt_conv_stat_rows(d)
         stats = torch.empty(rows, 2, d.out_c, device=x.device, dtype=torch.float32)
         flags |= capi.QT_EPI_STATS
-    with gemm_scope("conv_fprop", conv_flops(d) if _prof is not None else 0.0):
+    with gemm_scope(_fam(d, 0, "fprop"), conv_flops(d) if _prof is not None else 0.0):
         check(L().qt_conv_fprop(d, ptr(x), ptr(wf), ptr(y), ptr(bias), ptr(stats), flags, None, 0, stream()), "conv_fprop")
     _count()
     return stats
 
 
 def conv_dgrad(d, dy, wd, dx, accumulate=False):
-    with gemm_scope("conv_dgrad", conv_flops(d) if _prof is not None else 0.0):
+    with gemm_scope(_fam(d, 1, "dgrad"), conv_flops(d) if _prof is not None else 0.0):
         check(L().qt_conv_dgrad(d, ptr(dy), ptr(wd), ptr(dx), 1 if accumulate else 0, stream()), "conv_dgrad")
     _count(d.stride_h * d.stride_w * d.stride_d)
 
@@ -217,7 +226,7 @@ def conv_dgrad(d, dy, wd, dx, accumulate=False):
 def conv_wgrad(d, x, dy, dw, accumulate=False):
     nbytes = L().qt_conv_wgrad_workspace_bytes(d)
     ws = workspace(nbytes, x.device)
-    with gemm_scope("conv_wgrad", conv_flops(d) if _prof is not None else 0.0):
+    with gemm_scope(_fam(d, 2, "wgrad"), conv_flops(d) if _prof is not None else 0.0):
         check(L().qt_conv_wgrad(d, ptr(x), ptr(dy), ptr(dw), 1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
               "conv_wgrad")
     _count(2)

@@ -23,7 +23,11 @@ def test_conv_desc_matches_c_struct_layout():
     d = capi.conv_desc(2, (1, 14, 14), 256, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     assert ctypes.sizeof(capi.ConvDesc) == 16 * 4 + 16 * 8
     assert (d.x_stride[0], d.x_stride[2], d.x_stride[3]) == (14 * 14 * 256, 14 * 256, 256)
-    assert capi.lib().qt_conv_stat_rows(d) == (2 * 14 * 14 + 127) // 128
+    # 3x3/s1: persistent slab kernel -> one BatchNorm partial row per CTA (= number of 256-pixel tiles of the padded map)
+    assert capi.lib().qt_conv_stat_rows(d) == (2 * 16 * 16 + 255) // 256
+    # strided conv: generic gather kernel -> one row per 128-pixel tile
+    d2 = capi.conv_desc(2, (1, 14, 14), 256, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert capi.lib().qt_conv_stat_rows(d2) == (2 * 7 * 7 + 127) // 128
     bad = capi.conv_desc(2, (1, 14, 14), 250, 128, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     assert capi.lib().qt_conv_stat_rows(bad) == -1
     assert b"multiples of 8" in capi.lib().qt_last_error()
