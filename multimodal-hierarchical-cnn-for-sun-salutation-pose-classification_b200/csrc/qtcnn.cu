@@ -277,7 +277,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.bn = nout <= 64 ? 64 : 128;
-  pl.mt = (g_tune[5] == 1 && pl.bn == 128) ? 1 : 2;  // experimental: 128-pixel tiles, two CTAs per SM
+  pl.mt = (g_tune[5] >= 1 && pl.bn == 128) ? 1 : 2;  // experimental: 128-pixel tiles (1: two CTAs per SM, 2: one CTA per SM, deeper rings)
   const int bm = kBM * pl.mt;
   pl.R = ((bm + 2 * (d->in_w + 3)) + 15) / 16 * 16;
   pl.plane_stride = pl.R * 16 + 16;
@@ -296,9 +296,9 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
     pl.nslab = 3;
     if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
   } else if (pl.mt == 1) {
-    pl.nb = 3;
+    pl.nb = g_tune[5] == 2 ? 8 : 3;
     pl.resident = 0;
-    pl.nslab = 2;
+    pl.nslab = g_tune[5] == 2 ? 3 : 2;
   } else {
     pl.nb = 6;
     pl.resident = 0;
@@ -381,6 +381,10 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
       p.wtap[t] = static_cast<short>(t);
     }
   const int tiles = pl.num_m_tiles * pl.num_n_tiles;
+  if (pl.mt == 1 && g_tune[5] == 2) {
+    const int g1 = tiles < kNumSMs ? tiles : kNumSMs;
+    return launch_conv3x3<128, 1, 3, 8>(p, pl.smem, g1, st);
+  }
   if (pl.mt == 1) {
     const int g2 = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
     return launch_conv3x3<128, 1, 2, 3>(p, pl.smem, g2, st);
@@ -547,7 +551,7 @@ int qt_conv_plan(const qt_conv_desc* d, int pass) {
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
-  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; const int cap = pl.mt == 1 ? 2 * kNumSMs : kNumSMs; return tiles < cap ? tiles : cap; }
+  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; const int cap = (pl.mt == 1 && g_tune[5] != 2) ? 2 * kNumSMs : kNumSMs; return tiles < cap ? tiles : cap; }
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));
