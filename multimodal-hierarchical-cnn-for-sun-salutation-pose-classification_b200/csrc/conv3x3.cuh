@@ -1,6 +1,6 @@
 // Persistent 3x3 / stride-1 / pad-1 convolution on tcgen05 with input reuse across the nine taps.
 //
-// The M index runs over the pixels of a *virtual* zero-padded map [N][H+2][W+2]; in that space a filter tap is
+// The M index runs over the pixels of a *virtual* zero-padded map [N][H+1][W+2] (row 0 of every image is a zero row that doubles as the bottom padding of the image before it); in that space a filter tap is
 // a constant row shift (dh*(W+2) + dw), so one "slab" — the BM + 2(W+3) consecutive virtual pixels around an
 // M tile, 64 channels wide — staged ONCE in shared memory serves all nine taps: the A descriptor of tap t just
 // starts (dh+1)*(W+2) + (dw+1) rows further down. This cuts the L2->SM traffic of the activation operand ~6x
@@ -35,7 +35,7 @@ struct Conv3x3Params {
   int N, H, W, cin, nout, wtaps;
   int flags;
   int slabs;                // cin / 64
-  int V;                    // N * (H+2) * (W+2) virtual pixels
+  int V;                    // N * (H+1) * (W+2) virtual pixels
   int num_m_tiles, num_n_tiles;
   int R;                    // slab rows (multiple of 16)
   int plane_stride;         // bytes, R*16 + 16
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int Wp = p.W + 2, Hp = p.H + 1;  // one shared zero row between consecutive images
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 8) {

@@ -269,11 +269,11 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->pad_d != 0) return pl;
   if (d->groups != 1) return pl;
-  if (d->in_w < 10 && g_tune[4] == 0) return pl;  // 7x7 maps: 65 % border overhead, the gather kernel is faster (profiles/r01_conv_tuning.md)
+  if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
   if (cin % 64 || nout % 32) return pl;
   if (flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32)) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
-  const long long V = static_cast<long long>(d->n) * (d->in_h + 2) * (d->in_w + 2);
+  const long long V = static_cast<long long>(d->n) * (d->in_h + 1) * (d->in_w + 2);
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.bn = nout <= 64 ? 64 : 128;
@@ -415,11 +415,11 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->groups != 1) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
-  if (d->in_w < 10 && g_tune[4] == 0) return pl;
+  if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
   if (d->in_c == 64 && d->out_c == 64) pl.cfg = 0;
   else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
   else return pl;
-  const long long V = static_cast<long long>(d->n) * (d->in_h + 2) * (d->in_w + 2);
+  const long long V = static_cast<long long>(d->n) * (d->in_h + 1) * (d->in_w + 2);
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);

@@ -1,7 +1,7 @@
 // Weight gradient of 3x3 / stride-1 / pad-1 convolutions with input reuse across the taps (the backward twin of
 // conv3x3.cuh):   dW[tap][cin][cout] = sum over pixels  x[pixel + shift(tap)][cin] * dy[pixel][cout].
 //
-// The reduction (GEMM K) runs over the virtual zero-padded pixel space [N][H+2][W+2] in tiles of 128 pixels. Per
+// The reduction (GEMM K) runs over the virtual zero-padded pixel space [N][H+1][W+2] in tiles of 128 pixels. Per
 // tile the producers stage
 //   * the x "slab" (128 + 2(W+3) virtual pixels x 64*NSLAB channels) as no-swizzle planes [8-channel chunk][pixel][16 B]
 //     — used as the MN-major B operand (N = channels): chunk stride = SBO, 16 B between the pixels of a core
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int Wp = p.W + 2, Hp = p.H + 1;  // one shared zero row between consecutive images
   // CTA coordinates
   int type = blockIdx.x;
   const int tap_group = type % p.tap_groups; type /= p.tap_groups;
