@@ -70,6 +70,19 @@ int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_str
 /* both GEMM layouts from one read of the parameter (wd may be NULL). */
 int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream);
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream);
+/* Every weight of a model repacked in ONE launch (what the training loop needs after optimizer.step(),
+ * QS/Quadtree_train.py:72): fill w/wf/wd/cout/cin/taps of each item, call qt_wpack_item_plan (fills co_tile and
+ * ci_tiles, returns the item's block count or -1), set first_block to the running sum of the block counts, copy the
+ * table to device memory and pass it with the total block count and the largest taps value. */
+typedef struct qt_wpack_item {
+  const float* w;
+  void* wf;
+  void* wd; /* may be NULL */
+  int cout, cin, taps;
+  int co_tile, ci_tiles, first_block;
+} qt_wpack_item;
+int qt_wpack_item_plan(qt_wpack_item* item);
+int qt_wpack_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, qt_stream_t stream);
 int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
 
 /* ---- tensor-core implicit GEMM ------------------------------------------------------------------ */

@@ -39,6 +39,16 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class WpackItem(ctypes.Structure):
+    """Mirror of `qt_wpack_item` (one weight of a `qt_wpack_multi` launch)."""
+
+    _fields_ = [
+        ("w", c_void_p), ("wf", c_void_p), ("wd", c_void_p),
+        ("cout", c_int), ("cin", c_int), ("taps", c_int),
+        ("co_tile", c_int), ("ci_tiles", c_int), ("first_block", c_int),
+    ]
+
+
 def conv_desc(n, in_dhw, in_c, out_c, k_dhw, stride_dhw, pad_dhw, x_stride=None, y_stride=None,
               groups=1, x_group_off=(0, 0, 0, 0), y_group_off=(0, 0, 0, 0)) -> ConvDesc:
     """Dense channels-last descriptor unless explicit strides are given."""
@@ -79,6 +89,8 @@ _SIGNATURES = {
     "qt_wpack_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_dgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_both": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_wpack_item_plan": (c_int, [ctypes.POINTER(WpackItem)]),
+    "qt_wpack_multi": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_stem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "qt_conv_plan": (c_int, [ctypes.POINTER(ConvDesc), c_int]),

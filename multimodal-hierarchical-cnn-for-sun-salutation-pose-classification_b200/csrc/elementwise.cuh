@@ -130,16 +130,18 @@ __global__ void wpack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* _
       wd[(static_cast<long long>(ci) * T + t) * Cout + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
   }
 }
-// Both layouts from one read of w. grid (ceil(Cin/32), ceil(Cout/8)), block 256, dynamic smem 8*(32*(T|1)+1) floats.
-// (8 x 32 tiles keep even the 64x64 layers at 16+ blocks; the 16-byte runs of wd[ci][t][co0..co0+7] are one sector.)
-__global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T) {
-  extern __shared__ float tile[];  // [8 co][32 ci][T], odd pitches in both directions (bank-conflict free)
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 8;
+// Both layouts from one read of w: one block packs a tile of COT output channels x 32 input channels x T taps.
+// Dynamic smem COT*(32*(T|1)+1) floats, odd pitches in both directions (bank-conflict free). COT = 8 for filters
+// with taps (8 x 32 x 9 tiles keep even the 64x64 layers at 16+ blocks; the 16-byte runs of wd[ci][t][co0..co0+7]
+// are one sector), COT = 32 for T == 1 (1x1 convs and linear layers: a plain 32 x 32 transpose tile).
+__device__ __forceinline__ void wpack_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                           __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T, int COT, int bx, int by,
+                                           float* tile) {
+  const int ci0 = bx * 32, co0 = by * COT;
   const int TP = T | 1;
   const int CP = 32 * TP + 1;
   const int run = 32 * T;
-  for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
+  for (int i = threadIdx.x; i < COT * run; i += blockDim.x) {
     const int co = i / run, r = i - co * run;  // r = ci_local*T + t, contiguous in w for a fixed co
     const int cil = r / T, t = r - cil * T;
     float v = 0.f;
@@ -147,18 +149,44 @@ __global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __
     tile[co * CP + cil * TP + t] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * run; i += blockDim.x) {
+  for (int i = threadIdx.x; i < COT * run; i += blockDim.x) {
     {  // wf[co][t][ci]: ci fastest
-      const int cil = i & 31, t = (i >> 5) % T, co = i / (32 * T);
+      const int cil = i & 31, t = (i >> 5) % T, co = i / run;
       if (co0 + co < Cout && ci0 + cil < Cin)
         wf[(static_cast<long long>(co0 + co) * T + t) * Cin + ci0 + cil] = __float2bfloat16_rn(tile[co * CP + cil * TP + t]);
     }
-    if (wd) {  // wd[ci][t][co]: co fastest (8 per block)
-      const int col = i & 7, t = (i >> 3) % T, cil = i / (8 * T);
+    if (wd) {  // wd[ci][t][co]: co fastest (COT per block)
+      const int col = i % COT, t = (i / COT) % T, cil = i / (COT * T);
       if (co0 + col < Cout && ci0 + cil < Cin)
         wd[(static_cast<long long>(ci0 + cil) * T + t) * Cout + co0 + col] = __float2bfloat16_rn(tile[col * CP + cil * TP + t]);
     }
   }
+}
+__global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T, int COT) {
+  extern __shared__ float tile[];
+  wpack_tile(w, wf, wd, Cout, Cin, T, COT, blockIdx.x, blockIdx.y, tile);
+}
+// Every weight of a model in ONE launch (the per-step repack after an optimizer update): block b belongs to the
+// item with first_block <= b < next first_block (binary search over the device table).
+struct WpackItem {
+  const float* w;
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int cout, cin, taps;
+  int co_tile, ci_tiles, first_block;
+};
+__global__ void wpack_multi_kernel(const WpackItem* __restrict__ items, int nitems) {
+  extern __shared__ float tile[];
+  int lo = 0, hi = nitems - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= b) lo = mid; else hi = mid - 1;
+  }
+  const WpackItem it = items[lo];
+  const int local = b - it.first_block;
+  wpack_tile(it.w, it.wf, it.wd, it.cout, it.cin, it.taps, it.co_tile, local % it.ci_tiles, local / it.ci_tiles, tile);
 }
 // Stem 7x7x3 filter -> [Cout][8 row-taps][32 = (s, c4)] with zero padding (s == 7, c == 3, r == 7).
 __global__ void wpack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin,
@@ -672,73 +700,126 @@ __global__ void bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, 
     *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
-    float best[8];
-    int bi[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = -1; }
+    // all nine window loads are issued before any arithmetic (clamped coordinates + validity mask)
+    uint4 v[9];
+    unsigned okmask = 0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = ho * 2 - 1 + r;
-      if (h < 0 || h >= H) continue;
+      const int hc = min(max(h, 0), H - 1);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int w = wo * 2 - 1 + q;
-        if (w < 0 || w >= W) continue;
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + ((static_cast<long long>(n) * H + h) * W + w) * C + cg * 8), f);
+        const int wc = min(max(w, 0), W - 1);
+        if (h == hc && w == wc) okmask |= 1u << (r * 3 + q);
+        v[r * 3 + q] = ld_nc16(y + ((static_cast<long long>(n) * H + hc) * W + wc) * C + cg * 8);
+      }
+    }
+    // running max / arg-max on packed bf16 pairs: the activated value is a bf16 (same rounding as the unfused
+    // path), a > best is strict so the first maximum wins, and best starts at -inf so the first valid tap always
+    // takes (activations are >= 0)
+    unsigned best2[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u}, bi2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          // same rounding as the unfused path: the activated value is a bf16
-          const float a = bf16_round(fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f));
-          if (a > best[e] || bi[e] < 0) { best[e] = a; bi[e] = r * 3 + q; }
-        }
+    for (int t = 0; t < 9; ++t) {
+      if (!((okmask >> t) & 1u)) continue;
+      const unsigned raw[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(raw[j] << 16), hi = __uint_as_float(raw[j] & 0xffff0000u);
+        const unsigned a2 = pack_bf16x2(fmaxf(fmaf(lo, sc[2 * j], sh[2 * j]), 0.f),
+                                        fmaxf(fmaf(hi, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+        const unsigned m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a2),
+                                       *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
+        best2[j] = (a2 & m) | (best2[j] & ~m);
+        bi2[j] = ((t * 0x00010001u) & m) | (bi2[j] & ~m);
       }
     }
     const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
-    *reinterpret_cast<uint4*>(out + o) = pack8(best);
+    *reinterpret_cast<uint4*>(out + o) = make_uint4(best2[0], best2[1], best2[2], best2[3]);
     if (argmax) {
       uint2 pk;
-      pk.x = (bi[0] & 0xff) | ((bi[1] & 0xff) << 8) | ((bi[2] & 0xff) << 16) | ((bi[3] & 0xff) << 24);
-      pk.y = (bi[4] & 0xff) | ((bi[5] & 0xff) << 8) | ((bi[6] & 0xff) << 16) | ((bi[7] & 0xff) << 24);
+      pk.x = __byte_perm(bi2[0], bi2[1], 0x6420);
+      pk.y = __byte_perm(bi2[2], bi2[3], 0x6420);
       *reinterpret_cast<uint2*>(argmax + o) = pk;
     }
   }
 }
-// dz at conv-output pixel (n,h,w), 8 channels: gather the pooled gradient through the arg-max plane and apply the
-// ReLU mask recomputed from y.
-__device__ __forceinline__ void stem_dz8(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
-                                         const float (&yv)[8], const float (&sc)[8], const float (&sh)[8], int n, int h,
-                                         int w, int cg, int C, int Ho, int Wo, float (&dz)[8]) {
+// Backward works on 2x2 input blocks (rows 2a,2a+1 x cols 2b,2b+1; H and W even): exactly four pooling windows
+// (a,b) (a,b+1) (a+1,b) (a+1,b+1) cover such a block, and each of its pixels sits at a fixed window position
+// (arg-max code r*3+q) in each of them, so one thread issues all 12 loads (4 y, 4 dpool, 4 arg-max words) up
+// front and then only compares codes. dz = pooled gradient gathered through the arg-max plane, times the ReLU
+// mask recomputed from y.
+struct StemQuad {
+  uint4 y[4];   // pixels (2a,2b) (2a,2b+1) (2a+1,2b) (2a+1,2b+1)
+  uint4 d[4];   // windows (a,b) (a,b+1) (a+1,b) (a+1,b+1)
+  uint2 am[4];
+};
+__device__ __forceinline__ void stem_quad_load(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                                               const __nv_bfloat16* __restrict__ y, long long quad, int cg, int W, int C, int Ho,
+                                               int Wo, StemQuad& q) {
+  const int b = static_cast<int>(quad % Wo);
+  const long long na = quad / Wo;  // n*Ho + a
+  const int a = static_cast<int>(na % Ho);
+  const bool hb = a + 1 < Ho, wb = b + 1 < Wo;
+  const long long y0 = ((na * 2) * W + 2 * b) * C + cg * 8;  // rows of image n are contiguous: n*H + 2a == 2*(n*Ho + a)
+  const long long o0 = (na * Wo + b) * C + cg * 8;
+  q.y[0] = ld_nc16(y + y0);
+  q.y[1] = ld_nc16(y + y0 + C);
+  q.y[2] = ld_nc16(y + y0 + static_cast<long long>(W) * C);
+  q.y[3] = ld_nc16(y + y0 + static_cast<long long>(W) * C + C);
+  const long long o[4] = {o0, o0 + C, o0 + static_cast<long long>(Wo) * C, o0 + static_cast<long long>(Wo) * C + C};
+  const bool ok[4] = {true, wb, hb, hb && wb};
 #pragma unroll
-  for (int e = 0; e < 8; ++e) dz[e] = 0.f;
-  const int ho_lo = max(0, h / 2), ho_hi = min(Ho - 1, (h + 1) / 2);
-  const int wo_lo = max(0, w / 2), wo_hi = min(Wo - 1, (w + 1) / 2);
-  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-    const int r = h - (ho * 2 - 1);
-    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-      const int q = w - (wo * 2 - 1);
-      const int code = r * 3 + q;
-      const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
-      const uint2 pk = *reinterpret_cast<const uint2*>(argmax + o);
-      float d[8];
-      unpack8(*reinterpret_cast<const uint4*>(dpool + o), d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int a = (e < 4 ? (pk.x >> (8 * e)) : (pk.y >> (8 * (e - 4)))) & 0xff;
-        if (a == code) dz[e] += d[e];
-      }
-    }
+  for (int k = 0; k < 4; ++k) {
+    q.d[k] = ok[k] ? ld_nc16(dpool + o[k]) : make_uint4(0, 0, 0, 0);
+    q.am[k] = ok[k] ? __ldg(reinterpret_cast<const uint2*>(argmax + o[k])) : make_uint2(0xffffffffu, 0xffffffffu);
   }
+}
+// dz += d where the window's arg-max code equals `code`
+__device__ __forceinline__ void stem_take(const uint2 am, const float (&d)[8], unsigned code, float (&dz)[8]) {
+  const unsigned rep = code * 0x01010101u;
+  const unsigned m0 = __vcmpeq4(am.x, rep), m1 = __vcmpeq4(am.y, rep);
 #pragma unroll
-  for (int e = 0; e < 8; ++e)
-    if (!(fmaf(yv[e], sc[e], sh[e]) > 0.f)) dz[e] = 0.f;
+  for (int e = 0; e < 4; ++e) {
+    if (m0 & (1u << (8 * e))) dz[e] += d[e];
+    if (m1 & (1u << (8 * e))) dz[4 + e] += d[4 + e];
+  }
+}
+__device__ __forceinline__ void stem_quad_dz(const StemQuad& q, const float (&sc)[8], const float (&sh)[8], float (&yv)[4][8],
+                                             float (&dz)[4][8]) {
+  float d[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { unpack8(q.d[k], d[k]); unpack8(q.y[k], yv[k]); }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dz[k][e] = 0.f;
+  // pixel (2a,2b): window (a,b) position (1,1)
+  stem_take(q.am[0], d[0], 4, dz[0]);
+  // pixel (2a,2b+1): (a,b) at (1,2); (a,b+1) at (1,0)
+  stem_take(q.am[0], d[0], 5, dz[1]);
+  stem_take(q.am[1], d[1], 3, dz[1]);
+  // pixel (2a+1,2b): (a,b) at (2,1); (a+1,b) at (0,1)
+  stem_take(q.am[0], d[0], 7, dz[2]);
+  stem_take(q.am[2], d[2], 1, dz[2]);
+  // pixel (2a+1,2b+1): (a,b) at (2,2); (a,b+1) at (2,0); (a+1,b) at (0,2); (a+1,b+1) at (0,0)
+  stem_take(q.am[0], d[0], 8, dz[3]);
+  stem_take(q.am[1], d[1], 6, dz[3]);
+  stem_take(q.am[2], d[2], 2, dz[3]);
+  stem_take(q.am[3], d[3], 0, dz[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(fmaf(yv[k][e], sc[e], sh[e]) > 0.f)) dz[k][e] = 0.f;
 }
 // pass 1: partial[blocks][2][C] = { sum dz, sum dz*xhat }
-__global__ void stem_bn_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
-                                               const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                                               const float* __restrict__ shift, const float* __restrict__ mean,
-                                               const float* __restrict__ invstd, int N, int H, int W, int C, int Ho, int Wo,
-                                               float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 2)
+stem_bn_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                               const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                               const float* __restrict__ shift, const float* __restrict__ mean,
+                               const float* __restrict__ invstd, int N, int H, int W, int C, int Ho, int Wo,
+                               float* __restrict__ partial) {
   extern __shared__ float sm[];
   const int groups = C / 8;
   const int lanes = blockDim.x / groups;
@@ -748,16 +829,16 @@ __global__ void stem_bn_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__
     float sc[8], sh[8], mu[8], is[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = scale[cg * 8 + e]; sh[e] = shift[cg * 8 + e]; mu[e] = mean[cg * 8 + e]; is[e] = invstd[cg * 8 + e]; }
-    const long long M = static_cast<long long>(N) * H * W;
-    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += static_cast<long long>(gridDim.x) * lanes) {
-      const int w = r % W;
-      const int h = (r / W) % H;
-      const int n = r / (static_cast<long long>(W) * H);
-      float yv[8], dz[8];
-      unpack8(ld_nc16(y + r * C + cg * 8), yv);
-      stem_dz8(dpool, argmax, yv, sc, sh, n, h, w, cg, C, Ho, Wo, dz);
+    const long long Q = static_cast<long long>(N) * Ho * Wo;
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < Q; r += static_cast<long long>(gridDim.x) * lanes) {
+      StemQuad q;
+      stem_quad_load(dpool, argmax, y, r, cg, W, C, Ho, Wo, q);
+      float yv[4][8], dz[4][8];
+      stem_quad_dz(q, sc, sh, yv, dz);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s1[e] += dz[e]; s2[e] += dz[e] * (yv[e] - mu[e]) * is[e]; }
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s1[e] += dz[k][e]; s2[e] += dz[k][e] * (yv[k][e] - mu[e]) * is[e]; }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -773,18 +854,17 @@ __global__ void stem_bn_pool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__
   }
 }
 // pass 2: dy = A*dz + B*y + K (coef = [A | B | K])
-__global__ void stem_bn_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
-                                              const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                                              const float* __restrict__ shift, const float* __restrict__ coef,
-                                              __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int Ho, int Wo) {
+__global__ void __launch_bounds__(256, 2)
+stem_bn_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax,
+                              const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ coef,
+                              __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int Ho, int Wo) {
   const int groups = C / 8;
-  const long long total = static_cast<long long>(N) * H * W * groups;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = i % groups;
-    const int w = (i / groups) % W;
-    const int h = (i / (static_cast<long long>(groups) * W)) % H;
-    const int n = i / (static_cast<long long>(groups) * W * H);
+    const int cg = static_cast<int>(i % groups);
+    const long long quad = i / groups;
     float sc[8], sh[8], ca[8], cb[8], ck[8];
 #pragma unroll
     for (int e = 0; e < 8; e += 4) {
@@ -794,12 +874,20 @@ __global__ void stem_bn_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ 
       *reinterpret_cast<float4*>(cb + e) = __ldg(reinterpret_cast<const float4*>(coef + C + cg * 8 + e));
       *reinterpret_cast<float4*>(ck + e) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + cg * 8 + e));
     }
-    float yv[8], dz[8], o[8];
-    unpack8(ld_nc16(y + i * 8), yv);
-    stem_dz8(dpool, argmax, yv, sc, sh, n, h, w, cg, C, Ho, Wo, dz);
+    StemQuad q;
+    stem_quad_load(dpool, argmax, y, quad, cg, W, C, Ho, Wo, q);
+    float yv[4][8], dz[4][8];
+    stem_quad_dz(q, sc, sh, yv, dz);
+    const int b = static_cast<int>(quad % Wo);
+    const long long y0 = (((quad / Wo) * 2) * W + 2 * b) * C + cg * 8;
+    const long long off[4] = {y0, y0 + C, y0 + static_cast<long long>(W) * C, y0 + static_cast<long long>(W) * C + C};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = fmaf(ca[e], dz[e], fmaf(cb[e], yv[e], ck[e]));
-    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(ca[e], dz[k][e], fmaf(cb[e], yv[k][e], ck[e]));
+      *reinterpret_cast<uint4*>(dy + off[k]) = pack8(o);
+    }
   }
 }
 

@@ -613,46 +613,59 @@ __global__ void splitk_reduce_rows_kernel(const float* __restrict__ ws, int nspl
 }
 
 // Weight-gradient result: ws[z][f = tap*cin + c][n] -> grad[n][c][tap] (PyTorch parameter layout
-// [nout][cin][ntaps]). grid (ceil(cin/32), ceil(N/32), ntaps), block 256 = 8 warps x 32 lanes. Reads: a warp owns 4
-// channel rows, lanes run along n (128-byte rows of the workspace), four splits in flight per thread. The 32x32
-// tile is transposed through shared memory so the gradient is written with lanes along c (contiguous for
-// linear layers, stride ntaps for convs). accumulate != 0 adds.
+// [nout][cin][ntaps]). grid (ceil(cin/CT), ceil(N/32), ntaps), block 256 = 8 warps x 32 lanes. Reads: a warp owns
+// CT/8 channel rows, lanes run along n (128-byte rows of the workspace), eight splits in flight per thread. The
+// CT x 32 tile is transposed through shared memory so the gradient is written with lanes along c (contiguous for
+// linear layers, stride ntaps for convs). CT = 8 is for the small layers (64x64x9 has only 36 tiles of 32x32, and
+// up to 148 splits to sum: the narrow tile spreads that over 144 blocks). accumulate != 0 adds.
+template <int CT>
 __global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsplit, int F, int N, int Mpad, int Npad,
                                            int cin, int ntaps, float* __restrict__ grad, int accumulate) {
-  __shared__ float tile[32][33];  // [c][n]
-  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tap = blockIdx.z;
+  __shared__ float tile[CT][33];  // [c][n]
+  const int c0 = blockIdx.x * CT, n0 = blockIdx.y * 32, tap = blockIdx.z;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const long long zstride = static_cast<long long>(Mpad) * Npad;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int cl = wrp * 4 + j;
+  for (int j = 0; j < CT / 8; ++j) {
+    const int cl = wrp * (CT / 8) + j;
     const int c = c0 + cl, n = n0 + lane;
     float acc = 0.f;
     if (c < cin && n < N) {
       const float* src = ws + (static_cast<long long>(tap) * cin + c) * Npad + n;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int z = 0;
-      for (; z + 4 <= nsplit; z += 4) {
-        a0 += src[(z + 0) * zstride];
-        a1 += src[(z + 1) * zstride];
-        a2 += src[(z + 2) * zstride];
-        a3 += src[(z + 3) * zstride];
+      for (; z + 8 <= nsplit; z += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += src[(z + u) * zstride];
       }
-      for (; z < nsplit; ++z) a0 += src[z * zstride];
-      acc = (a0 + a1) + (a2 + a3);
+      for (; z < nsplit; ++z) a[0] += src[z * zstride];
+      acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     tile[cl][lane] = acc;
   }
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int nl = wrp * 4 + j;
-    const int n = n0 + nl, c = c0 + lane;
-    if (c < cin && n < N) {
-      float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
-      const float v = tile[lane][nl];
-      *dst = accumulate ? (*dst + v) : v;
+  constexpr int kCLanes = CT < 32 ? CT : 32;  // lanes along c in the write phase
+  const int wc = threadIdx.x % kCLanes;
+  for (int nl = threadIdx.x / kCLanes; nl < 32; nl += 256 / kCLanes) {
+    for (int cl = wc; cl < CT; cl += kCLanes) {
+      const int n = n0 + nl, c = c0 + cl;
+      if (c < cin && n < N) {
+        float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
+        const float v = tile[cl][nl];
+        *dst = accumulate ? (*dst + v) : v;
+      }
     }
+  }
+}
+inline void launch_splitk_reduce_wgrad(const float* ws, int nsplit, int F, int N, int Mpad, int Npad, int cin, int ntaps,
+                                       float* grad, int accumulate, cudaStream_t st) {
+  const long long blocks32 = static_cast<long long>((cin + 31) / 32) * ((N + 31) / 32) * ntaps;
+  if (blocks32 >= 296) {
+    dim3 g((cin + 31) / 32, (N + 31) / 32, ntaps);
+    splitk_reduce_wgrad_kernel<32><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
+  } else {
+    dim3 g((cin + 7) / 8, (N + 31) / 32, ntaps);
+    splitk_reduce_wgrad_kernel<8><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
   }
 }
 

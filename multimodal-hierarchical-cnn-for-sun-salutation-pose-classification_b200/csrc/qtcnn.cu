@@ -205,11 +205,7 @@ int run_wgrad(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, float* 
   else if (g_tune[0] == 2) rc = (BN == 64) ? launch_wgrad<64, 4, 1, 4>(p, grid, st) : launch_wgrad<128, 3, 1, 4>(p, grid, st);
   else rc = (BN == 64) ? launch_wgrad<64, 4, 1, 8>(p, grid, st) : launch_wgrad<128, 3, 1, 8>(p, grid, st);
   if (rc) return rc;
-  {
-    dim3 rgrid((cin_real + 31) / 32, (p.nout + 31) / 32, taps_real);
-    splitk_reduce_wgrad_kernel<<<rgrid, 256, 0, st>>>(p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad,
-                                                          cin_real, taps_real, dw, accumulate);
-  }
+  launch_splitk_reduce_wgrad(p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad, cin_real, taps_real, dw, accumulate, st);
   return cuda_status("splitk_reduce_wgrad_kernel");
 }
 
@@ -473,9 +469,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
     for (int kw = 0; kw < 3; ++kw, ++t) { p.off_h[t] = static_cast<signed char>(kh - 1); p.off_w[t] = static_cast<signed char>(kw - 1); }
   int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 5, 1, 3, 1>(p, pl, st) : launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st);
   if (rc) return rc;
-  dim3 rgrid((d->in_c + 31) / 32, (d->out_c + 31) / 32, 9);
-  splitk_reduce_wgrad_kernel<<<rgrid, 256, 0, st>>>(p.ws, pl.splits, 9 * d->in_c, d->out_c, 9 * d->in_c, d->out_c, d->in_c, 9, dw,
-                                                    accumulate);
+  launch_splitk_reduce_wgrad(p.ws, pl.splits, 9 * d->in_c, d->out_c, 9 * d->in_c, d->out_c, d->in_c, 9, dw, accumulate, st);
   return cuda_status("splitk_reduce_wgrad_kernel");
 }
 
@@ -522,13 +516,32 @@ int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_str
   wpack_dgrad_kernel<<<grid, block, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wd), cout, cin, taps);
   return cuda_status("wpack_dgrad");
 }
+namespace {
+inline int wpack_co_tile(int taps) { return taps == 1 ? 32 : 8; }
+inline size_t wpack_smem(int taps) { return static_cast<size_t>(wpack_co_tile(taps)) * (32 * (taps | 1) + 1) * sizeof(float); }
+}  // namespace
 int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream) {
-  if (taps > 32) return fail("wpack_both: too many taps");
-  dim3 grid((cin + 31) / 32, (cout + 7) / 8);
-  const size_t smem = static_cast<size_t>(8) * (32 * (taps | 1) + 1) * sizeof(float);
-  wpack_both_kernel<<<grid, 256, smem, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd), cout, cin,
-                                                  taps);
+  if (taps < 1 || taps > 32) return fail("wpack_both: taps must be 1..32");
+  const int cot = wpack_co_tile(taps);
+  dim3 grid((cin + 31) / 32, (cout + cot - 1) / cot);
+  wpack_both_kernel<<<grid, 256, wpack_smem(taps), S(stream)>>>(w, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd),
+                                                                 cout, cin, taps, cot);
   return cuda_status("wpack_both");
+}
+int qt_wpack_item_plan(qt_wpack_item* item) {
+  if (!item || item->cout < 1 || item->cin < 1 || item->taps < 1 || item->taps > 32) return fail("wpack_item_plan: bad item");
+  item->co_tile = wpack_co_tile(item->taps);
+  item->ci_tiles = (item->cin + 31) / 32;
+  return item->ci_tiles * ((item->cout + item->co_tile - 1) / item->co_tile);
+}
+int qt_wpack_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, qt_stream_t stream) {
+  static_assert(sizeof(qt_wpack_item) == sizeof(WpackItem), "qt_wpack_item layout");
+  if (nitems < 1 || total_blocks < 1) return 0;
+  if (max_taps < 1 || max_taps > 32) return fail("wpack_multi: taps must be 1..32");
+  size_t smem = wpack_smem(1);
+  for (int t = 2; t <= max_taps; ++t) smem = wpack_smem(t) > smem ? wpack_smem(t) : smem;
+  wpack_multi_kernel<<<total_blocks, 256, smem, S(stream)>>>(static_cast<const WpackItem*>(items_dev), nitems);
+  return cuda_status("wpack_multi");
 }
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream) {
   if (cin > 4 || r > 8 || s > 8) return fail("wpack_stem: filter does not fit the 8x(8x4) packing");
@@ -937,13 +950,15 @@ int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y,
                            qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_relu_maxpool_bwd: c must be a multiple of 8 and <= 2048");
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_relu_maxpool_bwd: workspace too small");
+  if ((h | w) & 1) return fail("bn_relu_maxpool_bwd: h and w must be even (2x2 block decomposition)");
   const int ho = out_dim(h, 3, 2, 1), wo = out_dim(w, 3, 2, 1);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
   float* coef = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;
   const int block = rowlane_block(c);
   const int lanes = block / (c / 8);
   const long long m = static_cast<long long>(n) * h * w;
-  long long want = (m + lanes - 1) / lanes;
+  const long long quads = static_cast<long long>(n) * ho * wo;
+  long long want = (quads + lanes - 1) / lanes;
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
   stem_bn_pool_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
@@ -952,7 +967,7 @@ int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y,
   bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
                                                                              invstd, gamma, dgamma, dbeta, 0, eval_mode, coef);
   if (int rc = cuda_status("bn_bwd_finalize")) return rc;
-  const long long total = m * (c / 8);
+  const long long total = quads * (c / 8);
   stem_bn_pool_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
       shift, coef, static_cast<__nv_bfloat16*>(dy), n, h, w, c, ho, wo);

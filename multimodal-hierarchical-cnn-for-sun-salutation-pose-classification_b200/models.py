@@ -85,14 +85,21 @@ class _StemFn(torch.autograd.Function):
         dout = ops.as_nhwc(dout)
         dgamma = ops.grad_out(bn_w)
         dbeta = ops.grad_out(bn_b)
-        # max-pool gather, then BatchNorm backward with the ReLU mask recomputed from y (the activated 112x112 map
-        # was never stored). The fully fused backward (qt_bn_relu_maxpool_bwd) measured slower than these two
-        # streaming passes (profiles/r01_conv_tuning.md).
-        da = torch.empty_like(y)
-        check(L().qt_maxpool2d_bwd(ptr(dout), ptr(am), ptr(da), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_bwd")
-        ops._count()
         dy = torch.empty_like(y)
-        ops.bn_backward(da, None, y, st, bn_w.detach(), dgamma, dbeta, dy, None, eval_mode=not ctx.training, mask_from_y=True)
+        if ho % 2 == 0 and wo % 2 == 0:
+            # fused: max-pool gather through the arg-max plane + ReLU mask recomputed from y + BatchNorm backward in two
+            # passes over 2x2 pixel blocks; neither the activated 112x112 map nor its gradient is ever materialised
+            wsb = L().qt_bn_workspace_bytes(cout)
+            ws = ops.workspace(wsb, dev)
+            check(L().qt_bn_relu_maxpool_bwd(ptr(dout), ptr(am), ptr(y), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
+                                             ptr(bn_w.detach()), n, ho, wo, cout, ptr(dgamma), ptr(dbeta), 0 if ctx.training else 1,
+                                             ptr(dy), ptr(ws), wsb, stream()), "bn_relu_maxpool_bwd")
+            ops._count(3)
+        else:
+            da = torch.empty_like(y)
+            check(L().qt_maxpool2d_bwd(ptr(dout), ptr(am), ptr(da), n, ho, wo, cout, 3, 2, 1, stream()), "maxpool_bwd")
+            ops._count()
+            ops.bn_backward(da, None, y, st, bn_w.detach(), dgamma, dbeta, dy, None, eval_mode=not ctx.training, mask_from_y=True)
         dw = None
         if ctx.needs_input_grad[1]:
             dw = _zeros_like_param(conv_w)

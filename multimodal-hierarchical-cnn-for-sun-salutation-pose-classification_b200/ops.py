@@ -5,6 +5,7 @@ are fp32. Nothing here computes on the host or falls back to ATen kernels for th
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 from typing import Optional, Tuple
 
@@ -67,12 +68,13 @@ except Exception as _e:  # pragma: no cover
 
 
 class _Packed:
-    __slots__ = ("version", "ptr", "wf", "wd", "w8")
+    __slots__ = ("version", "ptr", "wf", "wd", "w8", "registered", "__weakref__")
 
     def __init__(self):
         self.version = None
         self.ptr = 0
         self.wf = self.wd = self.w8 = None
+        self.registered = False
 
 
 class _IdMap:
@@ -100,15 +102,98 @@ class _IdMap:
 _packed = _IdMap()
 
 
+class _PackRegistry:
+    """All GEMM weights of one device that have been packed in both layouts. After an optimizer step the first
+    conv that asks for a weight repacks EVERY registered weight with one `qt_wpack_multi` launch (in place: the
+    bf16 buffers and therefore the device table stay valid across steps)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []          # (weakref(param), entry)
+        self.table = None        # uint8 device tensor holding qt_wpack_item[]
+        self.table_ptrs = None
+        self.blocks = 0
+        self.max_taps = 1
+        self.generation = -1     # generation the registered weights were last packed at
+
+    def add(self, w, e):
+        self.items.append((weakref.ref(w), e))
+        e.registered = True
+        self.table = None
+
+    def _rebuild(self):
+        live = []
+        for ref, e in self.items:
+            w = ref()
+            if w is not None and e.wf is not None and _packed.get(w) is e:
+                live.append((ref, e))
+            else:
+                e.registered = False
+        self.items = live
+        arr = (capi.WpackItem * max(len(live), 1))()
+        first, max_taps, ptrs = 0, 1, []
+        for i, (ref, e) in enumerate(live):
+            w = ref()
+            cout, cin, taps = _w_dims(w)
+            it = arr[i]
+            it.w, it.wf, it.wd = w.data_ptr(), e.wf.data_ptr(), (e.wd.data_ptr() if e.wd is not None else None)
+            it.cout, it.cin, it.taps = cout, cin, taps
+            nb = L().qt_wpack_item_plan(ctypes.byref(it))
+            if nb < 0:
+                check(-1, "wpack_item_plan")
+            it.first_block = first
+            first += nb
+            max_taps = max(max_taps, taps)
+            ptrs.append((w.data_ptr(), e.wf.data_ptr(), e.wd.data_ptr() if e.wd is not None else 0))
+        raw = bytes(arr)[: ctypes.sizeof(capi.WpackItem) * len(live)] if live else b""
+        self.table = torch.frombuffer(bytearray(raw or b"\0"), dtype=torch.uint8).to(self.device)
+        self.table_ptrs, self.blocks, self.max_taps = ptrs, first, max_taps
+
+    def repack_all(self):
+        if self.table is not None:
+            cur = []
+            for ref, e in self.items:
+                w = ref()
+                if w is None or e.wf is None:
+                    cur = None
+                    break
+                cur.append((w.data_ptr(), e.wf.data_ptr(), e.wd.data_ptr() if e.wd is not None else 0))
+            if cur != self.table_ptrs:
+                self.table = None
+        if self.table is None:
+            self._rebuild()
+        if self.items:
+            check(L().qt_wpack_multi(ptr(self.table), len(self.items), self.blocks, self.max_taps, stream()), "wpack_multi")
+            _count()
+        self.generation = _generation
+        for ref, e in self.items:
+            w = ref()
+            e.version, e.ptr = (w._version, _generation), w.data_ptr()
+
+
+_registries = {}
+
+
+def _registry(device) -> _PackRegistry:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    r = _registries.get(key)
+    if r is None:
+        r = _registries[key] = _PackRegistry(device)
+    return r
+
+
 def _entry(w: torch.Tensor) -> _Packed:
     e = _packed.get(w)
     if e is None:
         e = _Packed()
         _packed.set(w, e)
+    if e.registered and e.version is not None and e.version[1] != _generation and e.ptr == w.data_ptr():
+        _registry(w.device).repack_all()  # optimizer stepped: every registered weight in one launch
     ver = (w._version, _generation)
     if e.version != ver or e.ptr != w.data_ptr():
         e.version, e.ptr = ver, w.data_ptr()
         e.wf = e.wd = e.w8 = None
+        e.registered = False
     return e
 
 
@@ -132,6 +217,8 @@ def packed_fprop(w: torch.Tensor) -> torch.Tensor:
             e.wd = torch.empty(cin, taps, cout, device=w.device, dtype=BF16)
         check(L().qt_wpack_both(ptr(wc), ptr(e.wf), ptr(e.wd), cout, cin, taps, stream()), "wpack_both")
         _count()
+        if e.wd is not None and w.is_contiguous() and w.dtype == torch.float32 and w.is_cuda and taps <= 32:
+            _registry(w.device).add(w, e)
     return e.wf
 
 
