@@ -271,85 +271,96 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       const uint32_t ab = tile_it & 1;
       mbar_wait(&acc_full[ab], (tile_it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
+      bool row_ok[MT];
+      long long orow[MT];
+#pragma unroll
       for (int u = 0; u < MT; ++u) {
         const int v = (m_tile * MT + u) * kBM + warp * 32 + lane;
-        bool row_ok = v < p.V;
-        long long orow = 0;
-        if (row_ok) {
+        row_ok[u] = v < p.V;
+        orow[u] = 0;
+        if (row_ok[u]) {
           const int wp = v % Wp;
           const int rest = v / Wp;
           const int hp = rest % Hp;
           const int n = rest / Hp;
-          row_ok = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
-          orow = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.nout;
+          row_ok[u] = (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
+          orow[u] = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.nout;
         }
+      }
+      // chunk-outer / sub-tile-inner: the per-column sums of the MT sub-tiles are added in registers first, so the
+      // 32x32 transpose-reduce (the expensive part: 62 shuffles per thread) runs once per chunk, not once per sub-tile
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int ncol = n0 + c0;
+        if (ncol >= p.nout) break;
+        float s1v[32], s2v[32];
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ab * (MT * BN) + u * BN + c0, r);
           tmem_ld_wait();
-          const int ncol = n0 + c0;
-          if (ncol >= p.nout) break;
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]);
-          if ((flags & EPI_ADDEND) && row_ok) {
-            const __nv_bfloat16* ad = p.addend + orow + ncol;
+          if ((flags & EPI_ADDEND) && row_ok[u]) {
+            const __nv_bfloat16* ad = p.addend + orow[u] + ncol;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              float f[8];
               const uint4 q = *reinterpret_cast<const uint4*>(ad + j);
               const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[e]);
-                f[2 * e] = __low2float(h2);
-                f[2 * e + 1] = __high2float(h2);
+                vv[j + 2 * e] += __uint_as_float(w4[e] << 16);
+                vv[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
               }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) vv[j + e] += f[e];
             }
           }
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vv[j] = bf16_round(vv[j]);
-          if (row_ok) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + ncol;
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(vv[2 * j], vv[2 * j + 1]);
+          if (row_ok[u]) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[u] + ncol;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(vv[j], vv[j + 1]);
-              q.y = pack_bf16x2(vv[j + 2], vv[j + 3]);
-              q.z = pack_bf16x2(vv[j + 4], vv[j + 5]);
-              q.w = pack_bf16x2(vv[j + 6], vv[j + 7]);
-              *reinterpret_cast<uint4*>(dst + j) = q;
-            }
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
           if (flags & EPI_STATS) {
-            float sq[32];
+            // statistics of the stored (bf16-rounded) values; rows outside the image contribute zero
+            const uint32_t keep = row_ok[u] ? 0xffffffffu : 0u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              vv[j] = row_ok ? vv[j] : 0.f;
-              sq[j] = vv[j] * vv[j];
+            for (int j = 0; j < 16; ++j) {
+              const float lo = __uint_as_float((pk[j] << 16) & keep), hi = __uint_as_float(pk[j] & 0xffff0000u & keep);
+              if (u == 0) {
+                s1v[2 * j] = lo; s1v[2 * j + 1] = hi;
+                s2v[2 * j] = lo * lo; s2v[2 * j + 1] = hi * hi;
+              } else {
+                s1v[2 * j] += lo; s1v[2 * j + 1] += hi;
+                s2v[2 * j] = fmaf(lo, lo, s2v[2 * j]); s2v[2 * j + 1] = fmaf(hi, hi, s2v[2 * j + 1]);
+              }
             }
-            const float s1 = warp_transpose_reduce(vv);
-            const float s2 = warp_transpose_reduce(sq);
-            scratch[(0 * 4 + warp) * BN + c0 + lane] = s1;
-            scratch[(1 * 4 + warp) * BN + c0 + lane] = s2;
           }
         }
         if (flags & EPI_STATS) {
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          for (int i = threadIdx.x; i < 2 * BN; i += kProducerThreads) {
-            const int which = i / BN, col = i - which * BN;
+          const float s1 = warp_transpose_reduce(s1v);
+          const float s2 = warp_transpose_reduce(s2v);
+          scratch[(0 * 4 + warp) * BN + c0 + lane] = s1;
+          scratch[(1 * 4 + warp) * BN + c0 + lane] = s2;
+        }
+      }
+      // every tcgen05.ld of this accumulator has completed: hand it back before the cross-warp combine
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+      if (flags & EPI_STATS) {
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        for (int i = threadIdx.x; i < 2 * BN; i += kProducerThreads) {
+          const int which = i / BN, col = i - which * BN;
+          if (n0 + col < p.nout) {
             const float* sc = scratch + which * 4 * BN + col;
             running[(n_tile * 2 + which) * BN + col] += (sc[0] + sc[BN]) + (sc[2 * BN] + sc[3 * BN]);
           }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
         }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
     }
     if (flags & EPI_STATS) {
       // one deterministic partial row per CTA: [2][nout]
