@@ -12,7 +12,7 @@ import re
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqtcnn.so")
+LIB_PATH = os.environ.get("QTCNN_LIB") or os.path.join(_HERE, "libqtcnn.so")  # QTCNN_LIB: A/B builds of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "qtcnn.h")
 
 QT_EPI_BIAS = 1

@@ -91,6 +91,18 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     const int rbase = t >> 3;
     const uint32_t dsw = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
+    // loop-invariant kernel parameters in registers (the cp.async asm carries a memory clobber); real-pixel byte
+    // offsets are kept incrementally: +16 virtual pixels = adv, a w-carry skips the 2 pad columns, an h-carry the
+    // shared zero row
+    const int pW = p.W, pN = p.N, pR = p.R;
+    const long long dy_pix = static_cast<long long>(p.cout) * 2, x_pix = static_cast<long long>(p.cin) * 2;
+    const long long dy_adv = (static_cast<long long>(adv_h) * pW + adv_w) * dy_pix, x_adv = (static_cast<long long>(adv_h) * pW + adv_w) * x_pix;
+    const long long dy_row = pW * dy_pix, x_row = pW * x_pix;
+    const char* dy_c = reinterpret_cast<const char*>(p.dy + cout0 + chunk * 8);
+    const char* x_c = reinterpret_cast<const char*>(p.x + cin0 + chunk * 8);
+    const void* dummy_dy = p.dy;
+    const void* dummy_x = p.x;
+    const uint32_t plane_stride = p.plane_stride;
     for (int it = 0; it < nit; ++it) {
       const int s = it % STAGES;
       if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
@@ -105,42 +117,43 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           hp = rest % Hp;
           n = rest / Hp;
         }
-        const uint32_t dst0 = smem_u32(st) + dsw;
+        const char* src = dy_c + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * dy_pix;
+        const uint32_t dst0 = smem_u32(st) + dsw + rbase * 128;
 #pragma unroll
         for (int i = 0; i < kW3KP / 16; ++i) {
-          const bool ok = (n < p.N) && (wp >= 1) && (wp <= p.W) && (hp >= 1) && (hp <= p.H);
-          const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
-          const __nv_bfloat16* src = ok ? (p.dy + static_cast<long long>(pix) * p.cout + cout0 + chunk * 8) : p.dy;
+          const bool ok = (n < pN) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int b = 0; b < CB; ++b)
-            cp_async16(dst0 + b * (kW3KP * 128) + (rbase + 16 * i) * 128, ok ? src + b * 64 : p.dy, ok ? 16u : 0u);
+            cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
+          src += dy_adv;
           wp += adv_w; hp += adv_h;
-          if (wp >= Wp) { wp -= Wp; ++hp; }
-          if (hp >= Hp) { hp -= Hp; ++n; }
+          if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * dy_pix; }
+          if (hp >= Hp) { hp -= Hp; ++n; src -= dy_row; }
         }
       }
       {  // ---- x slab: row j <-> virtual pixel q0 - (W+3) + j
         int n, hp, wp;
         {
-          const int vv = q0 - (p.W + 3) + rbase + Wp * Hp;
+          const int vv = q0 - (pW + 3) + rbase + Wp * Hp;
           wp = vv % Wp;
           const int rest = vv / Wp;
           hp = rest % Hp;
           n = rest / Hp - 1;
         }
-        const uint32_t dst0 = smem_u32(st + dy_bytes) + chunk * p.plane_stride;
-        const __nv_bfloat16* src_c = p.x + cin0 + chunk * 8;
-        for (int j = rbase; j < p.R; j += 16) {
-          const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(p.N)) && (wp >= 1) && (wp <= p.W) && (hp >= 1) &&
-                          (hp <= p.H);
-          const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
-          const __nv_bfloat16* src = ok ? (src_c + static_cast<long long>(pix) * p.cin) : p.x;
+        const char* src = x_c + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
+        uint32_t dst = smem_u32(st + dy_bytes) + chunk * plane_stride + rbase * 16;
+#pragma unroll 2
+        for (int j = rbase; j < pR; j += 16) {
+          const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(pN)) &&
+                          (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int sl = 0; sl < NSLAB; ++sl)
-            cp_async16(dst0 + sl * 8 * p.plane_stride + j * 16, ok ? src + sl * 64 : p.x, ok ? 16u : 0u);
+            cp_async16(dst + sl * 8 * plane_stride, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
+          dst += 256;
+          src += x_adv;
           wp += adv_w; hp += adv_h;
-          if (wp >= Wp) { wp -= Wp; ++hp; }
-          if (hp >= Hp) { hp -= Hp; ++n; }
+          if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * x_pix; }
+          if (hp >= Hp) { hp -= Hp; ++n; src -= x_row; }
         }
       }
       // completion is tracked by the mbarrier itself (no wait_group): the producers run ahead by up to STAGES
