@@ -41,23 +41,25 @@ struct Conv3x3Params {
   int plane_stride;         // bytes, R*16 + 16
   int b_resident;           // 1: all 9*slabs weight tiles stay in the B ring
   int b_tma;                // 1: weight tiles arrive by TMA (cp.async.bulk.tensor.2d through `wmap`), else cp.async
+  int debug_skip;           // timing experiments only (qt_set_tuning knob 7): bit 0 skips the A copies, bit 1 the epilogue body
   signed char off_h[9], off_w[9];
   short wtap[9];
 };
 
-template <int BN, int MT, int NSLAB, int NB>
+template <int BN, int MT, int NSLAB, int NB, bool STAGED>
 struct C3Smem {
   static constexpr int kBTile = BN * 128;
   static constexpr int kBBytes = NB * kBTile;
   static constexpr int kScratch = 2 * 4 * BN * 4 + 4 * 2 * BN * 4;  // cross-warp combine + running sums (<= 4 n-tiles)
+  static constexpr int kStage = STAGED ? 4 * 32 * 64 : 0;  // per epilogue warp: 32 rows x 64 B output staging (coalesced write-out)
   static constexpr int kBarBytes = 512;
-  // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][barriers][slabs...]
+  // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][staging][barriers][slabs...]
 };
 
-template <int BN, int MT, int NSLAB, int NB>
+template <int BN, int MT, int NSLAB, int NB, bool STAGED>
 __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(const __grid_constant__ Conv3x3Params p,
                                                                                 const __grid_constant__ CUtensorMap wmap) {
-  using L = C3Smem<BN, MT, NSLAB, NB>;
+  using L = C3Smem<BN, MT, NSLAB, NB, STAGED>;
   constexpr uint32_t TCOLS = 2 * MT * BN;  // double-buffered accumulators
   static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
   static_assert(MT == 1 || MT == 2, "one MMA-issuer warp per sub-tile: warps 8 and 9 (warp 9 idles when MT == 1)");
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
   uint8_t* b_ring = smem;
   float* scratch = reinterpret_cast<float*>(smem + L::kBBytes);
   float* running = scratch + 2 * 4 * BN;  // [n_tile][2][BN] per-CTA BatchNorm partial sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBBytes + L::kScratch);
+  uint8_t* stage = smem + L::kBBytes + L::kScratch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBBytes + L::kScratch + L::kStage);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NSLAB;
   uint64_t* b_full = a_empty + NSLAB;
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
   uint64_t* acc_full = b_empty + NB;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* slab_base = smem + L::kBBytes + L::kScratch + L::kBarBytes;
+  uint8_t* slab_base = smem + L::kBBytes + L::kScratch + L::kStage + L::kBarBytes;
   const int slab_bytes = 8 * p.plane_stride;
 
   const int warp = threadIdx.x >> 5;
@@ -109,6 +112,13 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     // ahead by the full depth of the rings and never block in wait_group; the issuers fence after their waits.
     bool first_tile = true;
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
+    // kernel parameters used in the gather loop live in registers (the cp.async asm has a memory clobber, which would
+    // otherwise make the compiler re-read them from the constant bank every iteration)
+    const int pW = p.W, pH = p.H, pN = p.N, pR = p.R;
+    const long long pix_bytes = static_cast<long long>(p.cin) * 2;
+    const long long row_bytes = pW * pix_bytes;
+    const long long adv_off = (static_cast<long long>(adv_h) * pW + adv_w) * pix_bytes;
+    const void* dummy = p.a;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
@@ -123,21 +133,39 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           // then advance 16 virtual pixels per iteration with carries instead of dividing per row
           int n, hp, wp;
           {
-            const int vv = q0 - (p.W + 3) + rbase + Wp * Hp;
+            const int vv = q0 - (pW + 3) + rbase + Wp * Hp;
             wp = vv % Wp;
             const int rest = vv / Wp;
             hp = rest % Hp;
             n = rest / Hp - 1;
           }
-          for (int j = rbase; j < p.R; j += 16) {
-            const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(p.N)) && (wp >= 1) && (wp <= p.W) && (hp >= 1) &&
-                            (hp <= p.H);
-            const int pix = (n * p.H + (hp - 1)) * p.W + (wp - 1);
-            const __nv_bfloat16* src = ok ? (src_c + static_cast<long long>(pix) * p.cin) : p.a;
-            cp_async16(dst0 + j * 16, src, ok ? 16u : 0u);
-            wp += adv_w; hp += adv_h;
-            if (wp >= Wp) { wp -= Wp; ++hp; }
-            if (hp >= Hp) { hp -= Hp; ++n; }
+          // byte address of real pixel (n, hp-1, wp-1), kept incrementally (only dereferenced when the row is real):
+          // +16 virtual pixels = adv_off; a w-carry skips the 2 pad columns, an h-carry the shared zero row.
+          // Addresses are produced in batches of kBatch into distinct registers and only then handed to cp.async:
+          // the LSU releases a cp.async's address registers late, so reusing one register pair per copy would
+          // serialise the copies on that release.
+          const char* srcb = reinterpret_cast<const char*>(src_c) +
+                             (static_cast<long long>(n * pH + (hp - 1)) * pW + (wp - 1)) * pix_bytes;
+          uint32_t dst = dst0 + rbase * 16;
+          constexpr int kBatch = 4;
+          for (int j = rbase; j < pR; j += 16 * kBatch) {
+            const void* sp[kBatch];
+            uint32_t sz[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+              const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(pN)) &&
+                              (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
+              sp[b] = ok ? static_cast<const void*>(srcb) : dummy;
+              sz[b] = ok ? 16u : 0u;
+              srcb += adv_off;
+              wp += adv_w; hp += adv_h;
+              if (wp >= Wp) { wp -= Wp; ++hp; srcb -= 2 * pix_bytes; }
+              if (hp >= Hp) { hp -= Hp; ++n; srcb -= row_bytes; }
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b)
+              if (j + 16 * b < pR && !(p.debug_skip & 1)) cp_async16(dst + b * 256, sp[b], sz[b]);
+            dst += 256 * kBatch;
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);
           ++a_cnt;
@@ -210,6 +238,9 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t a_cnt = 0, b_cnt = 0, tile_it = 0;
       bool first_tile = true;
+      uint32_t tapoff[9];  // slab row (16-byte units) of each filter tap relative to the tile's first pixel
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) tapoff[tp] = static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         const uint32_t ab = tile_it & 1;
         if (tile_it >= 2) mbar_wait(&acc_empty[ab], ((tile_it >> 1) - 1) & 1);
@@ -219,33 +250,54 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           const int sa = a_cnt % NSLAB;
           mbar_wait(&a_full[sa], (a_cnt / NSLAB) & 1);
           fence_proxy_async_smem();
+          tc_fence_after();
           const uint32_t slab_lo = ((smem_u32(slab_base + sa * slab_bytes) >> 4) & 0x3FFFu) | a_lbo;
-#pragma unroll 1
-          for (int tp = 0; tp < 9; ++tp) {
-            int sb;
-            if (p.b_resident) {
-              sb = c * 9 + tp;
-              if (first_tile) mbar_wait(&b_full[sb], 0);
-            } else {
-              sb = b_cnt % NB;
-              mbar_wait(&b_full[sb], (b_cnt / NB) & 1);
-            }
-            fence_proxy_async_smem();
-            tc_fence_after();
-            const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
-            const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
+          if (p.b_resident && !first_tile) {
+            // resident filter, already waited for and fenced on the first tile: nine taps back to back
+            const uint32_t b0 = (((smem_u32(b_ring) >> 4) + c * 9 * (L::kBTile >> 4)) & 0x3FFFu) | b_lbo;
             if (lane == 0) {
               const int u = warp - 8;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
-                const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
-                umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
+              for (int tp = 0; tp < 9; ++tp) {
+                const uint32_t a_lo = slab_lo + tapoff[tp] + u * kBM;
+                const uint32_t b_lo = b0 + tp * (L::kBTile >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * kstep);
+                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
+                  umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
+                }
               }
-              if (!p.b_resident) umma_commit(&b_empty[sb]);
             }
             __syncwarp();
-            if (!p.b_resident) ++b_cnt;
+          } else {
+#pragma unroll 1
+            for (int tp = 0; tp < 9; ++tp) {
+              int sb;
+              if (p.b_resident) {
+                sb = c * 9 + tp;
+                mbar_wait(&b_full[sb], 0);
+              } else {
+                sb = b_cnt % NB;
+                mbar_wait(&b_full[sb], (b_cnt / NB) & 1);
+              }
+              if (!p.b_tma) fence_proxy_async_smem();  // cp.async-written filter tile (TMA writes are async-proxy already)
+              tc_fence_after();
+              const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
+              const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
+              if (lane == 0) {
+                const int u = warp - 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
+                  const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
+                  umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
+                }
+                if (!p.b_resident) umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              if (!p.b_resident) ++b_cnt;
+            }
           }
           if (lane == 0) umma_commit(&a_empty[sa]);
           __syncwarp();
@@ -287,12 +339,29 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           orow[u] = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * p.nout;
         }
       }
+      // Coalesced write-out: every 32x32 chunk goes through a per-warp staging tile so that one store instruction
+      // covers 8 rows x 64 contiguous bytes (consecutive virtual pixels are consecutive real pixels inside an image
+      // row) instead of 32 rows x 16 bytes - the scattered form keeps the LSU busy for 32 tag cycles per instruction
+      // and starves the producers' cp.async (measured: epilogue + gather together cost 2x either alone).
+      // srow[u][i]: output offset of row 8*i + lane/4 (the rows this lane writes out), -1 outside the image.
+      long long srow[MT][4];
+      if (STAGED) {
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+          const long long mine = row_ok[u] ? orow[u] : -1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) srow[u][i] = __shfl_sync(0xffffffffu, mine, 8 * i + (lane >> 2));
+        }
+      }
+      const uint32_t stage_w = smem_u32(stage) + warp * 2048;
+      const uint32_t st_own = stage_w + lane * 64, st_sw = (lane >> 1) & 3;
+      const uint32_t ld_row = stage_w + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
       // chunk-outer / sub-tile-inner: the per-column sums of the MT sub-tiles are added in registers first, so the
       // 32x32 transpose-reduce (the expensive part: 62 shuffles per thread) runs once per chunk, not once per sub-tile
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int ncol = n0 + c0;
-        if (ncol >= p.nout) break;
+        if (ncol >= p.nout || (p.debug_skip & 2)) break;
         float s1v[32], s2v[32];
 #pragma unroll
         for (int u = 0; u < MT; ++u) {
@@ -302,7 +371,27 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           float vv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]);
-          if ((flags & EPI_ADDEND) && row_ok[u]) {
+          if ((flags & EPI_ADDEND) && STAGED) {
+            // coalesced read of the addend chunk (8 rows x 64 B per instruction) through the staging tile
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q = make_uint4(0, 0, 0, 0);
+              if (srow[u][i] >= 0) q = *reinterpret_cast<const uint4*>(p.addend + srow[u][i] + ncol + (lane & 3) * 8);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(ld_row + i * 512), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w4[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(w4[0]), "=r"(w4[1]), "=r"(w4[2]), "=r"(w4[3]) : "r"(st_own + ((j ^ st_sw) << 4)) : "memory");
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                vv[8 * j + 2 * e] += __uint_as_float(w4[e] << 16);
+                vv[8 * j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              }
+            }
+            __syncwarp();
+          } else if ((flags & EPI_ADDEND) && row_ok[u]) {
             const __nv_bfloat16* ad = p.addend + orow[u] + ncol;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -318,7 +407,22 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(vv[2 * j], vv[2 * j + 1]);
-          if (row_ok[u]) {
+          if (STAGED) {
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(st_own + ((j ^ st_sw) << 4)), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+            __syncwarp();
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ld_row + i * 512) : "memory");
+              if (srow[u][i] >= 0)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + srow[u][i] + ncol + (lane & 3) * 8) = q;
+            }
+            __syncwarp();
+          } else if (row_ok[u]) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[u] + ncol;
 #pragma unroll
             for (int j = 0; j < 4; ++j)

@@ -252,7 +252,7 @@ bool dense_nhwc(const long long* st, int d, int h, int w, int c) {
 
 struct C3Plan {
   bool ok;
-  int bn, mt, nslab, nb, R, plane_stride, resident;
+  int bn, mt, nslab, nb, R, plane_stride, resident, staged;
   int num_m_tiles, num_n_tiles, V;
   size_t smem;
 };
@@ -273,14 +273,17 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.bn = nout <= 64 ? 64 : 128;
-  pl.mt = (g_tune[5] >= 1 && pl.bn == 128) ? 1 : 2;  // experimental: 128-pixel tiles (1: two CTAs per SM, 2: one CTA per SM, deeper rings)
+  pl.mt = 2;  // two 128-pixel sub-tiles per tile, one MMA-issuer warp each (single-sub-tile variants measured 5-40 % slower)
   const int bm = kBM * pl.mt;
-  pl.R = ((bm + 2 * (d->in_w + 3)) + 15) / 16 * 16;
+  pl.R = ((bm + 2 * (d->in_w + 3)) + 7) / 8 * 8;
   pl.plane_stride = pl.R * 16 + 16;
   const int slab_bytes = 8 * pl.plane_stride;
   const int slabs = cin / 64;
   const int btile = pl.bn * 128;
-  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + 512;
+  // staged (coalesced) write-out pays off on long image rows; on 14x14 / 7x7 maps the extra epilogue work costs more
+  // than the scattered 16-byte stores (profiles/r01_conv_tuning.md). Knob 5: 1 never, 2 always.
+  pl.staged = (g_tune[5] == 1) ? 0 : (g_tune[5] == 2 ? 1 : (d->in_w >= 20 ? 1 : 0));
+  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + (pl.staged ? 4 * 32 * 64 : 0) + 512;  // align slack + scratch + staging + barriers
   if ((nout + pl.bn - 1) / pl.bn > 4) return pl;
   const int budget = 227 * 1024;
   pl.num_m_tiles = static_cast<int>((V + bm - 1) / bm);
@@ -291,15 +294,12 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
     pl.resident = (slabs == 1 && pl.num_n_tiles == 1) ? 1 : 0;
     pl.nslab = 3;
     if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
-  } else if (pl.mt == 1) {
-    pl.nb = g_tune[5] == 2 ? 8 : 3;
-    pl.resident = 0;
-    pl.nslab = g_tune[5] == 2 ? 3 : 2;
   } else {
     pl.nb = 6;
     pl.resident = 0;
     pl.nslab = 3;
-    if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
+    if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nb = 5;
+    if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) { pl.nb = 6; pl.nslab = 2; }
   }
   pl.smem = static_cast<size_t>(fixed) + static_cast<size_t>(pl.nb) * btile + static_cast<size_t>(pl.nslab) * slab_bytes;
   if (pl.smem > static_cast<size_t>(budget)) return pl;
@@ -336,11 +336,11 @@ bool make_weight_tmap(CUtensorMap* map, const void* base, long long rows, long l
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int MT, int NSLAB, int NB>
+template <int BN, int MT, int NSLAB, int NB, bool STAGED>
 int launch_conv3x3(Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
   static size_t configured = 0;
   if (configured < smem) {
-    cudaFuncSetAttribute(conv3x3_kernel<BN, MT, NSLAB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(conv3x3_kernel<BN, MT, NSLAB, NB, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
   alignas(64) CUtensorMap wmap;
@@ -348,7 +348,7 @@ int launch_conv3x3(Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
   p.b_tma = (g_tune[6] == 0 && (reinterpret_cast<uintptr_t>(p.b) & 15) == 0 &&
              make_weight_tmap(&wmap, p.b, p.nout, static_cast<long long>(p.wtaps) * p.cin, BN))
                 ? 1 : 0;
-  conv3x3_kernel<BN, MT, NSLAB, NB><<<grid, kC3Threads, smem, st>>>(p, wmap);
+  conv3x3_kernel<BN, MT, NSLAB, NB, STAGED><<<grid, kC3Threads, smem, st>>>(p, wmap);
   return cuda_status("conv3x3_kernel");
 }
 
@@ -369,6 +369,7 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
   p.V = pl.V;
   p.num_m_tiles = pl.num_m_tiles; p.num_n_tiles = pl.num_n_tiles;
   p.R = pl.R; p.plane_stride = pl.plane_stride; p.b_resident = pl.resident;
+  p.debug_skip = g_tune[7];
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
     for (int kw = 0; kw < 3; ++kw, ++t) {
@@ -377,21 +378,23 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
       p.wtap[t] = static_cast<short>(t);
     }
   const int tiles = pl.num_m_tiles * pl.num_n_tiles;
-  if (pl.mt == 1 && g_tune[5] == 2) {
-    const int g1 = tiles < kNumSMs ? tiles : kNumSMs;
-    return launch_conv3x3<128, 1, 3, 8>(p, pl.smem, g1, st);
-  }
-  if (pl.mt == 1) {
-    const int g2 = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
-    return launch_conv3x3<128, 1, 2, 3>(p, pl.smem, g2, st);
-  }
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (pl.bn == 64) {
-    if (pl.nslab == 3) return launch_conv3x3<64, 2, 3, 9>(p, pl.smem, grid, st);
-    return launch_conv3x3<64, 2, 2, 9>(p, pl.smem, grid, st);
+    if (pl.staged) {
+      if (pl.nslab == 3) return launch_conv3x3<64, 2, 3, 9, true>(p, pl.smem, grid, st);
+      return launch_conv3x3<64, 2, 2, 9, true>(p, pl.smem, grid, st);
+    }
+    if (pl.nslab == 3) return launch_conv3x3<64, 2, 3, 9, false>(p, pl.smem, grid, st);
+    return launch_conv3x3<64, 2, 2, 9, false>(p, pl.smem, grid, st);
   }
-  if (pl.nslab == 3) return launch_conv3x3<128, 2, 3, 6>(p, pl.smem, grid, st);
-  return launch_conv3x3<128, 2, 2, 6>(p, pl.smem, grid, st);
+  if (pl.staged) {
+    if (pl.nslab == 3 && pl.nb == 6) return launch_conv3x3<128, 2, 3, 6, true>(p, pl.smem, grid, st);
+    if (pl.nslab == 3) return launch_conv3x3<128, 2, 3, 5, true>(p, pl.smem, grid, st);
+    return launch_conv3x3<128, 2, 2, 6, true>(p, pl.smem, grid, st);
+  }
+  if (pl.nslab == 3 && pl.nb == 6) return launch_conv3x3<128, 2, 3, 6, false>(p, pl.smem, grid, st);
+  if (pl.nslab == 3) return launch_conv3x3<128, 2, 3, 5, false>(p, pl.smem, grid, st);
+  return launch_conv3x3<128, 2, 2, 6, false>(p, pl.smem, grid, st);
 }
 
 
@@ -564,7 +567,7 @@ int qt_conv_plan(const qt_conv_desc* d, int pass) {
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
-  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; const int cap = (pl.mt == 1 && g_tune[5] != 2) ? 2 * kNumSMs : kNumSMs; return tiles < cap ? tiles : cap; }
+  if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; return tiles < kNumSMs ? tiles : kNumSMs; }
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   return static_cast<int>(d->groups * ((M + kBM - 1) / kBM));

@@ -161,6 +161,7 @@ def test_conv_fprop_bias_relu(C):
 @pytest.mark.parametrize("n,cin,cout,h,w,k,stride,pad", [
     (2, 64, 64, 8, 8, 3, 1, 1),
     (3, 64, 64, 30, 30, 3, 1, 1),
+    (3, 128, 256, 28, 28, 3, 1, 1),
     (4, 64, 128, 28, 28, 3, 2, 1),
     (4, 64, 128, 28, 28, 1, 2, 0),
     (6, 512, 512, 7, 7, 3, 1, 1),
