@@ -356,6 +356,9 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       const uint32_t stage_w = smem_u32(stage) + warp * 2048;
       const uint32_t st_own = stage_w + lane * 64, st_sw = (lane >> 1) & 3;
       const uint32_t ld_row = stage_w + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+      // column-sum reads: row 2k + (lane >> 4), 4-byte word (lane & 15); that row's 16-byte units are xor-swizzled by
+      // (row >> 1) & 3 = k & 3
+      const uint32_t cs_addr = stage_w + (lane >> 4) * 64 + (lane & 3) * 4;
       // chunk-outer / sub-tile-inner: the per-column sums of the MT sub-tiles are added in registers first, so the
       // 32x32 transpose-reduce (the expensive part: 62 shuffles per thread) runs once per chunk, not once per sub-tile
 #pragma unroll 1
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
         const int ncol = n0 + c0;
         if (ncol >= p.nout || (p.debug_skip & 2)) break;
         float s1v[32], s2v[32];
+        float cs1[2] = {0.f, 0.f}, cs2[2] = {0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < MT; ++u) {
           uint32_t r[32];
@@ -408,6 +412,10 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(vv[2 * j], vv[2 * j + 1]);
           if (STAGED) {
+            if ((flags & EPI_STATS) && !row_ok[u]) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = 0u;  // rows outside the image contribute zero to the statistics
+            }
   #pragma unroll
             for (int j = 0; j < 4; ++j)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(st_own + ((j ^ st_sw) << 4)), "r"(pk[4 * j]),
@@ -421,6 +429,18 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
               if (srow[u][i] >= 0)
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + srow[u][i] + ncol + (lane & 3) * 8) = q;
             }
+            if (flags & EPI_STATS) {
+              // column sums straight from the staged bf16 tile: lane l owns the column pair (l & 15) and every other
+              // row (parity l >> 4): 16 conflict-free 4-byte reads instead of two 32x32 shuffle transposes
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(w) : "r"(cs_addr + k * 128 + ((((lane >> 2) & 3) ^ (k & 3)) << 4)) : "memory");
+                const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+                cs1[0] += lo; cs1[1] += hi;
+                cs2[0] = fmaf(lo, lo, cs2[0]); cs2[1] = fmaf(hi, hi, cs2[1]);
+              }
+            }
             __syncwarp();
           } else if (row_ok[u]) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[u] + ncol;
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
-          if (flags & EPI_STATS) {
+          if (!STAGED && (flags & EPI_STATS)) {
             // statistics of the stored (bf16-rounded) values; rows outside the image contribute zero
             const uint32_t keep = row_ok[u] ? 0xffffffffu : 0u;
 #pragma unroll
@@ -444,7 +464,17 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
             }
           }
         }
-        if (flags & EPI_STATS) {
+        if (STAGED && (flags & EPI_STATS)) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            cs1[e] += __shfl_xor_sync(0xffffffffu, cs1[e], 16);
+            cs2[e] += __shfl_xor_sync(0xffffffffu, cs2[e], 16);
+          }
+          if (lane < 16) {
+            *reinterpret_cast<float2*>(&scratch[(0 * 4 + warp) * BN + c0 + 2 * lane]) = make_float2(cs1[0], cs1[1]);
+            *reinterpret_cast<float2*>(&scratch[(1 * 4 + warp) * BN + c0 + 2 * lane]) = make_float2(cs2[0], cs2[1]);
+          }
+        } else if (flags & EPI_STATS) {
           const float s1 = warp_transpose_reduce(s1v);
           const float s2 = warp_transpose_reduce(s2v);
           scratch[(0 * 4 + warp) * BN + c0 + lane] = s1;
