@@ -182,6 +182,9 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        for kv in filter(None, os.environ.get("QTCNN_TUNE", "").split(",")):  # developer knobs, e.g. QTCNN_TUNE=8=1
+            k, v = kv.split("=")
+            handle.qt_set_tuning(int(k), int(v))
         _lib = handle
     return _lib
 

@@ -38,7 +38,6 @@ struct Conv3x3Params {
   int V;                    // N * (H+1) * (W+2) virtual pixels
   int num_m_tiles, num_n_tiles;
   int R;                    // slab rows (multiple of 16)
-  int plane_stride;         // bytes, R*16 + 16
   int b_resident;           // 1: all 9*slabs weight tiles stay in the B ring
   int b_tma;                // 1: weight tiles arrive by TMA (cp.async.bulk.tensor.2d through `wmap`), else cp.async
   int debug_skip;           // timing experiments only (qt_set_tuning knob 7): bit 0 skips the A copies, bit 1 the epilogue body
@@ -52,7 +51,7 @@ struct C3Smem {
   static constexpr int kBBytes = NB * kBTile;
   static constexpr int kScratch = 2 * 4 * BN * 4 + 4 * 2 * BN * 4;  // cross-warp combine + running sums (<= 4 n-tiles)
   static constexpr int kStage = STAGED ? 4 * 32 * 64 : 0;  // per epilogue warp: 32 rows x 64 B output staging (coalesced write-out)
-  static constexpr int kBarBytes = 512;
+  static constexpr int kBarBytes = 1024;  // keeps the slabs 1024-byte aligned
   // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][staging][barriers][slabs...]
 };
 
@@ -78,7 +77,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint8_t* slab_base = smem + L::kBBytes + L::kScratch + L::kStage + L::kBarBytes;
-  const int slab_bytes = 8 * p.plane_stride;
+  const int slab_bytes = (p.R * 128 + 1023) / 1024 * 1024;  // [R rows][64 channels], 16-byte chunks xor-swizzled by row & 7
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,7 +126,6 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
         {  // ---- A slab: rows j <-> virtual pixel q0 - (W+3) + j
           const int s = a_cnt % NSLAB;
           if (a_cnt >= NSLAB) mbar_wait(&a_empty[s], ((a_cnt / NSLAB) - 1) & 1);
-          const uint32_t dst0 = smem_u32(slab_base + s * slab_bytes) + chunk * p.plane_stride;
           const __nv_bfloat16* src_c = p.a + c * 64 + chunk * 8;
           // first row of this thread: virtual pixel v0 (shifted by one image so the decomposition is non-negative),
           // then advance 16 virtual pixels per iteration with carries instead of dividing per row
@@ -146,7 +144,9 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
           // serialise the copies on that release.
           const char* srcb = reinterpret_cast<const char*>(src_c) +
                              (static_cast<long long>(n * pH + (hp - 1)) * pW + (wp - 1)) * pix_bytes;
-          uint32_t dst = dst0 + rbase * 16;
+          // slab row j holds virtual pixel q0 - (W+3) + j; a thread's rows are 16 apart, so its swizzle phase is fixed
+          uint32_t dst = smem_u32(slab_base + s * slab_bytes) + rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+          constexpr uint32_t dstep = 2048u;  // 16 rows further
           constexpr int kBatch = 4;
           for (int j = rbase; j < pR; j += 16 * kBatch) {
             const void* sp[kBatch];
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b)
-              if (j + 16 * b < pR && !(p.debug_skip & 1)) cp_async16(dst + b * 256, sp[b], sz[b]);
-            dst += 256 * kBatch;
+              if (j + 16 * b < pR && !(p.debug_skip & 1)) cp_async16(dst + b * dstep, sp[b], sz[b]);
+            dst += dstep * kBatch;
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);
           ++a_cnt;
@@ -230,17 +230,20 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
       // descriptor high words are constant: SBO>>4 [0,14) | version 1 [14,16) | layout [29,32)
-      constexpr uint32_t a_hi = (128u >> 4) | (1u << 14) | (kLayoutNone << 29);
+      // Both operands are K-major with the 128-byte swizzle (SBO = 1024: next 8 rows). The hardware applies the
+      // swizzle to the generated ADDRESS bits, so an A descriptor may start at any slab row (start = slab + row*128,
+      // base-offset field 0): that is how one slab serves all nine taps.
       constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);
-      const uint32_t a_lbo = (static_cast<uint32_t>(p.plane_stride >> 4) & 0x3FFFu) << 16;
+      constexpr uint32_t a_hi = b_hi;
+      constexpr uint32_t a_lbo = 1u << 16;
       constexpr uint32_t b_lbo = 1u << 16;
-      const uint32_t kstep = static_cast<uint32_t>(2 * p.plane_stride) >> 4;  // two 16-byte planes per K=16
+      constexpr uint32_t kstep = 2;  // 32 bytes (K = 16) inside the 128-byte row
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t a_cnt = 0, b_cnt = 0, tile_it = 0;
       bool first_tile = true;
-      uint32_t tapoff[9];  // slab row (16-byte units) of each filter tap relative to the tile's first pixel
+      uint32_t tapoff[9];  // slab row of each filter tap relative to the tile's first pixel, in 16-byte descriptor units
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) tapoff[tp] = static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
+      for (int tp = 0; tp < 9; ++tp) tapoff[tp] = static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1)) * 8;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         const uint32_t ab = tile_it & 1;
         if (tile_it >= 2) mbar_wait(&acc_empty[ab], ((tile_it >> 1) - 1) & 1);
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
               const int u = warp - 8;
 #pragma unroll
               for (int tp = 0; tp < 9; ++tp) {
-                const uint32_t a_lo = slab_lo + tapoff[tp] + u * kBM;
+                const uint32_t a_lo = slab_lo + tapoff[tp] + u * (kBM * 8);
                 const uint32_t b_lo = b0 + tp * (L::kBTile >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -284,12 +287,12 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
               if (!p.b_tma) fence_proxy_async_smem();  // cp.async-written filter tile (TMA writes are async-proxy already)
               tc_fence_after();
               const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
-              const uint32_t a_lo = slab_lo + static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1));
+              const uint32_t a_lo = slab_lo + (static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1)) + (warp - 8) * kBM) * 8;
               if (lane == 0) {
                 const int u = warp - 8;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + u * kBM + k * kstep);
+                  const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * kstep);
                   const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * 2);
                   umma_bf16(d_base + u * BN, ad, bd, idesc, (c | tp | k) ? 1u : 0u);
                 }

@@ -52,7 +52,7 @@ constexpr int kNumSMs = 148;
 // ------------------------------------------------------------------------------------------------
 // GEMM launch helpers
 // ------------------------------------------------------------------------------------------------
-int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // [0] wgrad pipeline variant, [1] kmajor pipeline variant
+int g_tune[16] = {0};  // [0] wgrad pipeline variant, [1] kmajor pipeline variant
 bool make_weight_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows);
 
 template <int BN, int STAGES, int LAG, int NPW>
@@ -252,7 +252,7 @@ bool dense_nhwc(const long long* st, int d, int h, int w, int c) {
 
 struct C3Plan {
   bool ok;
-  int bn, mt, nslab, nb, R, plane_stride, resident, staged;
+  int bn, mt, nslab, nb, R, resident, staged;
   int num_m_tiles, num_n_tiles, V;
   size_t smem;
 };
@@ -276,14 +276,13 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   pl.mt = 2;  // two 128-pixel sub-tiles per tile, one MMA-issuer warp each (single-sub-tile variants measured 5-40 % slower)
   const int bm = kBM * pl.mt;
   pl.R = ((bm + 2 * (d->in_w + 3)) + 7) / 8 * 8;
-  pl.plane_stride = pl.R * 16 + 16;
-  const int slab_bytes = 8 * pl.plane_stride;
+  const int slab_bytes = (pl.R * 128 + 1023) / 1024 * 1024;
   const int slabs = cin / 64;
   const int btile = pl.bn * 128;
   // staged (coalesced) write-out pays off on long image rows; on 14x14 / 7x7 maps the extra epilogue work costs more
   // than the scattered 16-byte stores (profiles/r01_conv_tuning.md). Knob 5: 1 never, 2 always.
   pl.staged = (g_tune[5] == 1) ? 0 : (g_tune[5] == 2 ? 1 : (d->in_w >= 20 ? 1 : 0));
-  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + (pl.staged ? 4 * 32 * 64 : 0) + 512;  // align slack + scratch + staging + barriers
+  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + (pl.staged ? 4 * 32 * 64 : 0) + 1024;  // align slack + scratch + staging + barriers
   if ((nout + pl.bn - 1) / pl.bn > 4) return pl;
   const int budget = 227 * 1024;
   pl.num_m_tiles = static_cast<int>((V + bm - 1) / bm);
@@ -368,7 +367,7 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
   p.slabs = cin / 64;
   p.V = pl.V;
   p.num_m_tiles = pl.num_m_tiles; p.num_n_tiles = pl.num_n_tiles;
-  p.R = pl.R; p.plane_stride = pl.plane_stride; p.b_resident = pl.resident;
+  p.R = pl.R; p.b_resident = pl.resident;
   p.debug_skip = g_tune[7];
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
@@ -466,6 +465,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   p.N = d->n; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
   p.V = pl.V; p.num_kt = pl.num_kt; p.kt_per_split = pl.kt_per_split;
   p.R = pl.R; p.plane_stride = pl.plane_stride;
+  p.debug_skip = g_tune[7];
   p.cout_tiles = pl.cout_tiles; p.cin_groups = pl.cin_groups; p.tap_groups = pl.tap_groups;
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
@@ -483,7 +483,7 @@ extern "C" {
 
 int qt_version(void) { return 101; }
 void qt_set_conv3x3_enabled(int on) { g_use_conv3x3 = on != 0; }
-void qt_set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tune[key] = value; }
+void qt_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 const char* qt_last_error(void) { return g_err; }
 int qt_take_timeout_flag(void) {
   unsigned int v = 0, z = 0;

@@ -29,6 +29,7 @@ struct Wgrad3x3Params {
   int R, plane_stride;       // slab rows (multiple of 16), bytes per plane (R*16 + 16)
   int cout_tiles, cin_groups, tap_groups;
   signed char off_h[9], off_w[9];
+  int debug_skip;            // timing experiments only (qt_set_tuning knob 7): bit 0 skips the gathers
 };
 
 template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           const bool ok = (n < pN) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int b = 0; b < CB; ++b)
-            cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
+            if (!(p.debug_skip & 1)) cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
           src += dy_adv;
           wp += adv_w; hp += adv_h;
           if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * dy_pix; }
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
                           (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int sl = 0; sl < NSLAB; ++sl)
-            cp_async16(dst + sl * 8 * plane_stride, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
+            if (!(p.debug_skip & 1)) cp_async16(dst + sl * 8 * plane_stride, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
           dst += 256;
           src += x_adv;
           wp += adv_w; hp += adv_h;
