@@ -40,7 +40,6 @@ struct Conv3x3Params {
   int R;                    // slab rows (multiple of 16)
   int b_resident;           // 1: all 9*slabs weight tiles stay in the B ring
   int b_tma;                // 1: weight tiles arrive by TMA (cp.async.bulk.tensor.2d through `wmap`), else cp.async
-  int debug_skip;           // timing experiments only (qt_set_tuning knob 7): bit 0 skips the A copies, bit 1 the epilogue body
   signed char off_h[9], off_w[9];
   short wtap[9];
 };
@@ -164,7 +163,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b)
-              if (j + 16 * b < pR && !(p.debug_skip & 1)) cp_async16(dst + b * dstep, sp[b], sz[b]);
+              if (j + 16 * b < pR) cp_async16(dst + b * dstep, sp[b], sz[b]);
             dst += dstep * kBatch;
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int ncol = n0 + c0;
-        if (ncol >= p.nout || (p.debug_skip & 2)) break;
+        if (ncol >= p.nout) break;
         float s1v[32], s2v[32];
         float cs1[2] = {0.f, 0.f}, cs2[2] = {0.f, 0.f};
 #pragma unroll

@@ -368,7 +368,6 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
   p.V = pl.V;
   p.num_m_tiles = pl.num_m_tiles; p.num_n_tiles = pl.num_n_tiles;
   p.R = pl.R; p.b_resident = pl.resident;
-  p.debug_skip = g_tune[7];
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
     for (int kw = 0; kw < 3; ++kw, ++t) {
@@ -403,7 +402,7 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
 struct W3Plan {
   bool ok;
   int cfg;  // 0: 64->64 (NSLAB 1, 5 taps, 3 stages), 1: 128-multiples (NSLAB 2, 3 taps, 2 stages)
-  int V, num_kt, splits, kt_per_split, R, plane_stride, cout_tiles, cin_groups, tap_groups;
+  int V, num_kt, splits, kt_per_split, R, cout_tiles, cin_groups, tap_groups;
   size_t smem, ws_bytes;
 };
 W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
@@ -421,8 +420,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);
-  pl.R = (kW3KP + 2 * (d->in_w + 3) + 15) / 16 * 16;
-  pl.plane_stride = pl.R * 16 + 16;
+  pl.R = (kW3KP + 2 * (d->in_w + 3) + 7) / 8 * 8;
   const int nslab = pl.cfg == 0 ? 1 : 2, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 3 : 2, taps = pl.cfg == 0 ? 5 : 3;
   pl.cout_tiles = d->out_c / (64 * cb);
   pl.cin_groups = d->in_c / (64 * nslab);
@@ -434,7 +432,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (splits < 1) splits = 1;
   pl.kt_per_split = (pl.num_kt + splits - 1) / splits;
   pl.splits = (pl.num_kt + pl.kt_per_split - 1) / pl.kt_per_split;
-  const size_t slab_bytes = (static_cast<size_t>(8) * nslab * pl.plane_stride + 1023) / 1024 * 1024;
+  const size_t slab_bytes = static_cast<size_t>(nslab) * ((static_cast<size_t>(pl.R) * 128 + 1023) / 1024 * 1024);
   pl.smem = 1024 + stages * (static_cast<size_t>(cb) * kW3KP * 128 + slab_bytes) + (cb == 1 ? kW3KP * 128 : 0) + 256;
   if (pl.smem > 227 * 1024) return pl;
   pl.ws_bytes = static_cast<size_t>(pl.splits) * 9 * d->in_c * d->out_c * sizeof(float);
@@ -464,8 +462,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   p.ws = static_cast<float*>(ws);
   p.N = d->n; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
   p.V = pl.V; p.num_kt = pl.num_kt; p.kt_per_split = pl.kt_per_split;
-  p.R = pl.R; p.plane_stride = pl.plane_stride;
-  p.debug_skip = g_tune[7];
+  p.R = pl.R;
   p.cout_tiles = pl.cout_tiles; p.cin_groups = pl.cin_groups; p.tap_groups = pl.tap_groups;
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)

@@ -26,10 +26,9 @@ struct Wgrad3x3Params {
   float* ws;                 // [splits][Mpad = 9*cin][Npad = cout]
   int N, H, W, cin, cout;
   int V, num_kt, kt_per_split;
-  int R, plane_stride;       // slab rows (multiple of 16), bytes per plane (R*16 + 16)
+  int R;                     // slab rows (multiple of 8)
   int cout_tiles, cin_groups, tap_groups;
   signed char off_h[9], off_w[9];
-  int debug_skip;            // timing experiments only (qt_set_tuning knob 7): bit 0 skips the gathers
 };
 
 template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
@@ -40,7 +39,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int dy_bytes = CB * kW3KP * 128;                        // CB blocks of [128 pixels][128 B]
-  const int slab_bytes = (8 * NSLAB * p.plane_stride + 1023) / 1024 * 1024;
+  const int xblk_bytes = (p.R * 128 + 1023) / 1024 * 1024;     // one 64-channel block of the slab: [R rows][128 B], 128-byte swizzle
+  const int slab_bytes = NSLAB * xblk_bytes;
   const int stage_bytes = dy_bytes + slab_bytes;
   uint8_t* zero_blk = smem + STAGES * stage_bytes;              // 16 KB of zeros (cout rows 64..127 when CB == 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + (CB == 1 ? kW3KP * 128 : 0));
@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     const char* x_c = reinterpret_cast<const char*>(p.x + cin0 + chunk * 8);
     const void* dummy_dy = p.dy;
     const void* dummy_x = p.x;
-    const uint32_t plane_stride = p.plane_stride;
     for (int it = 0; it < nit; ++it) {
       const int s = it % STAGES;
       if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           const bool ok = (n < pN) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int b = 0; b < CB; ++b)
-            if (!(p.debug_skip & 1)) cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
+            cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
           src += dy_adv;
           wp += adv_w; hp += adv_h;
           if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * dy_pix; }
@@ -142,15 +141,15 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           n = rest / Hp - 1;
         }
         const char* src = x_c + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
-        uint32_t dst = smem_u32(st + dy_bytes) + chunk * plane_stride + rbase * 16;
+        uint32_t dst = smem_u32(st + dy_bytes) + rbase * 128 + dsw;  // rows 16 apart keep the swizzle phase (row & 7)
 #pragma unroll 2
         for (int j = rbase; j < pR; j += 16) {
           const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(pN)) &&
                           (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
 #pragma unroll
           for (int sl = 0; sl < NSLAB; ++sl)
-            if (!(p.debug_skip & 1)) cp_async16(dst + sl * 8 * plane_stride, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
-          dst += 256;
+            cp_async16(dst + sl * xblk_bytes, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
+          dst += 2048;
           src += x_adv;
           wp += adv_w; hp += adv_h;
           if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * x_pix; }
@@ -167,8 +166,10 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     const int tpar = warp - 4;
     constexpr uint32_t idesc = make_idesc_bf16(kBM, NCH, 1, 1);
     constexpr uint32_t a_hi = (1024u >> 4) | (1u << 14) | (kLayoutSW128 << 29);   // SBO: next 8 pixels of dy
-    const uint32_t b_hi = (static_cast<uint32_t>(p.plane_stride >> 4) & 0x3FFFu) | (1u << 14) | (kLayoutNone << 29);  // SBO: next chunk plane
-    constexpr uint32_t b_lbo = (128u >> 4) << 16;                                 // LBO: next 8 pixels of the slab
+    // x slab: MN-major SW128 like the dy tile (SBO: next 8 pixels, LBO: next 64-channel block). The swizzle acts on
+    // address bits, so the descriptor may start at any slab row: start = slab + (tap row) * 128.
+    constexpr uint32_t b_hi = a_hi;
+    const uint32_t b_lbo = ((static_cast<uint32_t>(xblk_bytes) >> 4) & 0x3FFFu) << 16;
     const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
     // per-tap start rows (in 16-byte units) kept in registers; the 8 x TAPS MMAs of a k-tile are fully unrolled
     uint32_t row0[TAPS];
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           for (int tp = 0; tp < TAPS; ++tp) {
             if ((NMMA == 1 || (tp & 1) == tpar) && tp < ntap) {
               const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + ks * (2048 >> 4));
-              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (x_lo + row0[tp] + ks * 16);
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (x_lo + (row0[tp] + ks * 16) * 8);
               umma_bf16(tbase + tp * NCH, ad, bd, idesc, ks ? 1u : acc);
             }
           }
