@@ -421,7 +421,9 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   pl.V = static_cast<int>(V);
   pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);
   pl.R = (kW3KP + 2 * (d->in_w + 3) + 7) / 8 * 8;
-  const int nslab = pl.cfg == 0 ? 1 : 2, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 3 : 2, taps = pl.cfg == 0 ? 5 : 3;
+  // cfg 0 pairs horizontally adjacent taps in one MMA (wgrad3x3.cuh): 6 MMA groups cover all 9 taps in a single CTA
+  const int nslab = pl.cfg == 0 ? 1 : 2, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 4 : 2, taps = pl.cfg == 0 ? 9 : 3;
+  const int dy_rows = pl.cfg == 0 ? kW3KP + 8 : kW3KP;
   pl.cout_tiles = d->out_c / (64 * cb);
   pl.cin_groups = d->in_c / (64 * nslab);
   pl.tap_groups = (9 + taps - 1) / taps;
@@ -433,7 +435,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   pl.kt_per_split = (pl.num_kt + splits - 1) / splits;
   pl.splits = (pl.num_kt + pl.kt_per_split - 1) / pl.kt_per_split;
   const size_t slab_bytes = static_cast<size_t>(nslab) * ((static_cast<size_t>(pl.R) * 128 + 1023) / 1024 * 1024);
-  pl.smem = 1024 + stages * (static_cast<size_t>(cb) * kW3KP * 128 + slab_bytes) + (cb == 1 ? kW3KP * 128 : 0) + 256;
+  pl.smem = 1024 + stages * (static_cast<size_t>(cb) * dy_rows * 128 + slab_bytes) + 256;
   if (pl.smem > 227 * 1024) return pl;
   pl.ws_bytes = static_cast<size_t>(pl.splits) * 9 * d->in_c * d->out_c * sizeof(float);
   pl.ok = true;
@@ -467,7 +469,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
     for (int kw = 0; kw < 3; ++kw, ++t) { p.off_h[t] = static_cast<signed char>(kh - 1); p.off_w[t] = static_cast<signed char>(kw - 1); }
-  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 5, 1, 3, 1>(p, pl, st) : launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st);
+  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 6, 1, 4, 2>(p, pl, st) : launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st);
   if (rc) return rc;
   launch_splitk_reduce_wgrad(p.ws, pl.splits, 9 * d->in_c, d->out_c, 9 * d->in_c, d->out_c, d->in_c, 9, dw, accumulate, st);
   return cuda_status("splitk_reduce_wgrad_kernel");

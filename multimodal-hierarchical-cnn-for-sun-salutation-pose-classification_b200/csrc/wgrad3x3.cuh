@@ -38,12 +38,17 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
   static_assert(TAPS * NCH <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int dy_bytes = CB * kW3KP * 128;                        // CB blocks of [128 pixels][128 B]
+  // PAIR (64 -> 64 layers, CB == 1): the dy tile carries 8 extra pixel rows and the A descriptor's second 64-row atom
+  // starts ONE pixel row (128 B) after the first, so accumulator rows 64..127 see dy[p+1]: with the x slab started at
+  // tap (dh,+1) one MMA yields the gradients of taps (dh,+1) [rows 0..63] and (dh,0) [rows 64..127]. Six MMA groups
+  // (3 pairs + the 3 single dw=-1 taps) replace nine half-empty ones and fit one CTA, so nothing is gathered twice.
+  constexpr bool PAIR = (CB == 1);
+  constexpr int kDyRows = PAIR ? kW3KP + 8 : kW3KP;
+  const int dy_bytes = CB * kDyRows * 128;                      // CB blocks of [pixels][128 B]
   const int xblk_bytes = (p.R * 128 + 1023) / 1024 * 1024;     // one 64-channel block of the slab: [R rows][128 B], 128-byte swizzle
   const int slab_bytes = NSLAB * xblk_bytes;
   const int stage_bytes = dy_bytes + slab_bytes;
-  uint8_t* zero_blk = smem + STAGES * stage_bytes;              // 16 KB of zeros (cout rows 64..127 when CB == 1)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(zero_blk + (CB == 1 ? kW3KP * 128 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = full + STAGES;
   uint64_t* done = empty + STAGES;
@@ -58,17 +63,13 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
   const int cin_group = type % p.cin_groups;
   const int cout_tile = type / p.cin_groups;
   const int tap0 = tap_group * TAPS;
-  const int ntap = min(TAPS, 9 - tap0);
+  const int ntap = PAIR ? TAPS : min(TAPS, 9 - tap0);  // PAIR: TAPS == 6 MMA groups, one tap group
   const int cin0 = cin_group * NCH;
   const int cout0 = cout_tile * (64 * CB);
   const int kt0 = blockIdx.y * p.kt_per_split;
   const int kt1 = min(p.num_kt, kt0 + p.kt_per_split);
   const int nit = max(0, kt1 - kt0);
 
-  if (CB == 1) {
-    for (int i = threadIdx.x * 16; i < kW3KP * 128; i += 192 * 16) *reinterpret_cast<uint4*>(zero_blk + i) = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
-  }
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], NMMA); }
@@ -120,11 +121,13 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
         const char* src = dy_c + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * dy_pix;
         const uint32_t dst0 = smem_u32(st) + dsw + rbase * 128;
 #pragma unroll
-        for (int i = 0; i < kW3KP / 16; ++i) {
+        for (int i = 0; i < (kDyRows + 15) / 16; ++i) {
           const bool ok = (n < pN) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
+          if (rbase + 16 * i < kDyRows) {
 #pragma unroll
-          for (int b = 0; b < CB; ++b)
-            cp_async16(dst0 + b * (kW3KP * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
+            for (int b = 0; b < CB; ++b)
+              cp_async16(dst0 + b * (kDyRows * 128) + i * 2048, ok ? static_cast<const void*>(src + b * 128) : dummy_dy, ok ? 16u : 0u);
+          }
           src += dy_adv;
           wp += adv_w; hp += adv_h;
           if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * dy_pix; }
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     uint32_t row0[TAPS];
 #pragma unroll
     for (int tp = 0; tp < TAPS; ++tp) {
-      const int tsel = min(tap0 + tp, 8);
+      // PAIR: group 2*kh starts the slab at tap (kh, kw = 2) [pair with (kh, 1)], group 2*kh + 1 at tap (kh, kw = 0)
+      const int tsel = PAIR ? (tp >> 1) * 3 + ((tp & 1) ? 0 : 2) : min(tap0 + tp, 8);
       row0[tp] = static_cast<uint32_t>((p.off_h[tsel] + 1) * Wp + (p.off_w[tsel] + 1));
     }
     for (int it = 0; it < nit; ++it) {
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       tc_fence_after();
       uint8_t* st = smem + s * stage_bytes;
       const uint32_t a_addr = smem_u32(st);
-      const uint32_t a_lbo_bytes = (CB == 2) ? static_cast<uint32_t>(kW3KP * 128) : (smem_u32(zero_blk) - a_addr);
+      const uint32_t a_lbo_bytes = (CB == 2) ? static_cast<uint32_t>(kW3KP * 128) : 128u;  // PAIR: rows 64..127 <- next pixel
       const uint32_t a_lo = ((a_addr >> 4) & 0x3FFFu) | (((a_lbo_bytes >> 4) & 0x3FFFu) << 16);
       const uint32_t x_lo = ((smem_u32(st + dy_bytes) >> 4) & 0x3FFFu) | b_lbo;
       const uint32_t acc = it ? 1u : 0u;
@@ -215,18 +219,22 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       mbar_wait(done, 0);
       tc_fence_after();
     }
-    const int crow = warp * 32 + lane;            // cout within the 128-row accumulator
-    const bool row_ok = crow < 64 * CB && (cout0 + crow) < p.cout;
+    const int crow = warp * 32 + lane;            // row of the 128-row accumulator
     const long long Mpad = 9LL * p.cin;
     for (int tp = 0; tp < ntap; ++tp) {
+      // PAIR: rows 0..63 of group tp belong to the tap the slab was started at, rows 64..127 (pair groups only) to its
+      // left neighbour (kh, 1); otherwise row == cout and the accumulator is tap0 + tp
+      const int tap = PAIR ? (tp >> 1) * 3 + ((tp & 1) ? 0 : (crow < 64 ? 2 : 1)) : tap0 + tp;
+      const int co = PAIR ? (crow & 63) : crow;
+      const bool row_ok = PAIR ? (crow < 64 || !(tp & 1)) : ((cout0 + crow) < p.cout);
 #pragma unroll 1
       for (int c0 = 0; c0 < NCH; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tp * NCH + c0, r);
         tmem_ld_wait();
         if (row_ok) {
-          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap0 + tp) * p.cin + cin0 + c0) * p.cout +
-                       cout0 + crow;
+          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap) * p.cin + cin0 + c0) * p.cout +
+                       cout0 + co;
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.cout] = nit > 0 ? __uint_as_float(r[j]) : 0.f;
         }
