@@ -155,7 +155,7 @@ struct KMajorSmem {
 // K-major kernel: fprop / dgrad / linear
 // =============================================================================================
 template <int BN, int STAGES, int kLag, int NPW>
-__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p,
+__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p,
                                                                                        const __grid_constant__ CUtensorMap bmap) {
   using L = KMajorSmem<BN, STAGES>;
   constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
@@ -300,6 +300,13 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
     const long long orow = row_ok ? out_row_offset(p, m, p.o_goff[g]) : 0;
     float* stat_scratch = reinterpret_cast<float*>(smem);  // [2][4][BN], aliases stage 0 (all MMAs retired)
     const int flags = p.flags;
+    // rows this lane writes out in the staged (coalesced) path: 8*i + lane/4; -1 = outside the problem
+    long long srow[4];
+    {
+      const long long mine = row_ok ? orow : -1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) srow[i] = __shfl_sync(0xffffffffu, mine, 8 * i + (lane >> 2));
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -360,6 +367,54 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) ig
               if (ncol + j < p.nout) dst[j] = v[j];
           }
         }
+      } else if (__all_sync(0xffffffffu, full_chunk && (!row_ok || ((orow | ncol) & 7) == 0) &&
+                                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0))) {
+        // Coalesced write-out through a per-warp staging tile in the (retired) first pipeline stage: one store
+        // instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes, which keeps the LSU free for
+        // the co-resident CTA's cp.async gathers (same scheme as conv3x3.cuh). BatchNorm column sums are read back
+        // from the staged bf16 values.
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = row_ok ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+        const uint32_t stage_w = smem_u32(smem) + 4096 + warp * 2048;
+        const uint32_t st_own = stage_w + lane * 64, st_sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(st_own + ((j ^ st_sw) << 4)), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        const uint32_t ld_row = stage_w + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ld_row + i * 512) : "memory");
+          if (srow[i] >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + srow[i] + ncol + (lane & 3) * 8) = q;
+        }
+        if (flags & EPI_STATS) {
+          // lane l: column pair (l & 15), rows of parity l >> 4 (see conv3x3.cuh)
+          float cs1[2] = {0.f, 0.f}, cs2[2] = {0.f, 0.f};
+          const uint32_t cs_addr = stage_w + (lane >> 4) * 64 + (lane & 3) * 4;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(w) : "r"(cs_addr + k * 128 + ((((lane >> 2) & 3) ^ (k & 3)) << 4)) : "memory");
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+            cs1[0] += lo; cs1[1] += hi;
+            cs2[0] = fmaf(lo, lo, cs2[0]); cs2[1] = fmaf(hi, hi, cs2[1]);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            cs1[e] += __shfl_xor_sync(0xffffffffu, cs1[e], 16);
+            cs2[e] += __shfl_xor_sync(0xffffffffu, cs2[e], 16);
+          }
+          if (lane < 16) {
+            *reinterpret_cast<float2*>(&stat_scratch[(0 * 4 + warp) * BN + c0 + 2 * lane]) = make_float2(cs1[0], cs1[1]);
+            *reinterpret_cast<float2*>(&stat_scratch[(1 * 4 + warp) * BN + c0 + 2 * lane]) = make_float2(cs2[0], cs2[1]);
+          }
+        }
+        __syncwarp();
+        continue;
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
@@ -428,7 +483,7 @@ struct WgradSmem {
 };
 
 template <int BN, int STAGES, int kLag, int NPW>
-__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads) igemm_wgrad_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2) igemm_wgrad_kernel(const __grid_constant__ IgemmParams p) {
   using L = WgradSmem<BN, STAGES>;
   constexpr uint32_t TCOLS = BN;
   static_assert(BN % 64 == 0, "wgrad BN must be a multiple of 64");
