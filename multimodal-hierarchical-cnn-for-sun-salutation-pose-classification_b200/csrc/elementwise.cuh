@@ -397,18 +397,25 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M
 __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
                                 __nv_bfloat16* __restrict__ out, long long total8, int C, int relu) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  // When the grid stride is a multiple of C/8 vectors, a thread sees the same 8 channels in every iteration: the
+  // coefficients are loaded once (otherwise 4 extra L1 loads per 16-byte element vector).
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool fixed = ((stride * 8) % C) == 0;
+  float sc[8], sh[8];
+  auto load_coef = [&](long long i) {
     const int c0 = static_cast<int>((i * 8) % C);
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + c0));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+  };
+  if (fixed && i0 < total8) load_coef(i0);
+  for (long long i = i0; i < total8; i += stride) {
+    if (!fixed) load_coef(i);
     float f[8], r[8];
     unpack8(ld_nc16(y + i * 8), f);
     if (residual) unpack8(ld_nc16(residual + i * 8), r);
-    const float4 sa = __ldg(reinterpret_cast<const float4*>(scale + c0));
-    const float4 sb = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-    const float4 ha = __ldg(reinterpret_cast<const float4*>(shift + c0));
-    const float4 hb = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
-    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = fmaf(f[e], sc[e], sh[e]);
@@ -515,27 +522,31 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
                                     __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dz_out,
                                     long long total8, int C) {
   const bool ymask = (act == nullptr) && (msc != nullptr);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  // per-thread channel group is loop-invariant when the grid stride is a multiple of C/8 vectors (see bn_apply_kernel)
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool fixed = ((stride * 8) % C) == 0;
+  float ca[8], cb[8], ck[8], ms[8], mh[8];
+  auto load_coef = [&](long long i) {
     const int c0 = static_cast<int>((i * 8) % C);
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      *reinterpret_cast<float4*>(ca + e) = __ldg(reinterpret_cast<const float4*>(coef + c0 + e));
+      *reinterpret_cast<float4*>(cb + e) = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + e));
+      *reinterpret_cast<float4*>(ck + e) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0 + e));
+      if (ymask) {
+        *reinterpret_cast<float4*>(ms + e) = __ldg(reinterpret_cast<const float4*>(msc + c0 + e));
+        *reinterpret_cast<float4*>(mh + e) = __ldg(reinterpret_cast<const float4*>(msh + c0 + e));
+      }
+    }
+  };
+  if (fixed && i0 < total8) load_coef(i0);
+  for (long long i = i0; i < total8; i += stride) {
+    if (!fixed) load_coef(i);
     float d[8], a[8], v[8], o[8];
     unpack8(ld_nc16(dout + i * 8), d);
     unpack8(ld_nc16(y + i * 8), v);
     if (act) unpack8(ld_nc16(act + i * 8), a);
-    float ca[8], cb[8], ck[8];
-    *reinterpret_cast<float4*>(ca) = __ldg(reinterpret_cast<const float4*>(coef + c0));
-    *reinterpret_cast<float4*>(ca + 4) = __ldg(reinterpret_cast<const float4*>(coef + c0 + 4));
-    *reinterpret_cast<float4*>(cb) = __ldg(reinterpret_cast<const float4*>(coef + C + c0));
-    *reinterpret_cast<float4*>(cb + 4) = __ldg(reinterpret_cast<const float4*>(coef + C + c0 + 4));
-    *reinterpret_cast<float4*>(ck) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0));
-    *reinterpret_cast<float4*>(ck + 4) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4));
-    float ms[8], mh[8];
-    if (ymask) {
-      *reinterpret_cast<float4*>(ms) = __ldg(reinterpret_cast<const float4*>(msc + c0));
-      *reinterpret_cast<float4*>(ms + 4) = __ldg(reinterpret_cast<const float4*>(msc + c0 + 4));
-      *reinterpret_cast<float4*>(mh) = __ldg(reinterpret_cast<const float4*>(msh + c0));
-      *reinterpret_cast<float4*>(mh + 4) = __ldg(reinterpret_cast<const float4*>(msh + c0 + 4));
-    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const bool off = act ? !(a[e] > 0.f) : (ymask && !(fmaf(v[e], ms[e], mh[e]) > 0.f));
