@@ -134,33 +134,45 @@ __global__ void wpack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // Dynamic smem COT*(32*(T|1)+1) floats, odd pitches in both directions (bank-conflict free). COT = 8 for filters
 // with taps (8 x 32 x 9 tiles keep even the 64x64 layers at 16+ blocks; the 16-byte runs of wd[ci][t][co0..co0+7]
 // are one sector), COT = 32 for T == 1 (1x1 convs and linear layers: a plain 32 x 32 transpose tile).
-__device__ __forceinline__ void wpack_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                           __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T, int COT, int bx, int by,
-                                           float* tile) {
+template <int TC>  // TC > 0: taps known at compile time (index divisions become multiplies); 0: runtime T
+__device__ __forceinline__ void wpack_tile_t(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                             __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int Trt, int COT, int bx, int by,
+                                             float* tile) {
+  const int T = TC > 0 ? TC : Trt;
   const int ci0 = bx * 32, co0 = by * COT;
   const int TP = T | 1;
   const int CP = 32 * TP + 1;
   const int run = 32 * T;
+  const int cot_shift = COT == 32 ? 5 : 3;  // COT is 8 or 32
+  const bool full = (co0 + COT <= Cout) && (ci0 + 32 <= Cin);
   for (int i = threadIdx.x; i < COT * run; i += blockDim.x) {
     const int co = i / run, r = i - co * run;  // r = ci_local*T + t, contiguous in w for a fixed co
     const int cil = r / T, t = r - cil * T;
     float v = 0.f;
-    if (co0 + co < Cout && ci0 + cil < Cin) v = w[(static_cast<long long>(co0 + co) * Cin + ci0) * T + r];
+    if (full || (co0 + co < Cout && ci0 + cil < Cin)) v = w[(static_cast<long long>(co0 + co) * Cin + ci0) * T + r];
     tile[co * CP + cil * TP + t] = v;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < COT * run; i += blockDim.x) {
     {  // wf[co][t][ci]: ci fastest
-      const int cil = i & 31, t = (i >> 5) % T, co = i / run;
-      if (co0 + co < Cout && ci0 + cil < Cin)
+      const int cil = i & 31, q = i >> 5, co = q / T, t = q - co * T;
+      if (full || (co0 + co < Cout && ci0 + cil < Cin))
         wf[(static_cast<long long>(co0 + co) * T + t) * Cin + ci0 + cil] = __float2bfloat16_rn(tile[co * CP + cil * TP + t]);
     }
     if (wd) {  // wd[ci][t][co]: co fastest (COT per block)
-      const int col = i % COT, t = (i / COT) % T, cil = i / (COT * T);
-      if (co0 + col < Cout && ci0 + cil < Cin)
+      const int col = i & (COT - 1), q = i >> cot_shift, cil = q / T, t = q - cil * T;
+      if (full || (co0 + col < Cout && ci0 + cil < Cin))
         wd[(static_cast<long long>(ci0 + cil) * T + t) * Cout + co0 + col] = __float2bfloat16_rn(tile[col * CP + cil * TP + t]);
     }
   }
+}
+__device__ __forceinline__ void wpack_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                           __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T, int COT, int bx, int by,
+                                           float* tile) {
+  if (T == 9) wpack_tile_t<9>(w, wf, wd, Cout, Cin, T, COT, bx, by, tile);
+  else if (T == 1) wpack_tile_t<1>(w, wf, wd, Cout, Cin, T, COT, bx, by, tile);
+  else if (T == 27) wpack_tile_t<27>(w, wf, wd, Cout, Cin, T, COT, bx, by, tile);
+  else wpack_tile_t<0>(w, wf, wd, Cout, Cin, T, COT, bx, by, tile);
 }
 __global__ void wpack_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int T, int COT) {
