@@ -138,7 +138,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a mismatched collective should end the run in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from oracle import quadtree_oracle as O  # synthetic-input recipe + cpu_baseline only
     from qtcnn_b200 import models as M
     from qtcnn_b200 import ops, parallel
@@ -242,12 +244,14 @@ def run_ours(args):
     h2d = images_h.numel() * 4 + numerical_h.numel() * 4 + labels_h.numel() * 8
 
     roofline = None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:
+        # every rank runs the instrumented steps (their gradient all-reduces must match across ranks); rank 0 reports
         ops.profile_begin()
         for _ in range(min(3, args.steps)):
             step(images, numerical, labels)
         torch.cuda.synchronize()
         prof = ops.profile_end()
+    if not args.no_roofline and rank == 0:
         peaks = load_peaks()
         gemm = {k: v for k, v in prof.items() if v["flops"] > 0}
         nsteps = min(3, args.steps)
