@@ -55,7 +55,11 @@ int qt_take_timeout_flag(void);
 /* Tuning/debug switch: 0 routes 3x3 stride-1 convolutions through the generic gather kernel instead of the
  * persistent input-reuse kernel (both are tcgen05 paths). */
 void qt_set_conv3x3_enabled(int on);
-/* Experimental pipeline-shape selection (key 0: weight-gradient kernel, key 1: K-major kernel; value 0 = default). */
+/* Developer knobs (value 0 = default everywhere). key 0 / 1: pipeline shape of the generic weight-gradient / K-major
+ * kernels; 2: generic gather for the stem; 3: generic weight-gradient kernel for 3x3 convs; 4: 7x7 maps through the
+ * generic kernels; 5: staged (coalesced) conv3x3 write-out 1 = never, 2 = always (default: maps at least 20 wide);
+ * 6: weight tiles by cp.async instead of TMA. Also settable through the QTCNN_TUNE="k=v,..." environment variable
+ * of the Python binding. */
 void qt_set_tuning(int key, int value);
 
 /* ---- layout / packing ------------------------------------------------------------------------- */
