@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="quadtree_train", choices=["quadtree_train", "attention_infer", "quadtree3d_train"],
+    ap.add_argument("--workload", default="quadtree_train", choices=["quadtree_train", "attention_infer", "quadtree3d_train", "cnn_lstm_train"],
                     help="quadtree_train is the BASELINE.json headline (configs[2]); the other two time configs[1] / configs[3] "
                          "for profiles/ and print an informational line with their own metric name")
     return ap.parse_args()
@@ -326,6 +326,22 @@ def run_secondary(args):
                 return model(images, numerical)
         metric, unit, per_step = "AttentionHierarchicalCNN (level-1+2) inference images/sec @224^2 bf16", "images/s", B
         flops = 3.977e9 * B
+    elif args.workload == "cnn_lstm_train":
+        # BASELINE.json configs[4] / SURVEY §8 a17: 16 frames x 224^2 per sample, frozen ResNet-18 (3.63 GFLOP/frame forward)
+        B = 16 if args.batch == 256 else args.batch
+        model = M.get_model_seq("cnn_lstm", 8, dev, seq_len=16).train()
+        opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4, fused=True)
+        frames, numerical, labels = O.synthetic_batch(B, 1234, seq_len=16, clip_size=224)
+        frames, numerical, labels = frames.to(dev), numerical.to(dev), labels.to(dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(model(frames, numerical), labels)
+            loss.backward()
+            opt.step()
+            return loss
+        metric, unit, per_step = "CnnLstm train frames/sec 16x224^2 bf16 (frozen ResNet-18 + LSTM)", "frames/s", B * 16
+        flops = 3.63e9 * B * 16
     else:
         B = 32 if args.batch == 256 else args.batch
         model = M.Quadtree3DCNN(num_classes=8, sequence_length=16).to(dev).train()

@@ -661,6 +661,52 @@ class Quadtree3DCNN(nn.Module):
         return Fn.SmallLinear.apply(h, cls[3].weight, cls[3].bias, False, 0.0, self.training)
 
 
+# =================================================================================================
+# CnnLstm (cnn+lstm/models.py:14-89): every frame through the frozen ResNet-18 on the tensor cores; the temporal
+# LSTM stays torch
+# =================================================================================================
+class CnnLstm(nn.Module):
+    def __init__(self, num_classes, sequence_length=4, numerical_feature_dim=47, dropout_rate=0.5, lstm_hidden_size=256):
+        super().__init__()
+        self.sequence_length = sequence_length
+        resnet = make_resnet18()
+        self.cnn_backbone = FusedFeatures(*list(resnet.children())[:-1])  # same children / indices / keys as the reference
+        for param in self.cnn_backbone.parameters():
+            param.requires_grad = False
+        self.numerical_mlp = nn.Sequential(nn.Linear(numerical_feature_dim, 128), nn.ReLU(), nn.Linear(128, 128))
+        self.lstm = nn.LSTM(input_size=512 + 128, hidden_size=lstm_hidden_size, num_layers=2, batch_first=True,
+                            dropout=dropout_rate)
+        self.classifier = nn.Sequential(nn.Linear(lstm_hidden_size, 128), nn.ReLU(), nn.Dropout(dropout_rate),
+                                        nn.Linear(128, num_classes))
+        self.dropout_rate = dropout_rate
+
+    def forward(self, image_sequence, numerical_sequence):
+        _require_cuda(image_sequence, "CnnLstm")
+        batch_size, seq_len, c, h, w = image_sequence.shape
+        c_in = image_sequence.reshape(batch_size * seq_len, c, h, w)
+        c_out = self.cnn_backbone(c_in).flatten(1).float().view(batch_size, seq_len, -1)   # (B, T, 512)
+        mlp = self.numerical_mlp
+        num = numerical_sequence.to(c_out.device).float()
+        n_out = Fn.SmallLinear.apply(num, mlp[0].weight, mlp[0].bias, True, 0.0, self.training)
+        n_out = Fn.SmallLinear.apply(n_out, mlp[2].weight, mlp[2].bias, False, 0.0, self.training)
+        lstm_out, _ = self.lstm(torch.cat((c_out, n_out), dim=2))
+        final_state = lstm_out[:, -1, :]
+        cls = self.classifier
+        hdn = Fn.SmallLinear.apply(final_state, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(hdn, cls[3].weight, cls[3].bias, False, 0.0, self.training)
+
+
+def get_model_seq(model_name, num_classes, device, seq_len=4, num_features=47):
+    """`get_model` of cnn+lstm/models.py:147-155 (same argument names). Ji3DCNN is outside SURVEY.md §8."""
+    if model_name == "cnn_lstm":
+        model = CnnLstm(num_classes, sequence_length=seq_len, numerical_feature_dim=num_features)
+    elif model_name == "3d_cnn":
+        raise ValueError("get_model: '3d_cnn' (Ji3DCNN) is not on the accelerated path (SURVEY.md §8 scope)")
+    else:
+        raise ValueError(f"Unknown model name: {model_name}")
+    return model.to(device)
+
+
 def get_model(model_name="quadtree", num_classes=8, device="cuda", print_num_params=True):
     """`get_model` of Quadtree_from scratch/models.py:309-325 (same argument names and printout)."""
     name = model_name.lower()

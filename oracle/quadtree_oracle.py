@@ -129,7 +129,30 @@ def make_params(kind: str, num_classes: int = 8, seed: int = 0, numerical_featur
         _linear(g, p, "classifier.0", din // 2, din)
         _linear(g, p, "classifier.3", num_classes, din // 2)
         return p
+    if kind == "cnn_lstm":  # cnn+lstm/models.py:14-57 (ResNet-18 children[:-1] as cnn_backbone.{0,1,4,5,6,7})
+        r = resnet18_params(g, prefix="")
+        p = {}
+        for k, v in r.items():
+            head, rest = k.split(".", 1)
+            if head in _SEQ_INDEX:
+                p[f"cnn_backbone.{_SEQ_INDEX[head]}.{rest}"] = v
+        _linear(g, p, "numerical_mlp.0", 128, numerical_feature_dim)
+        _linear(g, p, "numerical_mlp.2", 128, 128)
+        hid, nin0 = 256, 512 + 128
+        for layer, nin in ((0, nin0), (1, hid)):
+            bound = 1.0 / math.sqrt(hid)
+            p[f"lstm.weight_ih_l{layer}"] = (torch.rand(4 * hid, nin, generator=g) * 2 - 1) * bound
+            p[f"lstm.weight_hh_l{layer}"] = (torch.rand(4 * hid, hid, generator=g) * 2 - 1) * bound
+            p[f"lstm.bias_ih_l{layer}"] = (torch.rand(4 * hid, generator=g) * 2 - 1) * bound
+            p[f"lstm.bias_hh_l{layer}"] = (torch.rand(4 * hid, generator=g) * 2 - 1) * bound
+        _linear(g, p, "classifier.0", 128, hid)
+        _linear(g, p, "classifier.3", num_classes, 128)
+        return p
     raise ValueError(kind)
+
+
+# position of the ResNet-18 children inside `nn.Sequential(*list(resnet.children())[:-1])` (cnn+lstm/models.py:23)
+_SEQ_INDEX = {"conv1": 0, "bn1": 1, "layer1": 4, "layer2": 5, "layer3": 6, "layer4": 7}
 
 
 def synthetic_batch(batch: int, seed: int = 1234, image_size: int = 224, num_classes: int = 8, seq_len: int = 0,
@@ -369,7 +392,34 @@ def quadtree3d_forward(p: Params, clips, numerical_seq, training=True, mode="qua
     return F.linear(h, p["classifier.3.weight"], p["classifier.3.bias"])
 
 
+def cnn_lstm_forward(p: Params, image_sequence, numerical_sequence, training=True, dropout_rate=0.0, new_buffers=None):
+    """CnnLstm.forward — cnn+lstm/models.py:59-89: every frame through the (frozen, BatchNorm in train mode) ResNet-18
+    up to avgpool, per-step MLP on the pose vector, concat 640 -> 2-layer LSTM -> last step -> classifier."""
+    b, t, c, h, w = image_sequence.shape
+    pre = "cnn_backbone."
+    q = dict(p)  # torchvision-style aliases of the Sequential-indexed names, so the ResNet helpers apply
+    for name, idx in _SEQ_INDEX.items():
+        for k, v in p.items():
+            if k.startswith(f"{pre}{idx}."):
+                q[f"{pre}{name}.{k[len(pre) + len(str(idx)) + 1:]}"] = v
+    nb_alias: dict = {}
+    x = _stem(q, pre, image_sequence.reshape(b * t, c, h, w), training, nb_alias)
+    for li in (1, 2, 3, 4):
+        x = _layer(q, pre, li, x, training, nb_alias)
+    if new_buffers is not None:
+        for k, v in nb_alias.items():  # back to the module's own buffer names
+            head, rest = k[len(pre):].split(".", 1)
+            new_buffers[f"{pre}{_SEQ_INDEX[head]}.{rest}"] = v
+    c_out = F.adaptive_avg_pool2d(x, 1).flatten(1).view(b, t, -1)
+    n_out = F.linear(F.relu(F.linear(numerical_sequence, p["numerical_mlp.0.weight"], p["numerical_mlp.0.bias"])),
+                     p["numerical_mlp.2.weight"], p["numerical_mlp.2.bias"])
+    last = _lstm_last(p, torch.cat((c_out, n_out), dim=2), name="lstm")
+    hdn = _dropout(F.relu(F.linear(last, p["classifier.0.weight"], p["classifier.0.bias"])), p, training, dropout_rate)
+    return F.linear(hdn, p["classifier.3.weight"], p["classifier.3.bias"])
+
+
 FORWARDS = {
+    "cnn_lstm": cnn_lstm_forward,
     "quadtree": quadtree_forward,
     "attention_hierarchical": attention_hier_forward,
     "hierarchical_quadtree": hier_forward,

@@ -100,6 +100,9 @@ def run_case(case):
     elif kind == "quadtree3d":
         mod = load_ref("3dcnn/models.py", "ref_3d")
         model = mod.Quadtree3DCNN(num_classes=8, sequence_length=case["seq_len"], dropout_rate=0.0, mode=mode)
+    elif kind == "cnn_lstm":
+        mod = load_ref("cnn+lstm/models.py", "ref_cnnlstm")
+        model = mod.CnnLstm(num_classes=8, sequence_length=case["seq_len"], dropout_rate=0.0)
     else:
         raise ValueError(kind)
     p = O.make_params(kind, 8, seed=case["param_seed"], mode=mode)
@@ -107,7 +110,7 @@ def run_case(case):
     res = model.load_state_dict(sd, strict=False)
     own_missing = [k for k in res.missing_keys if not k.startswith(("features_extractor.", "global_processor."))]
     assert not own_missing and not res.unexpected_keys, (own_missing[:5], res.unexpected_keys[:5])
-    if kind == "quadtree3d":
+    if kind in ("quadtree3d", "cnn_lstm"):
         images, numerical, labels = O.synthetic_batch(batch, seed, seq_len=case["seq_len"], clip_size=case["clip"])
     else:
         images, numerical, labels = O.synthetic_batch(batch, seed)
@@ -156,12 +159,16 @@ CASES = [
      "param_seed": 6, "seq_len": 4, "clip": 32},
     {"name": "quadtree3d_image_only_b2", "kind": "quadtree3d", "mode": "quadtree_3d_image_only", "batch": 2, "seed": 12,
      "param_seed": 7, "seq_len": 4, "clip": 32},
+    {"name": "cnn_lstm_train_b2", "kind": "cnn_lstm", "batch": 2, "seed": 21, "param_seed": 8, "seq_len": 3, "clip": 64},
 ]
 
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         res = run_case(case)
         path = os.path.join(HERE, case["name"] + ".json")
         with open(path, "w") as f:

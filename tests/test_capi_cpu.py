@@ -52,3 +52,22 @@ def test_module_mirror_surface_and_no_cpu_fallback():
     frozen = M.get_model_resnet(8, "cpu", mode="image_only", print_num_params=False)
     assert not any(p.requires_grad for p in frozen.base_cnn.parameters())
     assert frozen.classifier[0].in_features == 5120
+
+
+def test_cnn_lstm_module_surface():
+    """CnnLstm mirrors cnn+lstm/models.py:14-57: same state_dict keys as the reference (= the oracle's parameter names,
+    which tests/golden/cnn_lstm_train_b2.json loaded into the unmodified reference), 12.68 M parameters of which
+    1.50 M train, CPU tensors are refused (no fallback path)."""
+    import pytest
+    import torch
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import models as M
+    m = M.CnnLstm(8, sequence_length=3)
+    p = O.make_params("cnn_lstm", 8, seed=1)
+    assert set(m.state_dict()) == set(p)
+    assert all(tuple(m.state_dict()[k].shape) == tuple(v.shape) for k, v in p.items())
+    assert sum(q.numel() for q in m.parameters() if q.requires_grad) == 1_502_472
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 3, 64, 64), torch.zeros(1, 3, 47))
+    with pytest.raises(ValueError):
+        M.get_model_seq("nope", 8, "cpu")

@@ -141,6 +141,25 @@ def test_quadtree3d(env, mode):
     assert float((feats - ref).abs().max()) <= 4e-2 * float(ref.abs().max()) + 1e-3
 
 
+def test_cnn_lstm(env):
+    """CnnLstm (cnn+lstm/models.py:14-89): frames through the frozen tensor-core ResNet-18 (BatchNorm in
+    train mode over B*T frames), per-step MLP, torch LSTM, classifier — logits and every trainable gradient vs oracle."""
+    O, M = env
+    p = O.make_params("cnn_lstm", 8, seed=8)
+    frames, numerical, labels = O.synthetic_batch(3, 21, seq_len=4, clip_size=64)
+    model = M.get_model_seq("cnn_lstm", 8, "cuda", seq_len=4)
+    model.dropout_rate = 0.0
+    model.lstm.dropout = 0.0
+    M.load_oracle_params(model, p)
+    model.train()
+    assert sum(q.numel() for q in model.parameters()) == 12_678_984
+    assert sum(q.numel() for q in model.parameters() if q.requires_grad) == 1_502_472  # SURVEY §8 a17
+    check_train_step(O, "cnn_lstm", model, p, (frames, numerical), labels, min_cos=0.9)
+    assert model.cnn_backbone[7][1].conv2.weight.grad is None  # frozen backbone
+    with pytest.raises(ValueError):
+        M.get_model_seq("3d_cnn", 8, "cuda")
+
+
 def test_maxpool3d_exact(env):
     import qtcnn_b200.capi as C
     n, d, h, w, c = 2, 4, 6, 10, 16

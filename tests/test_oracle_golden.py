@@ -31,7 +31,7 @@ def test_oracle_matches_reference_fixture(path):
     kind, mode = case["kind"], case.get("mode", "fusion")
     training = case.get("training", True)
     p = O.make_params(kind, 8, seed=case["param_seed"], mode=mode)
-    if kind == "quadtree3d":
+    if kind in ("quadtree3d", "cnn_lstm"):
         images, numerical, labels = O.synthetic_batch(case["batch"], case["seed"], seq_len=case["seq_len"],
                                                       clip_size=case["clip"])
     else:
