@@ -266,6 +266,8 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->pad_d != 0) return pl;
   if (d->groups != 1) return pl;
   if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
+  // the producers advance 16 virtual pixels with ONE row carry and ONE image carry: needs 16/(W+2) < H+1 (fails for 2x2 maps)
+  if (16 / (d->in_w + 2) >= d->in_h + 1) return pl;
   if (cin % 64 || nout % 32) return pl;
   if (flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32)) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
@@ -413,6 +415,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->groups != 1) return pl;
   if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
   if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
+  if (16 / (d->in_w + 2) >= d->in_h + 1) return pl;  // single-carry coordinate advance (see plan_conv3x3)
   if (d->in_c == 64 && d->out_c == 64) pl.cfg = 0;
   else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
   else return pl;
