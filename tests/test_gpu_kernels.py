@@ -498,3 +498,47 @@ def test_fused_stem_tail(C):
     report("fused stem tail dgamma", dgamma, gref.grad, 2e-2)
     report("fused stem tail dbeta", dbeta, bref.grad, 2e-2)
     report("fused stem tail dy", dy.permute(0, 3, 1, 2), yf.grad, 2e-2)
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w", [(3, 64, 64, 56, 56), (3, 128, 128, 28, 28), (5, 256, 256, 14, 14), (9, 512, 512, 7, 7),
+                                            (7, 512, 512, 2, 2), (2, 64, 64, 21, 37)])
+def test_conv3x3_writes_stay_in_bounds(C, n, cin, cout, h, w):
+    """Guard bands around every output of the slab / generic conv kernels (fprop with statistics, data gradient with and
+    without accumulation, weight gradient): nothing outside the tensor may change (compute-sanitizer is not available on
+    the pool, so out-of-range stores are caught this way)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    guard = 4096
+
+    def banded(shape, dtype, fill):
+        numel = math.prod(shape)
+        buf = torch.full((numel + 2 * guard,), fill, device="cuda", dtype=dtype)
+        return buf, buf[guard:guard + numel].view(*shape)
+
+    def bands_intact(buf, fill):
+        return bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all())
+
+    x = bf16(torch.randn(n, h, w, cin, device="cuda", generator=g))
+    dy = bf16(torch.randn(n, h, w, cout, device="cuda", generator=g))
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * cin)
+    wf = torch.empty(cout, 9, cin, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(cin, 9, cout, device="cuda", dtype=torch.bfloat16)
+    run(C, C.lib().qt_wpack_both(C.ptr(wt), C.ptr(wf), C.ptr(wd), cout, cin, 9, C.stream()), "wpack_both")
+    d = C.conv_desc(n, (1, h, w), cin, cout, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    ybuf, y = banded((n, h, w, cout), torch.bfloat16, 7.0)
+    rows = C.lib().qt_conv_stat_rows(d)
+    sbuf, st = banded((rows, 2, cout), torch.float32, 7.0)
+    run(C, C.lib().qt_conv_fprop(d, C.ptr(x), C.ptr(wf), C.ptr(y), None, C.ptr(st), C.QT_EPI_STATS, None, 0, C.stream()), "fprop")
+    assert bands_intact(ybuf, 7.0) and bands_intact(sbuf, 7.0)
+    assert not bool((y == 7.0).all()) and bool(torch.isfinite(y.float()).all())
+    dxbuf, dx = banded((n, h, w, cin), torch.bfloat16, 7.0)
+    for acc in (0, 1):
+        run(C, C.lib().qt_conv_dgrad(d, C.ptr(dy), C.ptr(wd), C.ptr(dx), acc, C.stream()), "dgrad")
+        assert bands_intact(dxbuf, 7.0)
+    ws_bytes = C.lib().qt_conv_wgrad_workspace_bytes(d)
+    wsbuf, ws = banded((max(ws_bytes, 16),), torch.uint8, 7)
+    dwbuf, dw = banded((cout, cin, 3, 3), torch.float32, 7.0)
+    run(C, C.lib().qt_conv_wgrad(d, C.ptr(x), C.ptr(dy), C.ptr(dw), 0, C.ptr(ws), ws_bytes, C.stream()), "wgrad")
+    assert bands_intact(dwbuf, 7.0) and bands_intact(wsbuf, 7)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    report(f"wgrad (banded) c{cin}->{cout} {h}x{w}", dw, ref, F32_REL_L2)
+    assert C.lib().qt_take_timeout_flag() == 0
