@@ -148,7 +148,8 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
                    qt_stream_t stream);
 /* Stem tail fused (bn1 -> relu -> maxpool 3x3/s2/p1, torchvision resnet.py:198-200): one pass forward; backward =
  * max-pool gather + ReLU mask recomputed from y + BatchNorm backward, never materialising the full-resolution
- * activated map or its gradient. */
+ * activated map or its gradient. The backward works on 2x2 pixel blocks and needs even h and w (returns an error
+ * otherwise; callers then use qt_maxpool2d_bwd + qt_bn_backward). */
 int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, int n, int h,
                            int w, int c, qt_stream_t stream);
 int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const float* scale, const float* shift,

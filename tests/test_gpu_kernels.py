@@ -542,3 +542,35 @@ def test_conv3x3_writes_stay_in_bounds(C, n, cin, cout, h, w):
     ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
     report(f"wgrad (banded) c{cin}->{cout} {h}x{w}", dw, ref, F32_REL_L2)
     assert C.lib().qt_take_timeout_flag() == 0
+
+
+def test_wpack_multi_matches_single_packs(C):
+    """One qt_wpack_multi launch over a mixed table (3x3, 1x1 / linear, 3x3x3, ragged channel counts, one item without the
+    data-gradient layout) produces exactly the bf16 layouts of the per-weight reference transforms."""
+    import ctypes
+    g = torch.Generator(device="cuda").manual_seed(31)
+    shapes = [(64, 64, 9), (128, 64, 1), (72, 40, 9), (256, 128, 9), (200, 136, 1), (32, 8, 27), (2688, 544, 1)]
+    items = (C.WpackItem * len(shapes))()
+    keep, first, max_taps = [], 0, 1
+    for i, (cout, cin, taps) in enumerate(shapes):
+        w = torch.randn(cout, cin, taps, device="cuda", generator=g)
+        wf = torch.zeros(cout, taps, cin, device="cuda", dtype=torch.bfloat16)
+        wd = torch.zeros(cin, taps, cout, device="cuda", dtype=torch.bfloat16) if i != 4 else None
+        keep.append((w, wf, wd))
+        it = items[i]
+        it.w, it.wf, it.wd = w.data_ptr(), wf.data_ptr(), (wd.data_ptr() if wd is not None else None)
+        it.cout, it.cin, it.taps = cout, cin, taps
+        nb = C.lib().qt_wpack_item_plan(ctypes.byref(it))
+        assert nb > 0
+        it.first_block = first
+        first += nb
+        max_taps = max(max_taps, taps)
+    table = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).cuda()
+    run(C, C.lib().qt_wpack_multi(C.ptr(table), len(shapes), first, max_taps, C.stream()), "wpack_multi")
+    for w, wf, wd in keep:
+        assert torch.equal(wf, bf16(w).permute(0, 2, 1).contiguous())
+        if wd is not None:
+            assert torch.equal(wd, bf16(w).permute(1, 2, 0).contiguous())
+    bad = C.WpackItem()
+    bad.cout, bad.cin, bad.taps = 8, 8, 99
+    assert C.lib().qt_wpack_item_plan(ctypes.byref(bad)) < 0
