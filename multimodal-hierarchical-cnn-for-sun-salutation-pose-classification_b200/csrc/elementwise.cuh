@@ -52,24 +52,30 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
 // Stem input packing: NCHW fp32 [N,3,H,W] -> zero-padded NHWC4 bf16 [N, H+7, W+8, 4]
 // (3 rows/cols of padding before the image so that every 7x7/s2 window starts 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
+// One block per padded row (grid.x = N * (H+7)): only 32-bit index arithmetic per pixel; reads are 128-byte coalesced
+// per channel plane, writes 8 bytes per pixel.
 __global__ void stem_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
                                        int H, int W) {
   const int Hp = H + 7, Wp = W + 8;
-  const long long total = static_cast<long long>(N) * Hp * Wp;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wp = i % Wp;
-    const int hp = (i / Wp) % Hp;
-    const int n = i / (static_cast<long long>(Wp) * Hp);
-    const int h = hp - 3, w = wp - 3;
+  const int row = blockIdx.x;            // n * Hp + hp
+  const int n = row / Hp, hp = row - n * Hp;
+  const int h = hp - 3;
+  const bool row_in = h >= 0 && h < H;
+  const float* src = x + (static_cast<long long>(n) * C * H + (row_in ? h : 0)) * W;
+  const long long plane = static_cast<long long>(H) * W;
+  __nv_bfloat16* dst = out + static_cast<long long>(row) * Wp * 4;
+  for (int wp = threadIdx.x; wp < Wp; wp += blockDim.x) {
+    const int w = wp - 3;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (h >= 0 && h < H && w >= 0 && w < W) {
-      for (int c = 0; c < C && c < 4; ++c) v[c] = x[((static_cast<long long>(n) * C + c) * H + h) * W + w];
+    if (row_in && w >= 0 && w < W) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) v[c] = __ldg(src + c * plane + w);
     }
     uint2 q;
     q.x = pack_bf16x2(v[0], v[1]);
     q.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(out + i * 4) = q;
+    *reinterpret_cast<uint2*>(dst + wp * 4) = q;
   }
 }
 

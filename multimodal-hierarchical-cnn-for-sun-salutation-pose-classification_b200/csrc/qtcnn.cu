@@ -497,8 +497,10 @@ int qt_take_timeout_flag(void) {
 // ---- layout / packing -----------------------------------------------------------------------------
 int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream) {
   if (c > 4) return fail("stem_pack_input: at most 4 channels");
-  const long long total = static_cast<long long>(n) * (h + 7) * (w + 8);
-  stem_pack_input_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(xp), n, c, h, w);
+  const long long rows = static_cast<long long>(n) * (h + 7);
+  if (rows > 0x7fffffffLL) return fail("stem_pack_input: too many rows");
+  const int block = (w + 8) > 128 ? 256 : ((w + 8) > 64 ? 128 : 64);
+  stem_pack_input_kernel<<<static_cast<unsigned>(rows), block, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(xp), n, c, h, w);
   return cuda_status("stem_pack_input");
 }
 int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {

@@ -242,6 +242,9 @@ def test_stem(C, n, h, w):
     ref = F.conv2d(xq, wq, None, stride=2, padding=3)
     xp = torch.empty(n, h + 7, w + 8, 4, device="cuda", dtype=torch.bfloat16)
     run(C, C.lib().qt_stem_pack_input(C.ptr(x), C.ptr(xp), n, 3, h, w, C.stream()), "stem_pack_input")
+    expect = torch.zeros(n, h + 7, w + 8, 4, device="cuda", dtype=torch.bfloat16)   # 3 rows / cols of zeros in front
+    expect[:, 3:3 + h, 3:3 + w, :3] = bf16(x).permute(0, 2, 3, 1)
+    assert torch.equal(xp, expect), "stem_pack_input layout"
     w8 = torch.empty(cout, 8, 32, device="cuda", dtype=torch.bfloat16)
     run(C, C.lib().qt_wpack_stem(C.ptr(wt), C.ptr(w8), cout, 3, 7, 7, C.stream()), "wpack_stem")
     y = torch.full((n, h // 2, w // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
