@@ -117,7 +117,8 @@ class _PackRegistry:
         self.generation = -1     # generation the registered weights were last packed at
 
     def add(self, w, e):
-        self.items.append((weakref.ref(w), e))
+        if not any(x[1] is e for x in self.items):  # an entry whose buffers were dropped and re-created is already listed
+            self.items.append((weakref.ref(w), e))
         e.registered = True
         self.table = None
 
