@@ -279,7 +279,12 @@ def run_ours(args):
                                  "ms_per_step": tms / nsteps, "step_share": (tms / nsteps) / (ms / args.steps)},
                     "per_family": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / nsteps,
                                        "launches_per_step": v["n"] / nsteps}
-                                   for k, v in gemm.items() if v["ms"] > 0}}
+                                   for k, v in gemm.items() if v["ms"] > 0},
+                    # streaming kernels: algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+                    "hbm_families": {k: {"GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "frac_of_hbm_peak": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                         "ms_per_step": v["ms"] / nsteps, "calls_per_step": v["n"] / nsteps}
+                                     for k, v in prof.items() if v.get("bytes", 0) > 0 and v["ms"] > 0},
+                    "hbm_peak_GBps": peaks["hbm_gbs"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -52,7 +52,8 @@ class _StemFn(torch.autograd.Function):
         dev = x.device
         xf = x.detach().float().contiguous()
         xp = torch.empty(n, h + 7, w + 8, 4, device=dev, dtype=BF16)
-        check(L().qt_stem_pack_input(ptr(xf), ptr(xp), n, 3, h, w, stream()), "stem_pack_input")
+        with ops.gemm_scope("stem_pack_input", 0.0, 4.0 * xf.numel() + 2.0 * xp.numel()):
+            check(L().qt_stem_pack_input(ptr(xf), ptr(xp), n, 3, h, w, stream()), "stem_pack_input")
         w8 = ops.packed_stem(conv_w)
         ho, wo = h // 2, w // 2
         y = torch.empty(n, ho, wo, cout, device=dev, dtype=BF16)
@@ -68,8 +69,9 @@ class _StemFn(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
         am = torch.empty(n, po, qo, cout, device=dev, dtype=torch.int8) if need_bwd else None
         # bn1 + relu + maxpool in one pass: the 112x112 activated map is never written
-        check(L().qt_bn_relu_maxpool_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(am), n, ho, wo, cout, stream()),
-              "bn_relu_maxpool_fwd")
+        with ops.gemm_scope("stem_tail_fwd", 0.0, 2.0 * y.numel() + 3.0 * out.numel()):  # y in; pooled out + int8 arg-max
+            check(L().qt_bn_relu_maxpool_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(am), n, ho, wo, cout, stream()),
+                  "bn_relu_maxpool_fwd")
         ops._count()
         if need_bwd:
             ctx.saved = (xp, y, am, st, conv_w, bn_w, bn_b)
@@ -91,9 +93,11 @@ class _StemFn(torch.autograd.Function):
             # passes over 2x2 pixel blocks; neither the activated 112x112 map nor its gradient is ever materialised
             wsb = L().qt_bn_workspace_bytes(cout)
             ws = ops.workspace(wsb, dev)
-            check(L().qt_bn_relu_maxpool_bwd(ptr(dout), ptr(am), ptr(y), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
-                                             ptr(bn_w.detach()), n, ho, wo, cout, ptr(dgamma), ptr(dbeta), 0 if ctx.training else 1,
-                                             ptr(dy), ptr(ws), wsb, stream()), "bn_relu_maxpool_bwd")
+            # two passes over (y, pooled gradient, arg-max plane) + one write of dy
+            with ops.gemm_scope("stem_tail_bwd", 0.0, 2.0 * (2.0 * y.numel() + 3.0 * dout.numel()) + 2.0 * dy.numel()):
+                check(L().qt_bn_relu_maxpool_bwd(ptr(dout), ptr(am), ptr(y), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
+                                                 ptr(bn_w.detach()), n, ho, wo, cout, ptr(dgamma), ptr(dbeta), 0 if ctx.training else 1,
+                                                 ptr(dy), ptr(ws), wsb, stream()), "bn_relu_maxpool_bwd")
             ops._count(3)
         else:
             da = torch.empty_like(y)

@@ -357,8 +357,10 @@ def bn_finalize(stats, count, bn, c, device, training=True) -> BNState:
 def bn_apply(y, st: BNState, out, residual=None, relu=True):
     c = y.shape[-1]
     m = y.numel() // c
-    check(L().qt_bn_apply(ptr(y), ptr(st.scale), ptr(st.shift), ptr(residual), ptr(out), m, c, 1 if relu else 0, stream()),
-          "bn_apply")
+    # algorithmic bytes: y in, (residual in,) out — bf16
+    with gemm_scope("bn_apply", 0.0, 2.0 * y.numel() * (3 if residual is not None else 2)):
+        check(L().qt_bn_apply(ptr(y), ptr(st.scale), ptr(st.shift), ptr(residual), ptr(out), m, c, 1 if relu else 0, stream()),
+              "bn_apply")
     _count()
     return out
 
@@ -370,9 +372,12 @@ def bn_backward(dout, act, y, st: BNState, gamma, dgamma, dbeta, dy, dz_out=None
     m = y.numel() // c
     ws = workspace(L().qt_bn_workspace_bytes(c), y.device, "bn")
     msc, msh = (ptr(st.scale), ptr(st.shift)) if (mask_from_y and act is None) else (None, None)
-    check(L().qt_bn_backward(ptr(dout), ptr(act), ptr(y), ptr(st.mean), ptr(st.invstd), ptr(gamma), msc, msh, m, c, ptr(dgamma),
-                             ptr(dbeta), 0, 1 if eval_mode else 0, ptr(dy), ptr(dz_out), ptr(ws), ws.numel(), stream()),
-          "bn_backward")
+    # algorithmic bytes of the two passes: reduce reads dout, y (, act); apply reads them again and writes dy (, dz)
+    a = 1 if act is not None else 0
+    with gemm_scope("bn_backward", 0.0, 2.0 * y.numel() * ((2 + a) + (2 + a) + 1 + (1 if dz_out is not None else 0))):
+        check(L().qt_bn_backward(ptr(dout), ptr(act), ptr(y), ptr(st.mean), ptr(st.invstd), ptr(gamma), msc, msh, m, c, ptr(dgamma),
+                                 ptr(dbeta), 0, 1 if eval_mode else 0, ptr(dy), ptr(dz_out), ptr(ws), ws.numel(), stream()),
+              "bn_backward")
     _count(4)
 
 
@@ -439,20 +444,26 @@ def profile_end():
     rec, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
-    for fam, flops, e0, e1 in rec:
-        d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "n": 0})
+    for fam, flops, nbytes, e0, e1 in rec:
+        d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += flops
+        d["bytes"] += nbytes
         d["n"] += 1
     return out
 
 
-class gemm_scope:
-    """`with gemm_scope(family, flops): <launch>` — a no-op unless profiling is on."""
-    __slots__ = ("fam", "flops", "e0")
+def profiling() -> bool:
+    return _prof is not None
 
-    def __init__(self, fam, flops):
-        self.fam, self.flops, self.e0 = fam, flops, None
+
+class gemm_scope:
+    """`with gemm_scope(family, flops[, nbytes]): <launch>` — a no-op unless profiling is on. Tensor-core families carry
+    their algorithmic FLOPs, streaming (HBM-bound) families their algorithmic bytes."""
+    __slots__ = ("fam", "flops", "nbytes", "e0")
+
+    def __init__(self, fam, flops, nbytes=0.0):
+        self.fam, self.flops, self.nbytes, self.e0 = fam, flops, nbytes, None
 
     def __enter__(self):
         if _prof is not None:
@@ -464,7 +475,7 @@ class gemm_scope:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _prof.append((self.fam, self.flops, self.e0, e1))
+            _prof.append((self.fam, self.flops, self.nbytes, self.e0, e1))
         return False
 
 
