@@ -71,3 +71,21 @@ def test_cnn_lstm_module_surface():
         m(torch.zeros(1, 3, 3, 64, 64), torch.zeros(1, 3, 47))
     with pytest.raises(ValueError):
         M.get_model_seq("nope", 8, "cpu")
+
+
+def test_ncu_summary_is_reproducible_from_the_committed_launch_list(tmp_path):
+    """profiles/ncu_gemm_summary.json (read by bench.py for roofline.traffic / tensor-pipe numbers) is exactly what
+    tools/ncu_summary.py derives from the committed ncu CSV of one training step."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "profiles", "r01_ncu_gemm_launches.csv")
+    out = tmp_path / "summary.json"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), src, str(out)], check=True, capture_output=True)
+    with open(out) as f, open(os.path.join(root, "profiles", "ncu_gemm_summary.json")) as g:
+        new, committed = json.load(f), json.load(g)
+    assert new == committed
+    assert committed["conv3x3_kernel"]["launches_per_step"] == 26 and committed["wgrad3x3_kernel"]["launches_per_step"] == 13
+    assert 0 < committed["flop_weighted_tensor_active_pct"] < 100
