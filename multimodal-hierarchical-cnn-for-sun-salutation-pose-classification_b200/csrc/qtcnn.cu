@@ -483,7 +483,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
 // ================================================================================================
 extern "C" {
 
-int qt_version(void) { return 101; }
+int qt_version(void) { return 102; }  // 102: qt_wpack_multi, fused stem-tail backward on 2x2 blocks
 void qt_set_conv3x3_enabled(int on) { g_use_conv3x3 = on != 0; }
 void qt_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 const char* qt_last_error(void) { return g_err; }
