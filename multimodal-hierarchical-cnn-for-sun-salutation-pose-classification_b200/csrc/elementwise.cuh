@@ -469,29 +469,26 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
       ms[e] = ymask ? msc[cg * 8 + e] : 0.f; mh[e] = ymask ? msh[cg * 8 + e] : 1.f;
     }
     const long long step = static_cast<long long>(gridDim.x) * lanes;
-    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += 2 * step) {
-      // two rows in flight per iteration (six independent 16-byte loads)
-      const long long r2 = r + step;
-      const bool has2 = r2 < M;
-      const uint4 qd = ld_nc16(dout + r * C + cg * 8), qv = ld_nc16(y + r * C + cg * 8);
-      uint4 qa = make_uint4(0, 0, 0, 0), qd2 = qa, qv2 = qa, qa2 = qa;
-      if (act) qa = ld_nc16(act + r * C + cg * 8);
-      if (has2) {
-        qd2 = ld_nc16(dout + r2 * C + cg * 8);
-        qv2 = ld_nc16(y + r2 * C + cg * 8);
-        if (act) qa2 = ld_nc16(act + r2 * C + cg * 8);
-      }
-      float d[8], a[8], v[8];
-      unpack8(qd, d); unpack8(qv, v); unpack8(qa, a);
+    constexpr int kRows = 4;  // rows in flight per iteration (up to 12 independent 16-byte loads)
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += kRows * step) {
+      uint4 qd[kRows], qv[kRows], qa[kRows];
+      bool has[kRows];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool off = act ? !(a[e] > 0.f) : !(fmaf(v[e], ms[e], mh[e]) > 0.f);
-        const float dz = off ? 0.f : d[e];
-        s1[e] += dz;
-        s2[e] += dz * (v[e] - mu[e]) * is[e];
+      for (int k = 0; k < kRows; ++k) {
+        const long long rk = r + k * step;
+        has[k] = rk < M;
+        qd[k] = qv[k] = qa[k] = make_uint4(0, 0, 0, 0);
+        if (has[k]) {
+          qd[k] = ld_nc16(dout + rk * C + cg * 8);
+          qv[k] = ld_nc16(y + rk * C + cg * 8);
+          if (act) qa[k] = ld_nc16(act + rk * C + cg * 8);
+        }
       }
-      if (has2) {
-        unpack8(qd2, d); unpack8(qv2, v); unpack8(qa2, a);
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        if (!has[k]) continue;
+        float d[8], a[8], v[8];
+        unpack8(qd[k], d); unpack8(qv[k], v); unpack8(qa[k], a);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const bool off = act ? !(a[e] > 0.f) : !(fmaf(v[e], ms[e], mh[e]) > 0.f);
