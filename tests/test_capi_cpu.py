@@ -89,3 +89,22 @@ def test_ncu_summary_is_reproducible_from_the_committed_launch_list(tmp_path):
     assert new == committed
     assert committed["conv3x3_kernel"]["launches_per_step"] == 26 and committed["wgrad3x3_kernel"]["launches_per_step"] == 13
     assert 0 < committed["flop_weighted_tensor_active_pct"] < 100
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port timed on the host cores) prints one JSON
+    line with the keys the driver reads; non-zero ranks print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-batch", "2"]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=root, env={**os.environ, "RANK": "0"}).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f32"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    silent = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=root, env={**os.environ, "RANK": "1"}).stdout.strip()
+    assert silent == ""
