@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 0) QT_TRACE_GT(8);
   const int Wp = p.W + 2, Hp = p.H + 1;  // one shared zero row between consecutive images
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) QT_TRACE_GT(9);
 
   if (warp >= 4 && warp < 8) {
     // ================================================================= producers
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     // cp.async completion is tracked by the mbarriers themselves (cp.async.mbarrier.arrive.noinc): producers run
     // ahead by the full depth of the rings and never block in wait_group; the issuers fence after their waits.
     bool first_tile = true;
+    QT_TRACE_DECL(tr_a_empty);
+    const long long tr_p0 = QT_TRACE_NOW();
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
     // kernel parameters used in the gather loop live in registers (the cp.async asm has a memory clobber, which would
     // otherwise make the compiler re-read them from the constant bank every iteration)
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       for (int c = 0; c < p.slabs; ++c) {
         {  // ---- A slab: rows j <-> virtual pixel q0 - (W+3) + j
           const int s = a_cnt % NSLAB;
-          if (a_cnt >= NSLAB) mbar_wait(&a_empty[s], ((a_cnt / NSLAB) - 1) & 1);
+          if (a_cnt >= NSLAB) QT_TRACE_WAIT(tr_a_empty, mbar_wait(&a_empty[s], ((a_cnt / NSLAB) - 1) & 1));
           const __nv_bfloat16* src_c = p.a + c * 64 + chunk * 8;
           // first row of this thread: virtual pixel v0 (shifted by one image so the decomposition is non-negative),
           // then advance 16 virtual pixels per iteration with carries instead of dividing per row
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       first_tile = false;
     }
     cp_async_wait<0>();  // nothing may be in flight when the CTA retires
+    if (warp == 4) { QT_TRACE_PUT(6, tr_a_empty); QT_TRACE_PUT(7, QT_TRACE_NOW() - tr_p0); }
   } else if (warp == 10) {
     // ================================================================= TMA producer for the weight tiles
     // box = [BN rows][64 K-elements] of the 2-D weight matrix [nout][9*cin], 128B-swizzled by the TMA unit —
@@ -240,24 +245,26 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t a_cnt = 0, b_cnt = 0, tile_it = 0;
       bool first_tile = true;
+      QT_TRACE_DECL(tr_acc_empty); QT_TRACE_DECL(tr_a_full); QT_TRACE_DECL(tr_b_full);
+      const long long tr_m0 = QT_TRACE_NOW();
       uint32_t tapoff[9];  // slab row of each filter tap relative to the tile's first pixel, in 16-byte descriptor units
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) tapoff[tp] = static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1)) * 8;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         const uint32_t ab = tile_it & 1;
-        if (tile_it >= 2) mbar_wait(&acc_empty[ab], ((tile_it >> 1) - 1) & 1);
+        if (tile_it >= 2) QT_TRACE_WAIT(tr_acc_empty, mbar_wait(&acc_empty[ab], ((tile_it >> 1) - 1) & 1));
         tc_fence_after();
         const uint32_t d_base = tbase + ab * (MT * BN);
         for (int c = 0; c < p.slabs; ++c) {
           const int sa = a_cnt % NSLAB;
-          mbar_wait(&a_full[sa], (a_cnt / NSLAB) & 1);
+          QT_TRACE_WAIT(tr_a_full, mbar_wait(&a_full[sa], (a_cnt / NSLAB) & 1));
           fence_proxy_async_smem();
           tc_fence_after();
           const uint32_t slab_lo = ((smem_u32(slab_base + sa * slab_bytes) >> 4) & 0x3FFFu) | a_lbo;
           if (p.b_resident && !first_tile) {
             // resident filter, already waited for and fenced on the first tile: nine taps back to back
             const uint32_t b0 = (((smem_u32(b_ring) >> 4) + c * 9 * (L::kBTile >> 4)) & 0x3FFFu) | b_lbo;
-            if (lane == 0) {
+            if (elect_one()) {
               const int u = warp - 8;
 #pragma unroll
               for (int tp = 0; tp < 9; ++tp) {
@@ -281,13 +288,13 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
                 mbar_wait(&b_full[sb], 0);
               } else {
                 sb = b_cnt % NB;
-                mbar_wait(&b_full[sb], (b_cnt / NB) & 1);
+                QT_TRACE_WAIT(tr_b_full, mbar_wait(&b_full[sb], (b_cnt / NB) & 1));
               }
               if (!p.b_tma) fence_proxy_async_smem();  // cp.async-written filter tile (TMA writes are async-proxy already)
               tc_fence_after();
               const uint32_t b_lo = ((smem_u32(b_ring + sb * L::kBTile) >> 4) & 0x3FFFu) | b_lbo;
               const uint32_t a_lo = slab_lo + (static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1)) + (warp - 8) * kBM) * 8;
-              if (lane == 0) {
+              if (elect_one()) {
                 const int u = warp - 8;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -301,19 +308,22 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
               if (!p.b_resident) ++b_cnt;
             }
           }
-          if (lane == 0) umma_commit(&a_empty[sa]);
+          if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();
           ++a_cnt;
         }
-        if (lane == 0) umma_commit(&acc_full[ab]);
+        if (elect_one()) umma_commit(&acc_full[ab]);
         __syncwarp();
         first_tile = false;
       }
+      if (warp == 8) { QT_TRACE_GT(10); QT_TRACE_PUT(0, tr_acc_empty); QT_TRACE_PUT(1, tr_a_full); QT_TRACE_PUT(2, tr_b_full); QT_TRACE_PUT(3, QT_TRACE_NOW() - tr_m0); }
     }
   } else {
     // ================================================================= epilogue (warps 0-3)
     const int flags = p.flags;
     uint32_t tile_it = 0;
+    QT_TRACE_DECL(tr_acc_full);
+    const long long tr_e0 = QT_TRACE_NOW();
     if (flags & EPI_STATS) {
       for (int i = threadIdx.x; i < p.num_n_tiles * 2 * BN; i += kProducerThreads) running[i] = 0.f;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BN;
       const uint32_t ab = tile_it & 1;
-      mbar_wait(&acc_full[ab], (tile_it >> 1) & 1);
+      QT_TRACE_WAIT(tr_acc_full, mbar_wait(&acc_full[ab], (tile_it >> 1) & 1));
       tc_fence_after();
       bool row_ok[MT];
       long long orow[MT];
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
       }
     }
+    if (warp == 0) { QT_TRACE_GT(11); QT_TRACE_PUT(4, tr_acc_full); QT_TRACE_PUT(5, QT_TRACE_NOW() - tr_e0); }
     if (flags & EPI_STATS) {
       // one deterministic partial row per CTA: [2][nout]
       for (int i = threadIdx.x; i < p.num_n_tiles * 2 * BN; i += kProducerThreads) {
@@ -511,6 +522,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc<TCOLS>(tmem_base);
+  if (warp == 8) QT_TRACE_GT(12);
 }
 
 }  // namespace qt

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2)
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
         const uint32_t b_lo = a_lo + (L::kABytes >> 4);
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (a_lo + k * 2);
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2)
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(accum_bar);
+      if (elect_one()) umma_commit(accum_bar);
       __syncwarp();
     }
   }
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2)
         tc_fence_after();
         const uint32_t a_lo = ((smem_u32(smem + s * L::kStageBytes) >> 4) & 0x3FFFu) | d_lbo;
         const uint32_t b_lo = a_lo + (L::kABytes >> 4);
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 16 pixels (two 8-row swizzle atoms) per MMA
             const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (a_lo + k * (2048 >> 4));
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2)
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(accum_bar);
+      if (elect_one()) umma_commit(accum_bar);
       __syncwarp();
     }
   }

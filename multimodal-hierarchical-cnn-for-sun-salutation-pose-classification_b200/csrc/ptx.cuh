@@ -13,6 +13,24 @@ namespace qt {
 // descriptor/phase bug ends the kernel with garbage instead of hanging the GPU.
 __device__ unsigned int g_timeout_flag = 0;
 
+// Developer build (-DQT_TRACE, tools/trace_conv.py): per-CTA cycle counters of the barrier waits inside the persistent
+// kernels. 16 slots per CTA; compiled out of the product library.
+#ifdef QT_TRACE
+__device__ long long g_trace[1024 * 16];
+#define QT_TRACE_DECL(name) long long name = 0
+#define QT_TRACE_WAIT(acc, stmt) do { const long long _t = clock64(); stmt; acc += clock64() - _t; } while (0)
+#define QT_TRACE_NOW() clock64()
+__device__ __forceinline__ long long qt_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define QT_TRACE_GT(slot) QT_TRACE_PUT(slot, qt_globaltimer())
+#define QT_TRACE_PUT(slot, v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) g_trace[blockIdx.x * 16 + (slot)] = (v); } while (0)
+#else
+#define QT_TRACE_DECL(name)
+#define QT_TRACE_WAIT(acc, stmt) stmt
+#define QT_TRACE_NOW() 0
+#define QT_TRACE_PUT(slot, v)
+#define QT_TRACE_GT(slot)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -494,6 +494,18 @@ int qt_take_timeout_flag(void) {
   return static_cast<int>(v);
 }
 
+#ifdef QT_TRACE
+/* developer build only (not declared in include/qtcnn.h): copies the per-CTA wait counters to the host and clears them */
+int qt_debug_read_trace(long long* host, int count) {
+  if (count > 1024 * 16) count = 1024 * 16;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * count);
+  static long long zeros[1024 * 16];
+  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+  return 0;
+}
+#endif
+
 // ---- layout / packing -----------------------------------------------------------------------------
 int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream) {
   if (c > 4) return fail("stem_pack_input: at most 4 channels");

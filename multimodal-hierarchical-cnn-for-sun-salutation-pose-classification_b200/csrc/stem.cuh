@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fprop_kernel(const __gri
       mbar_wait(&in_full[s], (it / kStemStages) & 1);
       tc_fence_after();
       const uint32_t st_lo = ((smem_u32(stages + static_cast<size_t>(s) * p.stage_bytes) >> 4) & 0x3FFFu) | a_lbo;
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll 1
         for (int q = 0; q < kStemRows; ++q) {
           const uint32_t d = tbase + ab * (kStemRows * BN) + q * BN;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kSWThreads, 1) stem_wgrad_kernel(const __grid_
       tc_fence_after();
       uint8_t* st = smem + s * stage_bytes;
       const uint32_t x_lo = ((smem_u32(st + kSWRows * p.dy_bytes) >> 4) & 0x3FFFu) | b_lbo;
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll 1
         for (int q = 0; q < kSWRows; ++q) {
           const uint32_t a_addr = smem_u32(st + q * p.dy_bytes);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kSWThreads, 1) stem_wgrad_kernel(const __grid_
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(done);
+    if (elect_one()) umma_commit(done);
     __syncwarp();
   }
 

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       const uint32_t a_lo = ((a_addr >> 4) & 0x3FFFu) | (((a_lbo_bytes >> 4) & 0x3FFFu) << 16);
       const uint32_t x_lo = ((smem_u32(st + dy_bytes) >> 4) & 0x3FFFu) | b_lbo;
       const uint32_t acc = it ? 1u : 0u;
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kW3KP / 16; ++ks) {
 #pragma unroll
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(done);
+    if (elect_one()) umma_commit(done);
     __syncwarp();
   }
 
