@@ -10,8 +10,9 @@ hot loop of the reference's `Quadtree_from scratch/Quadtree_train.py:60-66`.
           pose vectors / labels and the D2H read of the loss are inside the timed region
   roofline : dominant kernel family = tcgen05 implicit-GEMM convolutions (tensor bound); per-launch CUDA-event
           times in a second, event-instrumented pass; achieved = algorithmic conv FLOPs / summed launch time
-  cpu_baseline : the oracle port of the reference's CPU path (fp32, torch CPU) timed on this box's host cores
-`--impl reference` times that same CPU port as the reference arm.
+  cpu_baseline : the UNMODIFIED reference model (baseline/_ref, staged by __graft_entry__.build()) driven like its own
+          training loop on this box's host cores (fp32, torch CPU); the oracle port only if the staged files are missing
+`--impl reference` times that same CPU path as the reference arm.
 """
 import argparse
 import json
@@ -90,22 +91,75 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------- CPU arm
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # unmodified reference model files, copied there by __graft_entry__.build()
+
+
+def load_reference_module(subdir="Quadtree_from scratch"):
+    """The UNMODIFIED reference `models.py` (baseline/_ref/<subdir>/models.py), imported by path. The only shim is the
+    one SURVEY.md §8(c) describes: `torchvision.models.resnet18(weights=IMAGENET1K_V1)` cannot download offline, so the
+    `weights=` argument is dropped (random init; throughput does not depend on the weight values)."""
+    import importlib.util
+    path = os.path.join(REF_DIR, subdir, "models.py")
+    if not os.path.exists(path):
+        return None
+    import torchvision
+    if not getattr(torchvision.models.resnet18, "_offline_shim", False):
+        orig = torchvision.models.resnet18
+
+        def resnet18_offline(weights=None, **kw):
+            return orig(weights=None, **kw)
+        resnet18_offline._offline_shim = True
+        torchvision.models.resnet18 = resnet18_offline
+    spec = importlib.util.spec_from_file_location("reference_models_" + subdir.replace(" ", "_").replace("+", "_"), path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cpu_reference_rate(batch, steps, warmup):
-    """The reference's CPU path (oracle port: fp32 torch CPU, fwd + CE + bwd + Adam), images/s."""
+    """The reference's own CPU path, images/s: the unmodified `QuadtreeCNN` driven exactly like the hot loop of
+    `Quadtree_from scratch/Quadtree_train.py:43-66` (get_model, nn.CrossEntropyLoss, optim.Adam(lr, weight_decay), zero_grad /
+    forward / loss / backward / step, loss.item()), fp32, all host threads. Falls back to the oracle port only when
+    baseline/_ref is missing; returns which one ran."""
+    import contextlib
+    import io
     import torch
-    from oracle import quadtree_oracle as O
+    from qtcnn_b200.data import synthetic_batch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = O.make_params("quadtree", 8, seed=0)
-    images, numerical, labels = O.synthetic_batch(batch, 1234)
-    state = None
+    images, numerical, labels = synthetic_batch(batch, 1234)
+    ref = load_reference_module()
+    if ref is not None:
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref.get_model(num_classes=8, device=torch.device("cpu"), model_name="quadtree")
+        criterion = torch.nn.CrossEntropyLoss()
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)  # Quadtree_train.py:21-22,45
+        model.train()
+
+        def one():
+            optimizer.zero_grad()
+            loss = criterion(model(images, numerical), labels)
+            loss.backward()
+            optimizer.step()
+            return loss.item()
+        kind = "reference"
+    else:
+        from oracle import quadtree_oracle as O
+        p = O.make_params("quadtree", 8, seed=0)
+        box = {"state": None}
+
+        def one():
+            loss, box["state"] = O.train_step_cpu("quadtree", p, (images, numerical), labels, state=box["state"])
+            return float(loss)
+        kind = "port"
     for _ in range(warmup):
-        _, state = O.train_step_cpu("quadtree", p, (images, numerical), labels, state=state)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        _, state = O.train_step_cpu("quadtree", p, (images, numerical), labels, state=state)
+        one()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    return batch * steps / dt, dt / steps, torch.get_num_threads(), kind
 
 
 def run_reference(args):
@@ -113,13 +167,14 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    rate, spi, threads = cpu_reference_rate(args.cpu_batch, steps, warmup)
+    rate, spi, threads, kind = cpu_reference_rate(args.cpu_batch, steps, warmup)
+    what = "unmodified reference QuadtreeCNN + nn.CrossEntropyLoss + optim.Adam" if kind == "reference" else "oracle port (baseline/_ref missing)"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": spi * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"QuadtreeCNN level-1 fwd+bwd+Adam 224x224 batch {args.cpu_batch} on CPU (reference path, oracle port)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        "config": {"workload": f"QuadtreeCNN level-1 fwd+bwd+Adam 224x224 batch {args.cpu_batch} on CPU ({what})"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{steps} steps of batch {args.cpu_batch} after {warmup} warm-up"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -141,7 +196,7 @@ def run_ours(args):
         import datetime
         # a mismatched collective should end the run in minutes, not after NCCL's default 10-minute watchdog
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-    from oracle import quadtree_oracle as O  # synthetic-input recipe + cpu_baseline only
+    from qtcnn_b200 import data as D  # synthetic-input recipe (the product arm never imports oracle/)
     from qtcnn_b200 import models as M
     from qtcnn_b200 import ops, parallel
 
@@ -151,7 +206,7 @@ def run_ours(args):
     dp = parallel.DataParallelGrads(model) if world > 1 else None
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-4, fused=True)
-    images_h, numerical_h, labels_h = O.synthetic_batch(B, 1234 + rank)
+    images_h, numerical_h, labels_h = D.synthetic_batch(B, 1234 + rank)
     images_h, numerical_h, labels_h = images_h.pin_memory(), numerical_h.pin_memory(), labels_h.pin_memory()
     images, numerical, labels = images_h.to(dev), numerical_h.to(dev), labels_h.to(dev)
 
@@ -288,8 +343,8 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, spi, threads = cpu_reference_rate(args.cpu_batch, 4, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        rate, spi, threads, kind = cpu_reference_rate(args.cpu_batch, 4, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"4 steps of batch {args.cpu_batch} (fwd+bwd+Adam, fp32) after 1 warm-up, {spi:.2f} s/step"}
 
     if rank == 0:
@@ -315,7 +370,7 @@ def run_secondary(args):
     """Informational timings of BASELINE.json configs[1] (level-1+2 inference) and configs[3] (3-D model training)."""
     import torch
     import torch.nn.functional as F
-    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import data as O
     from qtcnn_b200 import models as M
     from qtcnn_b200 import ops
     dev = torch.device("cuda", 0)

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     // ahead by the full depth of the rings and never block in wait_group; the issuers fence after their waits.
     bool first_tile = true;
     QT_TRACE_DECL(tr_a_empty);
-    const long long tr_p0 = QT_TRACE_NOW();
+    QT_TRACE_T0(tr_p0);
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
     // kernel parameters used in the gather loop live in registers (the cp.async asm has a memory clobber, which would
     // otherwise make the compiler re-read them from the constant bank every iteration)
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
       uint32_t a_cnt = 0, b_cnt = 0, tile_it = 0;
       bool first_tile = true;
       QT_TRACE_DECL(tr_acc_empty); QT_TRACE_DECL(tr_a_full); QT_TRACE_DECL(tr_b_full);
-      const long long tr_m0 = QT_TRACE_NOW();
+      QT_TRACE_T0(tr_m0);
       uint32_t tapoff[9];  // slab row of each filter tap relative to the tile's first pixel, in 16-byte descriptor units
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) tapoff[tp] = static_cast<uint32_t>((p.off_h[tp] + 1) * Wp + (p.off_w[tp] + 1)) * 8;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     const int flags = p.flags;
     uint32_t tile_it = 0;
     QT_TRACE_DECL(tr_acc_full);
-    const long long tr_e0 = QT_TRACE_NOW();
+    QT_TRACE_T0(tr_e0);
     if (flags & EPI_STATS) {
       for (int i = threadIdx.x; i < p.num_n_tiles * 2 * BN; i += kProducerThreads) running[i] = 0.f;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");

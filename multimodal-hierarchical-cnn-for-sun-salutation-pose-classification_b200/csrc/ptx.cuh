@@ -20,6 +20,7 @@ __device__ long long g_trace[1024 * 16];
 #define QT_TRACE_DECL(name) long long name = 0
 #define QT_TRACE_WAIT(acc, stmt) do { const long long _t = clock64(); stmt; acc += clock64() - _t; } while (0)
 #define QT_TRACE_NOW() clock64()
+#define QT_TRACE_T0(name) const long long name = clock64()
 __device__ __forceinline__ long long qt_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define QT_TRACE_GT(slot) QT_TRACE_PUT(slot, qt_globaltimer())
 #define QT_TRACE_PUT(slot, v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) g_trace[blockIdx.x * 16 + (slot)] = (v); } while (0)
@@ -27,6 +28,7 @@ __device__ __forceinline__ long long qt_globaltimer() { long long t; asm volatil
 #define QT_TRACE_DECL(name)
 #define QT_TRACE_WAIT(acc, stmt) stmt
 #define QT_TRACE_NOW() 0
+#define QT_TRACE_T0(name)
 #define QT_TRACE_PUT(slot, v)
 #define QT_TRACE_GT(slot)
 #endif
@@ -72,7 +74,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait (~0.5 s at 2 GHz). Returns false and raises g_timeout_flag on time-out.
+// Bounded wait (~0.5 s at 2 GHz). A time-out means a pipeline bug or a pre-empted GPU: the flag is raised for
+// qt_take_timeout_flag() and the kernel TRAPS, so the launch fails with a CUDA error instead of continuing on
+// unsynchronised shared memory / TMEM and returning garbage with rc = 0.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
@@ -80,7 +84,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (((++spins) & 0x3ff) == 0 && (clock64() - t0) > 1000000000LL) {
       atomicExch(&g_timeout_flag, 1u);
-      return false;
+      __threadfence_system();
+      __trap();
     }
   }
   return true;

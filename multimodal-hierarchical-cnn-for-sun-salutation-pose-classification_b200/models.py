@@ -15,6 +15,7 @@ There is no cuDNN / ATen fallback for the hot ops: CPU tensors or a missing libq
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Optional
 
 import torch
@@ -263,19 +264,28 @@ class FusedAvgPool(nn.AdaptiveAvgPool2d):
         return _GlobalAvgPoolFn.apply(x)
 
 
+_quiet_pretrained = [os.environ.get("QTCNN_QUIET_PRETRAINED", "") == "1"]  # benches / tests use random init on purpose
+
+
 def make_resnet18() -> nn.Module:
     """torchvision's ResNet-18 module tree (what the reference builds with `models.resnet18(...)`) with fused
     blocks. ImageNet weights are used only if the checkpoint is already in the local torch hub cache — the
     reference's `weights=IMAGENET1K_V1` needs a download that is impossible offline; otherwise torchvision's
     default initialisation (resnet.py:208-213) applies and real weights arrive through `load_state_dict`."""
     net = torchvision.models.resnet18(weights=None)
-    try:
+    ckpt = None
+    try:  # only the cache probe is best effort; a checkpoint that exists but does not load is an error
         url = torchvision.models.ResNet18_Weights.IMAGENET1K_V1.url
         ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(url))
-        if os.path.exists(ckpt):
-            net.load_state_dict(torch.load(ckpt, map_location="cpu"))
-    except Exception:  # pragma: no cover - cache probing is best effort
-        pass
+    except Exception:  # pragma: no cover
+        ckpt = None
+    if ckpt is not None and os.path.exists(ckpt):
+        net.load_state_dict(torch.load(ckpt, map_location="cpu"))
+    elif not _quiet_pretrained[0]:
+        warnings.warn("ResNet-18 IMAGENET1K_V1 weights are not in the torch hub cache (no network): the backbone starts from "
+                      "torchvision's random initialisation. The reference always starts from the pretrained checkpoint — load "
+                      "real weights with load_state_dict before training, especially for the frozen-backbone variants.",
+                      RuntimeWarning, stacklevel=3)
     for m in net.modules():
         if type(m) is BasicBlock:
             m.__class__ = FusedBasicBlock
@@ -759,33 +769,3 @@ def get_model_3d(num_classes, device, numerical_feature_dim=47, mode="fusion", s
         num_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
         print(f"Number of trainable parameters: {num_params / 1e6:.2f} Million (Mode: {mode})")
     return model
-
-
-def load_oracle_params(model: nn.Module, params: dict) -> None:
-    """Load a parameter dict in the oracle's naming (oracle/quadtree_oracle.make_params). For QuadtreeCNN /
-    StandardResNetCNN the names ARE the reference's state_dict keys; the hierarchical classes hold the ResNet
-    only through features_extractor / global_processor, so `base_cnn.*` names are mapped onto those."""
-    own = model.state_dict()
-    alias = {}
-    if not hasattr(model, "base_cnn") and any(k.startswith("base_cnn.") for k in params):
-        fe = {"conv1": "features_extractor.0", "bn1": "features_extractor.1", "layer1": "features_extractor.4",
-              "layer2": "features_extractor.5", "layer3": "global_processor.0", "layer4": "global_processor.1"}
-        for k, v in params.items():
-            if k.startswith("base_cnn."):
-                rest = k[len("base_cnn."):]
-                head = rest.split(".")[0]
-                if head in fe:
-                    alias[fe[head] + rest[len(head):]] = v
-            else:
-                alias[k] = v
-    else:
-        alias = params
-    sd = {k: v for k, v in alias.items() if k in own}
-    res = model.load_state_dict(sd, strict=False)
-    missing = [k for k in res.missing_keys if not k.startswith(("features_extractor.", "global_processor."))]
-    if missing and hasattr(model, "base_cnn"):
-        raise RuntimeError(f"load_oracle_params: missing {missing[:5]}")
-    if not hasattr(model, "base_cnn"):
-        really_missing = [k for k in own if k not in sd]
-        if really_missing:
-            raise RuntimeError(f"load_oracle_params: missing {really_missing[:5]}")

@@ -403,9 +403,21 @@ def as_nchw_view(buf: torch.Tensor) -> torch.Tensor:
     return buf.permute(0, 3, 1, 2)
 
 
+_rank_salt = [None]
+
+
 def new_seed() -> int:
-    """Dropout seed drawn from torch's CPU generator (so torch.manual_seed makes runs reproducible)."""
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
+    """Dropout seed drawn from torch's CPU generator (so torch.manual_seed makes runs reproducible; a host-side draw,
+    no device synchronisation), mixed with the data-parallel rank so that ranks seeded identically still apply
+    independent masks to their shards (as per-device Philox streams do under DDP)."""
+    base = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if _rank_salt[0] is None:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            _rank_salt[0] = (dist.get_rank() * 0x9E3779B97F4A7C15) & ((1 << 62) - 1)
+        else:
+            return base  # not cached: a process group may still be created later
+    return base ^ _rank_salt[0]
 
 
 # ------------------------------------------------------------------------------------------------- param grads
@@ -422,9 +434,12 @@ def unregister_grad_view(p):
 
 
 def grad_out(p: torch.Tensor) -> torch.Tensor:
-    """Destination tensor for the gradient of parameter `p` (a bucket view under data parallelism)."""
+    """Destination tensor for the gradient of parameter `p`: the bucket view under data parallelism, but only while
+    `p.grad` is None (autograd then adopts the view as `p.grad`). When a gradient already exists (zero_grad with
+    set_to_none=False, micro-batch accumulation) a fresh tensor is returned, so autograd's `p.grad += new` adds into
+    the view instead of a kernel overwriting it and the sum doubling."""
     v = _grad_views.get(p)
-    if v is not None:
+    if v is not None and getattr(p, "grad", None) is None:
         return v
     return torch.empty_like(p, memory_format=torch.contiguous_format)
 

@@ -51,12 +51,15 @@ class DataParallelGrads:
             tensors = list({id(t): t for t in list(model.parameters()) + list(model.buffers())}.values())
             for t in tensors:
                 dist.broadcast(t.data, src=0)
+            # the broadcast wrote through .data (no _version bump): drop bf16 GEMM copies packed before wrapping
+            ops.invalidate_packed_weights()
         self.buckets: List[_Bucket] = []
         self.bucket_of: Dict[torch.nn.Parameter, _Bucket] = {}
         self._order: List[torch.nn.Parameter] = []   # production order observed during the first backward
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.collectives_last_step = 0
         self.avg = dist.get_backend() == "nccl"  # gloo has no AVG
+        self._sync = True
 
     # ------------------------------------------------------------------------------------------
     def _build_buckets(self):
@@ -77,15 +80,35 @@ class DataParallelGrads:
                 self.bucket_of[p] = b
                 ops.register_grad_view(p, b.views[p])
 
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only accumulate into `p.grad` (the
+        bucket views); the all-reduce is issued by the first backward outside it, as with DDP.no_sync()."""
+        dp = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                self_inner.prev, dp._sync = dp._sync, False
+
+            def __exit__(self_inner, *exc):
+                dp._sync = self_inner.prev
+                return False
+        return _NoSync()
+
     def _hook(self, p):
         b = self.bucket_of.get(p)
         if b is None:  # first step: learn which parameters receive gradients and in which order
-            self._order.append(p)
+            if not any(q is p for q in self._order):
+                self._order.append(p)
             return
         v = b.views[p]
         if p.grad.data_ptr() != v.data_ptr():  # autograd cloned instead of adopting our view
             v.copy_(p.grad)
             p.grad = v
+        if not self._sync:
+            return
+        if b.pending == 0:
+            raise RuntimeError("DataParallelGrads: a second backward reached an already reduced bucket before finish(); "
+                               "wrap all but the last micro-batch backward in `with dp.no_sync():`")
         b.pending -= 1
         if b.pending == 0:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)

@@ -92,8 +92,8 @@ def test_ncu_summary_is_reproducible_from_the_committed_launch_list(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the reference's CPU path = the oracle port timed on the host cores) prints one JSON
-    line with the keys the driver reads; non-zero ranks print nothing."""
+    """`bench.py --impl reference` (the reference's CPU path: the unmodified reference model from baseline/_ref when staged,
+    else the oracle port) prints one JSON line with the keys the driver reads; non-zero ranks print nothing."""
     import json
     import os
     import subprocess
@@ -104,7 +104,8 @@ def test_bench_reference_arm_contract():
     line = json.loads(out[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f32"
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(root, "baseline", "_ref", "Quadtree_from scratch", "models.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     silent = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=root, env={**os.environ, "RANK": "1"}).stdout.strip()
     assert silent == ""

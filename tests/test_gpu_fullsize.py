@@ -1,8 +1,8 @@
 """BASELINE.json's full configuration (QuadtreeCNN, 224x224, batch 256) through size-independent properties and one
 full-size comparison with the oracle (evaluated in fp32 on the GPU; its pin to the reference is the CPU golden test):
 
-* a train step at batch 256 matches the oracle within the stated tolerance (logits <= 3e-2 * max|logit|, loss <= 2e-2,
-  gradient cosine >= min(0.97, torch-bf16-autocast cosine - 0.05) on the large tensors, BatchNorm running statistics <= 2e-2 relative);
+* a train step at batch 256 matches the oracle within the stated tolerance (logits <= 3e-2 * max|logit|, loss <= 2e-3,
+  gradient cosine >= torch-bf16-autocast cosine - 0.02 and rel_L2 <= 1.25 x autocast's on every parameter (tests/parity.py), BatchNorm running statistics <= 2e-2 relative);
 * the step is bitwise reproducible (fixed-order reductions everywhere: two runs give identical logits and gradients);
 * eval-mode forward is equivariant under a permutation of the batch, bit for bit (no cross-sample coupling, no
   position-dependent accumulation order).
@@ -10,6 +10,9 @@ full-size comparison with the oracle (evaluated in fp32 on the GPU; its pin to t
 import pytest
 import torch
 import torch.nn.functional as F
+
+import parity
+from oracle.loading import load_oracle_params
 
 pytestmark = pytest.mark.gpu
 B = 256
@@ -30,7 +33,7 @@ def setup():
 
 def make_model(M, p, train):
     model = M.QuadtreeCNN(num_classes=8, dropout_rate=0.0)
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     return model.cuda().train(train)
 
 
@@ -56,18 +59,14 @@ def test_full_size_train_step_vs_oracle(setup):
         _, _, ac_g, _ = O.loss_and_grads("quadtree", pg, (images, numerical), labels, training=True)
     model = make_model(M, p, True)
     logits, loss, grads = train_step(model, images, numerical, labels)
-    lmax = float(ref_logits.abs().max())
-    assert float((logits - ref_logits).abs().max()) <= 3e-2 * lmax + 1e-3
-    assert abs(float(loss) - float(ref_loss)) <= 2e-2
-    seen = 0
+    parity.assert_logits_loss(logits, loss, ref_logits, ref_loss)
+    seen, report = 0, []
     for name, g in grads.items():
         if name.startswith(("features_extractor.", "global_processor.")) or name not in ref_g:
             continue
-        if g.numel() >= 4096:
-            c, c_ac = cos(g, ref_g[name]), cos(ac_g[name], ref_g[name])
-            assert c >= min(0.97, c_ac - 0.05), (name, c, c_ac)
-            seen += 1
-    assert seen >= 20
+        seen += parity.assert_grad(name, g, ref_g[name], ac_g[name], report)
+    parity.print_worst(report)
+    assert seen >= 60
     sd = model.state_dict()
     for name, ref in ref_nb.items():
         if name.endswith("running_mean") or name.endswith("running_var"):

@@ -1,9 +1,12 @@
 """Parity of the remaining drop-in classes against the oracle (evaluated in fp32 on the GPU):
 AttentionHierarchicalCNN / HierarchicalQuadtreeCNN (level-1 + level-2 quadtree), StandardResNetCNN (frozen) and
-Quadtree3DCNN (Conv3d stack, both modes). Tolerances as in test_gpu_model.py."""
+Quadtree3DCNN (Conv3d stack, both modes). Tolerances: the SURVEY §8(d) contract in tests/parity.py (autocast-relative)."""
 import pytest
 import torch
 import torch.nn.functional as F
+
+import parity
+from oracle.loading import load_oracle_params
 
 pytestmark = pytest.mark.gpu
 
@@ -39,20 +42,14 @@ def oracle_names(model, name):
     return name
 
 
-def check_train_step(O, kind, model, p, inputs, labels, min_cos=0.9, **kw):
-    ref_logits, ref_loss, ref_g, _ = O.loss_and_grads(kind, to_cuda(p), tuple(t.cuda() for t in inputs), labels.cuda(),
-                                                     training=True, **kw)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        _, _, ac_g, _ = O.loss_and_grads(kind, to_cuda(p), tuple(t.cuda() for t in inputs), labels.cuda(), training=True, **kw)
+def check_train_step(O, kind, model, p, inputs, labels, **kw):
+    (ref_logits, ref_loss, ref_g, _), (_, _, ac_g, _) = parity.oracle_fp32_and_autocast(O, kind, p, inputs, labels, **kw)
     logits = model(*(t.cuda() for t in inputs))
     loss = F.cross_entropy(logits, labels.cuda())
     loss.backward()
-    lmax = float(ref_logits.abs().max())
-    lerr = float((logits.detach() - ref_logits).abs().max())
-    print(f"{kind}: logits err {lerr:.3e} / max {lmax:.3f}; loss {float(loss.detach()):.5f} vs {float(ref_loss):.5f}")
-    assert lerr <= 4e-2 * lmax + 1e-3
-    assert abs(float(loss.detach()) - float(ref_loss)) <= 3e-2
-    checked = 0
+    print(f"{kind}: loss {float(loss.detach()):.5f} vs {float(ref_loss):.5f}")
+    parity.assert_logits_loss(logits, loss.detach(), ref_logits, ref_loss)
+    checked, report = 0, []
     seen = set()
     for name, prm in model.named_parameters():
         if id(prm) in seen or not prm.requires_grad:
@@ -63,11 +60,8 @@ def check_train_step(O, kind, model, p, inputs, labels, min_cos=0.9, **kw):
             assert prm.grad is None, f"{name} received a gradient the oracle does not produce"
             continue
         assert prm.grad is not None, f"no gradient for {name}"
-        c_o, c_a = cos(prm.grad, ref_g[on]), cos(ac_g[on], ref_g[on])
-        if float(ref_g[on].abs().max()) < 1e-6:  # conv bias before train-mode BN: true gradient is 0
-            continue
-        assert c_o >= min(min_cos, c_a - 0.06), (name, c_o, c_a)
-        checked += 1
+        checked += parity.assert_grad(name, prm.grad, ref_g[on], ac_g[on], report)
+    parity.print_worst(report)
     assert checked > 5
     return logits
 
@@ -77,7 +71,7 @@ def test_attention_hierarchical_train_and_eval(env):
     p = O.make_params("attention_hierarchical", 8, seed=1)
     images, numerical, labels = O.synthetic_batch(8, 99)
     model = M.AttentionHierarchicalCNN(num_classes=8, dropout_rate=0.0)
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     model = model.cuda().train()
     assert len(model.state_dict()) == len([k for k in model.state_dict()])
     check_train_step(O, "attention_hierarchical", model, p, (images, numerical), labels)
@@ -86,7 +80,7 @@ def test_attention_hierarchical_train_and_eval(env):
     with torch.no_grad():
         out = model(images.cuda(), numerical.cuda())
         ref = O.attention_hier_forward(sd, images.cuda(), numerical.cuda(), training=False)
-    assert float((out - ref).abs().max()) <= 4e-2 * float(ref.abs().max())
+    assert float((out - ref).abs().max()) <= parity.LOGIT_TOL * float(ref.abs().max())
 
 
 def test_hierarchical_quadtree_train(env):
@@ -95,7 +89,7 @@ def test_hierarchical_quadtree_train(env):
     images, numerical, labels = O.synthetic_batch(8, 5)
     model = M.get_model("hierarchical_quadtree", 8, "cuda", print_num_params=False)
     model.dropout_rate = 0.0
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     model.train()
     assert sum(q.numel() for q in model.parameters()) == 13_641_480  # SURVEY §0.2 [probe]
     check_train_step(O, "hierarchical_quadtree", model, p, (images, numerical), labels)
@@ -107,19 +101,19 @@ def test_standard_resnet_frozen(env):
     images, numerical, labels = O.synthetic_batch(8, 55)
     model = M.get_model_resnet(8, "cuda", mode="standard_resnet_only", print_num_params=False)
     model.dropout_rate = 0.0
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     model.train()
-    ref_logits, ref_loss, ref_g, _ = O.loss_and_grads("standard_resnet", to_cuda(p), (images.cuda(), numerical.cuda()),
-                                                     labels.cuda(), training=True)
+    (ref_logits, ref_loss, ref_g, _), (_, _, ac_g, _) = parity.oracle_fp32_and_autocast(O, "standard_resnet", p, (images, numerical), labels)
     logits = model(images.cuda(), None)
-    F.cross_entropy(logits, labels.cuda()).backward()
-    assert float((logits.detach() - ref_logits).abs().max()) <= 4e-2 * float(ref_logits.abs().max()) + 1e-3
+    loss = F.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    parity.assert_logits_loss(logits, loss.detach(), ref_logits, ref_loss)
     named = dict(model.named_parameters())
     assert named["base_cnn.layer4.1.conv2.weight"].grad is None
-    for n in ("classifier.0.weight", "classifier.3.weight", "classifier.0.bias"):
-        # B=8, near-zero hidden pre-activations: a handful of ReLU mask flips from the bf16 backbone move this cosine by
-        # +-0.01 between equally exact conv routings (0.966 / 0.980 measured), hence 0.95
-        assert cos(named[n].grad, ref_g[n]) > 0.95, n
+    report = []
+    for n in ("classifier.0.weight", "classifier.3.weight", "classifier.0.bias", "classifier.3.bias"):
+        parity.assert_grad(n, named[n].grad, ref_g[n], ac_g[n], report)
+    parity.print_worst(report)
 
 
 @pytest.mark.parametrize("mode", ["quadtree_3d_fusion", "quadtree_3d_image_only"])
@@ -128,17 +122,17 @@ def test_quadtree3d(env, mode):
     p = O.make_params("quadtree3d", 8, seed=6, mode=mode)
     clips, numerical, labels = O.synthetic_batch(4, 11, seq_len=4, clip_size=32)
     model = M.Quadtree3DCNN(num_classes=8, sequence_length=4, dropout_rate=0.0, mode=mode)
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     model = model.cuda().train()
     assert sum(q.numel() for q in M.Quadtree3DCNN(8).parameters()) == 9_992_024  # SURVEY §8a14 [probe] (fusion)
-    check_train_step(O, "quadtree3d", model, p, (clips, numerical), labels, min_cos=0.85, mode=mode)
+    check_train_step(O, "quadtree3d", model, p, (clips, numerical), labels, mode=mode)
     # the conv stack alone (north-star: Conv3d forward/backward of the 3-D model)
     with torch.no_grad():
         model.eval()
         feats = model.conv_stack(clips.cuda())
         sd = model.state_dict()
         ref = O.quadtree3d_conv_stack({k: v for k, v in sd.items()}, clips.cuda(), training=False)
-    assert float((feats - ref).abs().max()) <= 4e-2 * float(ref.abs().max()) + 1e-3
+    assert float((feats - ref).abs().max()) <= parity.LOGIT_TOL * float(ref.abs().max()) + 1e-3
 
 
 def test_cnn_lstm(env):
@@ -150,11 +144,11 @@ def test_cnn_lstm(env):
     model = M.get_model_seq("cnn_lstm", 8, "cuda", seq_len=4)
     model.dropout_rate = 0.0
     model.lstm.dropout = 0.0
-    M.load_oracle_params(model, p)
+    load_oracle_params(model, p)
     model.train()
     assert sum(q.numel() for q in model.parameters()) == 12_678_984
     assert sum(q.numel() for q in model.parameters() if q.requires_grad) == 1_502_472
-    check_train_step(O, "cnn_lstm", model, p, (frames, numerical), labels, min_cos=0.9)
+    check_train_step(O, "cnn_lstm", model, p, (frames, numerical), labels)
     assert model.cnn_backbone[7][1].conv2.weight.grad is None  # frozen backbone
     with pytest.raises(ValueError):
         M.get_model_seq("3d_cnn", 8, "cuda")

@@ -51,8 +51,46 @@ def _worker(rank, world, port, q):
                 ok = ok and torch.allclose(ref, s, atol=1e-6)
             in_views = all(p.grad.data_ptr() == dp.bucket_of[p].views[p].data_ptr() for p in dp.bucket_of) if step > 0 else True
             results.append((ok, in_views, len(dp.buckets), dp.collectives_last_step))
-        q.put((rank, results, w0.tolist(), unused.weight.grad is None, ops.grad_out(model[0].weight).data_ptr() ==
-               dp.bucket_of[model[0].weight].views[model[0].weight].data_ptr()))
+        view_ptr = dp.bucket_of[model[0].weight].views[model[0].weight].data_ptr()
+        # (advisor finding, round 1) the view is handed out only while p.grad is None; with a live gradient a fresh tensor
+        # is returned so that autograd's accumulation adds into the view instead of a kernel overwriting it
+        live_is_fresh = ops.grad_out(model[0].weight).data_ptr() != view_ptr
+        model[0].weight.grad = None
+        none_is_view = ops.grad_out(model[0].weight).data_ptr() == view_ptr
+        # zero_grad(set_to_none=False): gradients stay allocated (the views) and must not double
+        x = torch.randn(4, 6, generator=torch.Generator().manual_seed(77 + rank))
+        used = [p for n, p in model.named_parameters() if not n.startswith("unused")]
+        for p in model.parameters():
+            p.grad = None
+        model[2](model[1](model[0](x))).square().mean().backward()
+        dp.finish()
+        first = [p.grad.detach().clone() for p in used]
+        for p in used:
+            p.grad.zero_()
+        model[2](model[1](model[0](x))).square().mean().backward()
+        dp.finish()
+        keep_ok = all(torch.allclose(a, p.grad, atol=1e-7) for a, p in zip(first, used))
+        # micro-batch accumulation: no_sync() for all but the last backward
+        for p in used:
+            p.grad.zero_()
+        with dp.no_sync():
+            (0.5 * model[2](model[1](model[0](x))).square().mean()).backward()
+        (0.5 * model[2](model[1](model[0](x))).square().mean()).backward()
+        dp.finish()
+        accum_ok = all(torch.allclose(a, p.grad, atol=1e-6) for a, p in zip(first, used))
+        # a second synchronising backward before finish() must raise instead of silently corrupting the buckets
+        for p in used:
+            p.grad.zero_()
+        model[2](model[1](model[0](x))).square().mean().backward()
+        try:
+            model[2](model[1](model[0](x))).square().mean().backward()
+            raised = False
+        except RuntimeError:
+            raised = True
+        for b in dp.buckets:  # drain the collectives the first backward issued
+            if b.work is not None:
+                b.work.wait()
+        q.put((rank, results, w0.tolist(), unused.weight.grad is None, live_is_fresh and none_is_view, keep_ok, accum_ok, raised))
     finally:
         dist.destroy_process_group()
 
@@ -71,8 +109,11 @@ def test_bucketed_allreduce_world2():
         assert p.exitcode == 0
     outs.sort()
     assert outs[0][2] == outs[1][2], "parameters must be broadcast from rank 0"
-    for rank, results, _, unused_none, view_ok in outs:
+    for rank, results, _, unused_none, view_ok, keep_ok, accum_ok, raised in outs:
         assert unused_none and view_ok
+        assert keep_ok, "zero_grad(set_to_none=False) changed the synchronised gradient"
+        assert accum_ok, "no_sync() accumulation differs from the single-backward gradient"
+        assert raised, "a second synchronising backward before finish() must raise"
         for ok, in_views, nb, ncoll in results:
             assert ok and in_views
         assert results[-1][2] >= 2 and results[-1][3] == results[-1][2]  # several buckets, one collective each
