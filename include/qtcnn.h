@@ -66,6 +66,16 @@ void qt_set_tuning(int key, int value);
 /* images.to(device) feeding base_cnn.conv1 (QS/Quadtree_train.py:61, QS/models.py:222):
  * NCHW fp32 [n,3,h,w] -> zero-padded NHWC4 bf16 [n,h+7,w+8,4]. */
 int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream);
+/* The same packing from fp32 / bf16 / uint8 NCHW input. uint8 = decoded pixels: transforms.ToTensor + Normalize
+ * (QS/dataloader.py:35-36) is applied on the device as v * scale[c] + shift[c] (scale = 1/(255 std), shift = -mean/std),
+ * so one byte per value crosses PCIe instead of four. scale/shift may be NULL for the float types. */
+#define QT_DTYPE_F32 0
+#define QT_DTYPE_BF16 1
+#define QT_DTYPE_U8 2
+int qt_stem_pack_input_ex(const void* x, int dtype, const float* scale, const float* shift, void* xp, int n, int c, int h, int w,
+                          qt_stream_t stream);
+int qt_nchw_to_nhwc_bf16_ex(const void* x, int dtype, const float* scale, const float* shift, void* out, int n, int c, long long hw,
+                            int c_pad, qt_stream_t stream);
 int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream);
 int qt_nhwc_bf16_to_nchw_f32(const void* x, float* out, int n, int c, long long hw, int c_pad, qt_stream_t stream);
 /* fp32 parameter [cout][cin][taps] -> bf16 GEMM operands (forward [cout][taps][cin], dgrad [cin][taps][cout]). */
@@ -203,6 +213,64 @@ int qt_relu_dropout(float* h, void* h16, long long n, float drop_p, unsigned lon
                     qt_stream_t stream);
 int qt_relu_dropout_bwd(const float* dout, const float* act, float* dz, void* dz16, long long n, float drop_p,
                         unsigned long long seed, int relu, qt_stream_t stream);
+
+
+/* ---- loss and fused classifier tail (QS/Quadtree_train.py:44,64; QS/models.py:268-271,303) -------------------------- */
+/* nn.CrossEntropyLoss() (mean reduction, int64 class labels) and, when dlogits != NULL, its gradient
+ * (softmax - onehot) * grad_scale * (*upstream) in the same pass (grad_scale = 1/b for the mean; upstream: device scalar,
+ * the gradient arriving at the loss, NULL = 1). loss_rows [b] and the zero-initialised device word `counter` (reset by
+ * the kernel) implement a fixed-order mean. nc <= 32. */
+int qt_cross_entropy(const float* logits, long long ld, const long long* labels, int b, int nc, float grad_scale,
+                     const float* upstream, float* loss_rows, float* loss_mean, float* dlogits, unsigned int* counter,
+                     qt_stream_t stream);
+/* Everything behind the classifier.0 GEMM in one launch: h [b][nhid] fp32 pre-activation -> ReLU + Dropout (h updated
+ * in place, optional bf16 copy h16) -> classifier.3 -> logits [b][nc]; with labels also the cross-entropy loss. */
+int qt_head_tail_fwd(float* h, void* h16, int nhid, const float* w3, const float* b3, int nc, const long long* labels, int b,
+                     float drop_p, unsigned long long seed, float* logits, float* loss_rows, float* loss_mean,
+                     unsigned int* counter, qt_stream_t stream);
+/* Backward of the tail: with labels dlogits = (softmax(logits) - onehot) * grad_scale * (*upstream) is produced (upstream:
+ * device scalar, NULL = 1), without labels it is read; dh16 [b][nhid] bf16 = (dlogits . w3) through the ReLU / dropout gate
+ * recorded in act (= h after qt_head_tail_fwd). */
+int qt_head_tail_bwd(const float* act, int nhid, const float* w3, int nc, const float* logits, const long long* labels,
+                     float grad_scale, const float* upstream, float drop_p, unsigned long long seed, float* dlogits, void* dh16,
+                     int b, qt_stream_t stream);
+
+/* ---- optimizer: optim.Adam(params, lr, weight_decay) of the scripts (QS/Quadtree_train.py:45) + clip_grad_norm_
+ * (3dcnn/train_3D_Quadtree_cnn_model.py:123), every parameter in one launch -------------------------------------------- */
+typedef struct qt_adam_group {
+  float step_size;    /* lr / (1 - beta1^t) */
+  float beta1, beta2;
+  float eps;
+  float weight_decay; /* L2, added to the gradient (torch.optim.Adam, not AdamW) */
+  float inv_bc2_sqrt; /* 1 / sqrt(1 - beta2^t) */
+} qt_adam_group;
+typedef struct qt_adam_item {
+  float* p;       /* fp32 parameter, updated in place */
+  const float* g; /* gradient */
+  float* m;       /* exp_avg */
+  float* v;       /* exp_avg_sq */
+  void* wf;       /* optional bf16 GEMM copy [cout][taps][cin] refreshed by the same pass (NULL: plain tensor) */
+  void* wd;       /* optional bf16 copy [cin][taps][cout] */
+  long long n;
+  int cout, cin, taps;
+  int co_tile, ci_tiles, first_block; /* co_tile / ci_tiles filled by qt_adam_item_plan, first_block by the caller */
+  int group, pad;
+} qt_adam_item;
+/* returns the item's block count (or -1); first_block = running sum of the counts, table copied to device memory */
+int qt_adam_item_plan(qt_adam_item* item);
+/* clip_coef: device scalar multiplied into every gradient (from qt_grad_clip_coef), or NULL */
+int qt_adam_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, const qt_adam_group* groups, int ngroups,
+                  const float* clip_coef, qt_stream_t stream);
+typedef struct qt_norm_item {
+  const float* g;
+  long long n;
+  int first_block, pad;
+} qt_norm_item;
+int qt_grad_norm_blocks(long long n);
+/* total_norm = ||all gradients||_2 (fixed-order reduction), coef = min(1, max_norm / (total_norm + 1e-6));
+ * partial: fp32 scratch [total_blocks]. */
+int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float* partial, float* total_norm,
+                      float* coef, qt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ QT_EPI_BIAS = 1
 QT_EPI_RELU = 2
 QT_EPI_STATS = 4
 QT_EPI_OUT_F32 = 16
+QT_DTYPE_F32, QT_DTYPE_BF16, QT_DTYPE_U8 = 0, 1, 2
 
 
 class ConvDesc(ctypes.Structure):
@@ -37,6 +38,24 @@ class ConvDesc(ctypes.Structure):
         ("x_group_off", c_longlong * 4),
         ("y_group_off", c_longlong * 4),
     ]
+
+
+class AdamGroup(ctypes.Structure):
+    """Mirror of `qt_adam_group`."""
+    _fields_ = [("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float),
+                ("inv_bc2_sqrt", c_float)]
+
+
+class AdamItem(ctypes.Structure):
+    """Mirror of `qt_adam_item`."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("wf", c_void_p), ("wd", c_void_p),
+                ("n", c_longlong), ("cout", c_int), ("cin", c_int), ("taps", c_int),
+                ("co_tile", c_int), ("ci_tiles", c_int), ("first_block", c_int), ("group", c_int), ("pad", c_int)]
+
+
+class NormItem(ctypes.Structure):
+    """Mirror of `qt_norm_item`."""
+    _fields_ = [("g", c_void_p), ("n", c_longlong), ("first_block", c_int), ("pad", c_int)]
 
 
 class WpackItem(ctypes.Structure):
@@ -84,6 +103,18 @@ _SIGNATURES = {
     "qt_set_conv3x3_enabled": (None, [c_int]),
     "qt_set_tuning": (None, [c_int, c_int]),
     "qt_stem_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_stem_pack_input_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_nchw_to_nhwc_bf16_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "qt_cross_entropy": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
+    "qt_head_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_ulonglong, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qt_head_tail_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_float, c_ulonglong, c_void_p,
+                                 c_void_p, c_int, c_void_p]),
+    "qt_adam_item_plan": (c_int, [ctypes.POINTER(AdamItem)]),
+    "qt_adam_multi": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdamGroup), c_int, c_void_p, c_void_p]),
+    "qt_grad_norm_blocks": (c_int, [c_longlong]),
+    "qt_grad_clip_coef": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qt_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_wpack_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

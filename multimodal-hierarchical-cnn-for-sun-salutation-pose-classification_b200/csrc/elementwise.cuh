@@ -54,23 +54,42 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
 // ---------------------------------------------------------------------------------------------
 // One block per padded row (grid.x = N * (H+7)): only 32-bit index arithmetic per pixel; reads are 128-byte coalesced
 // per channel plane, writes 8 bytes per pixel.
-__global__ void stem_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
-                                       int H, int W) {
+// TIn = float (normalised fp32, what `images.to(device)` delivers), __nv_bfloat16, or uint8_t (decoded pixels: the
+// ToTensor + Normalize of dataloader.py:35-36 is applied here as v * scale[c] + shift[c], scale = 1/(255 std), shift = -mean/std,
+// so only one byte per value crosses PCIe).
+template <typename TIn>
+__device__ __forceinline__ float stem_in(const TIn* p, float sc, float sh);
+template <>
+__device__ __forceinline__ float stem_in<float>(const float* p, float, float) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float stem_in<__nv_bfloat16>(const __nv_bfloat16* p, float, float) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float stem_in<uint8_t>(const uint8_t* p, float sc, float sh) { return fmaf(static_cast<float>(__ldg(p)), sc, sh); }
+
+template <typename TIn>
+__global__ void stem_pack_input_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
+                                       int H, int W, const float* __restrict__ scale, const float* __restrict__ shift) {
   const int Hp = H + 7, Wp = W + 8;
   const int row = blockIdx.x;            // n * Hp + hp
   const int n = row / Hp, hp = row - n * Hp;
   const int h = hp - 3;
   const bool row_in = h >= 0 && h < H;
-  const float* src = x + (static_cast<long long>(n) * C * H + (row_in ? h : 0)) * W;
+  const TIn* src = x + (static_cast<long long>(n) * C * H + (row_in ? h : 0)) * W;
   const long long plane = static_cast<long long>(H) * W;
   __nv_bfloat16* dst = out + static_cast<long long>(row) * Wp * 4;
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (scale) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) { sc[c] = scale[c]; sh[c] = shift[c]; }
+  }
   for (int wp = threadIdx.x; wp < Wp; wp += blockDim.x) {
     const int w = wp - 3;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (row_in && w >= 0 && w < W) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c < C) v[c] = __ldg(src + c * plane + w);
+        if (c < C) v[c] = stem_in<TIn>(src + c * plane + w, sc[c], sh[c]);
     }
     uint2 q;
     q.x = pack_bf16x2(v[0], v[1]);
@@ -80,15 +99,18 @@ __global__ void stem_pack_input_kernel(const float* __restrict__ x, __nv_bfloat1
 }
 
 // NCHW fp32 -> NHWC bf16 with channel padding to Cp (generic; used by the 3-D stack and tests).
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N,
-                                             int C, long long HW, int Cp) {
+template <typename TIn>
+__global__ void nchw_to_nhwc_bf16_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long long HW,
+                                         int Cp, const float* __restrict__ scale, const float* __restrict__ shift) {
   const long long total = static_cast<long long>(N) * HW * Cp;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = i % Cp;
     const long long p = (i / Cp) % HW;
     const long long n = i / (static_cast<long long>(Cp) * HW);
-    out[i] = __float2bfloat16_rn(c < C ? x[(n * C + c) * HW + p] : 0.f);
+    float v = 0.f;
+    if (c < C) v = stem_in<TIn>(x + (n * C + c) * HW + p, scale ? scale[c] : 1.f, scale ? shift[c] : 0.f);
+    out[i] = __float2bfloat16_rn(v);
   }
 }
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N,
@@ -923,9 +945,10 @@ stem_bn_pool_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dpool, const sig
 //   l4   : [B][GH*GW][Cg] bf16, layer4 output
 //   feat : [B][ldf] bf16, columns [0,Cg) = mean over GH*GW, then per quadrant (TL,TR,BL,BR)
 //          Cq*PH*PW values in NCHW flatten order c*(PH*PW) + ph*PW + pw, MaxPool2d(2,2) floor mode.
-// One thread per (b, quadrant, channel) / (b, global channel); loads are coalesced across channels.
+// Generic-shape fallback: one thread per (b, quadrant, channel) / (b, global channel). The shapes of the reference
+// (7x7x128 quadrants, 7x7x512 global map, 16-byte aligned feature rows) take the vectorised kernels below.
 // ---------------------------------------------------------------------------------------------
-__global__ void quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ l4,
+__global__ void quadtree_pool_fwd_generic_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ l4,
                                          __nv_bfloat16* __restrict__ feat, int B, int QH, int QW, int Cq, int GHW,
                                          int Cg, int ldf) {
   const int PH = QH / 2, PW = QW / 2;
@@ -962,7 +985,7 @@ __global__ void quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q, co
 // Backward (scatter-free broadcast): every quadrant-conv output element looks up whether it is the
 // (first) arg-max of its pooling window and whether its ReLU was active; every layer4 element
 // receives dfeat/GHW.  dfeat: [B][ldf] bf16.
-__global__ void quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat, const __nv_bfloat16* __restrict__ q,
+__global__ void quadtree_pool_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dfeat, const __nv_bfloat16* __restrict__ q,
                                          __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dl4, int B,
                                          int QH, int QW, int Cq, int GHW, int Cg, int ldf) {
   const int PH = QH / 2, PW = QW / 2;
@@ -999,6 +1022,145 @@ __global__ void quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat
       const int c = j % Cg;
       const int b = j / (static_cast<long long>(Cg) * GHW);
       dl4[j] = __float2bfloat16_rn(__bfloat162float(dfeat[static_cast<long long>(b) * ldf + c]) / GHW);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quadtree stage, vectorised (the kernel `north_star` describes): one CTA per (image, part), part = quadrant 0..3 or
+// the global branch. Every global access is a 128-bit load/store on a 16-byte chunk of 8 channels, consecutive lanes
+// on consecutive chunks (256 / 1024 contiguous bytes per pixel).
+//   quadrant part : the QHxQWxCq tile (12.5 KB at 7x7x128) is staged in shared memory with coalesced 16-byte loads;
+//                   thread t then produces the 8 consecutive outputs 8t..8t+7 of the NCHW-flatten order
+//                   c*(PH*PW) + ph*PW + pw (the shared-memory read IS the transpose) and writes them with one 16-byte
+//                   store, so the 2304-byte quadrant slice of the feature row leaves as full lines.
+//   global part   : lane = 8 chunks x 4 pixel phases; each lane adds its pixels (p = phase, phase+4, ...) in fp32 and
+//                   the four phases are combined with two warp shuffles (fixed order: deterministic).
+// Requirements (checked by the host wrapper, else the generic kernels run): Cq % 8 == 0, Cg % 64 == 0, ldf % 8 == 0,
+// (Cq*PH*PW) % 8 == 0, the quadrant tile fits in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQtThreads = 256;
+
+__global__ void __launch_bounds__(kQtThreads) quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q,
+                                                                       const __nv_bfloat16* __restrict__ l4,
+                                                                       __nv_bfloat16* __restrict__ feat, int B, int QH, int QW,
+                                                                       int Cq, int GHW, int Cg, int ldf) {
+  extern __shared__ __align__(16) uint8_t qt_smem[];
+  const int b = blockIdx.x, part = blockIdx.y;
+  const int PH = QH / 2, PW = QW / 2;
+  if (part < 4) {
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qt_smem);  // [QH*QW][Cq]
+    const int n16 = QH * QW * Cq / 8;
+    const uint4* src = reinterpret_cast<const uint4*>(q + (static_cast<long long>(part) * B + b) * QH * QW * Cq);
+    for (int i = threadIdx.x; i < n16; i += kQtThreads) reinterpret_cast<uint4*>(tile)[i] = ld_nc16(src + i);
+    __syncthreads();
+    const int PP = PH * PW;
+    const int nout8 = Cq * PP / 8;
+    __nv_bfloat16* dst = feat + static_cast<long long>(b) * ldf + Cg + static_cast<long long>(part) * Cq * PP;
+    for (int t = threadIdx.x; t < nout8; t += kQtThreads) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float m2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int o = 8 * t + j + e;
+          const int c = o / PP, r = o - c * PP;
+          const int ph = r / PW, pw = r - ph * PW;
+          const __nv_bfloat16* win = tile + ((2 * ph) * QW + 2 * pw) * Cq + c;
+          // max of bf16 values is exact in any order; same operands as MaxPool2d(2,2) floor mode
+          m2[e] = fmaxf(fmaxf(__bfloat162float(win[0]), __bfloat162float(win[Cq])),
+                        fmaxf(__bfloat162float(win[QW * Cq]), __bfloat162float(win[QW * Cq + Cq])));
+        }
+        pk[j >> 1] = pack_bf16x2(m2[0], m2[1]);
+      }
+      reinterpret_cast<uint4*>(dst)[t] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int phase = lane >> 3;
+    const float inv = 1.0f / static_cast<float>(GHW);
+    const __nv_bfloat16* src = l4 + static_cast<long long>(b) * GHW * Cg;
+    for (int c0 = warp * 64; c0 < Cg; c0 += (kQtThreads / 32) * 64) {
+      const int c = c0 + (lane & 7) * 8;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = phase; p < GHW; p += 4) {
+        float f[8];
+        unpack8(ld_nc16(src + static_cast<long long>(p) * Cg + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        acc[e] *= inv;
+      }
+      if (phase == 0) *reinterpret_cast<uint4*>(feat + static_cast<long long>(b) * ldf + c) = pack8(acc);
+    }
+  }
+}
+
+// Backward, scatter-free: the quadrant part re-derives the (first) arg-max of every 2x2 window from q, masks by the
+// fused ReLU (max > 0) and routes the gradient of output c*(PH*PW)+ph*PW+pw to that pixel, writing all four pixels of
+// the window (and the row / column the floor-mode pool dropped) as 16-byte chunks; the global part broadcasts dfeat/GHW.
+__global__ void __launch_bounds__(kQtThreads) quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat,
+                                                                       const __nv_bfloat16* __restrict__ q,
+                                                                       __nv_bfloat16* __restrict__ dq,
+                                                                       __nv_bfloat16* __restrict__ dl4, int B, int QH, int QW,
+                                                                       int Cq, int GHW, int Cg, int ldf) {
+  extern __shared__ __align__(16) uint8_t qt_smem[];
+  const int b = blockIdx.x, part = blockIdx.y;
+  const int PH = QH / 2, PW = QW / 2, PP = PH * PW;
+  if (part < 4) {
+    __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(qt_smem);  // this quadrant's slice of the feature-row gradient
+    const uint4* gsrc = reinterpret_cast<const uint4*>(dfeat + static_cast<long long>(b) * ldf + Cg + static_cast<long long>(part) * Cq * PP);
+    for (int i = threadIdx.x; i < Cq * PP / 8; i += kQtThreads) reinterpret_cast<uint4*>(gs)[i] = ld_nc16(gsrc + i);
+    __syncthreads();
+    const long long base = (static_cast<long long>(part) * B + b) * QH * QW * Cq;
+    const int nch = Cq / 8;
+    for (int i = threadIdx.x; i < PP * nch; i += kQtThreads) {
+      const int ch = i % nch, win = i / nch;
+      const int ph = win / PW, pw = win - ph * PW;
+      const long long o00 = base + (static_cast<long long>(2 * ph) * QW + 2 * pw) * Cq + ch * 8;
+      const long long offs[4] = {o00, o00 + Cq, o00 + static_cast<long long>(QW) * Cq, o00 + static_cast<long long>(QW) * Cq + Cq};
+      float v[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) unpack8(ld_nc16(q + offs[k]), v[k]);
+      float out[4][8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int am = 0;
+        float m = v[0][e];
+        if (v[1][e] > m) { m = v[1][e]; am = 1; }
+        if (v[2][e] > m) { m = v[2][e]; am = 2; }
+        if (v[3][e] > m) { m = v[3][e]; am = 3; }
+        const float g = (m > 0.f) ? __bfloat162float(gs[(ch * 8 + e) * PP + win]) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k][e] = (k == am) ? g : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dq + offs[k]) = pack8(out[k]);
+    }
+    // pixels outside every pooling window (odd QH / QW: last row / column) receive no gradient
+    if ((QH & 1) || (QW & 1)) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < QH * QW * nch; i += kQtThreads) {
+        const int ch = i % nch, pix = i / nch;
+        const int h = pix / QW, w = pix - h * QW;
+        if (h >= 2 * PH || w >= 2 * PW) *reinterpret_cast<uint4*>(dq + base + static_cast<long long>(pix) * Cq + ch * 8) = z;
+      }
+    }
+  } else {
+    const int nch = Cg / 8;
+    const float inv_n = static_cast<float>(GHW);
+    for (int i = threadIdx.x; i < GHW * nch; i += kQtThreads) {
+      const int ch = i % nch, p = i / nch;
+      float f[8];
+      unpack8(ld_nc16(dfeat + static_cast<long long>(b) * ldf + ch * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] / inv_n;
+      *reinterpret_cast<uint4*>(dl4 + (static_cast<long long>(b) * GHW + p) * Cg + ch * 8) = pack8(f);
     }
   }
 }

@@ -11,6 +11,8 @@
 #include "conv3x3.cuh"
 #include "stem.cuh"
 #include "wgrad3x3.cuh"
+#include "head.cuh"
+#include "optim.cuh"
 
 using namespace qt;
 
@@ -483,7 +485,7 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
 // ================================================================================================
 extern "C" {
 
-int qt_version(void) { return 102; }  // 102: qt_wpack_multi, fused stem-tail backward on 2x2 blocks
+int qt_version(void) { return 200; }  // 200: round 2 (loss / head tail / Adam / uint8 input / vectorised quadtree stage)
 void qt_set_conv3x3_enabled(int on) { g_use_conv3x3 = on != 0; }
 void qt_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 const char* qt_last_error(void) { return g_err; }
@@ -507,18 +509,42 @@ int qt_debug_read_trace(long long* host, int count) {
 #endif
 
 // ---- layout / packing -----------------------------------------------------------------------------
-int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream) {
+int qt_stem_pack_input_ex(const void* x, int dtype, const float* scale, const float* shift, void* xp, int n, int c, int h, int w,
+                          qt_stream_t stream) {
   if (c > 4) return fail("stem_pack_input: at most 4 channels");
   const long long rows = static_cast<long long>(n) * (h + 7);
   if (rows > 0x7fffffffLL) return fail("stem_pack_input: too many rows");
+  if ((scale == nullptr) != (shift == nullptr)) return fail("stem_pack_input: scale and shift come together");
+  if (dtype == QT_DTYPE_U8 && !scale) return fail("stem_pack_input: uint8 input needs per-channel scale / shift");
   const int block = (w + 8) > 128 ? 256 : ((w + 8) > 64 ? 128 : 64);
-  stem_pack_input_kernel<<<static_cast<unsigned>(rows), block, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(xp), n, c, h, w);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(xp);
+  const unsigned grid = static_cast<unsigned>(rows);
+  if (dtype == QT_DTYPE_F32) stem_pack_input_kernel<float><<<grid, block, 0, S(stream)>>>(static_cast<const float*>(x), o, n, c, h, w, scale, shift);
+  else if (dtype == QT_DTYPE_BF16)
+    stem_pack_input_kernel<__nv_bfloat16><<<grid, block, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), o, n, c, h, w, scale, shift);
+  else if (dtype == QT_DTYPE_U8) stem_pack_input_kernel<uint8_t><<<grid, block, 0, S(stream)>>>(static_cast<const uint8_t*>(x), o, n, c, h, w, scale, shift);
+  else return fail("stem_pack_input: unknown dtype %d", dtype);
   return cuda_status("stem_pack_input");
 }
-int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {
+int qt_stem_pack_input(const float* x, void* xp, int n, int c, int h, int w, qt_stream_t stream) {
+  return qt_stem_pack_input_ex(x, QT_DTYPE_F32, nullptr, nullptr, xp, n, c, h, w, stream);
+}
+int qt_nchw_to_nhwc_bf16_ex(const void* x, int dtype, const float* scale, const float* shift, void* out, int n, int c, long long hw,
+                            int c_pad, qt_stream_t stream) {
   const long long total = static_cast<long long>(n) * hw * c_pad;
-  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n, c, hw, c_pad);
-  return cuda_status("nchw_f32_to_nhwc_bf16");
+  if ((scale == nullptr) != (shift == nullptr)) return fail("nchw_to_nhwc: scale and shift come together");
+  if (dtype == QT_DTYPE_U8 && !scale) return fail("nchw_to_nhwc: uint8 input needs per-channel scale / shift");
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  const int grid = grid_for(total, 256, 1 << 20);
+  if (dtype == QT_DTYPE_F32) nchw_to_nhwc_bf16_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(x), o, n, c, hw, c_pad, scale, shift);
+  else if (dtype == QT_DTYPE_BF16)
+    nchw_to_nhwc_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), o, n, c, hw, c_pad, scale, shift);
+  else if (dtype == QT_DTYPE_U8) nchw_to_nhwc_bf16_kernel<uint8_t><<<grid, 256, 0, S(stream)>>>(static_cast<const uint8_t*>(x), o, n, c, hw, c_pad, scale, shift);
+  else return fail("nchw_to_nhwc: unknown dtype %d", dtype);
+  return cuda_status("nchw_to_nhwc_bf16");
+}
+int qt_nchw_f32_to_nhwc_bf16(const float* x, void* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {
+  return qt_nchw_to_nhwc_bf16_ex(x, QT_DTYPE_F32, nullptr, nullptr, out, n, c, hw, c_pad, stream);
 }
 int qt_nhwc_bf16_to_nchw_f32(const void* x, float* out, int n, int c, long long hw, int c_pad, qt_stream_t stream) {
   const long long total = static_cast<long long>(n) * hw * c;
@@ -1057,19 +1083,39 @@ int qt_maxpool2d_bwd(const void* dout, const void* argmax, void* dx, int n, int 
                                                                     ksize, stride, pad);
   return cuda_status("maxpool2d_bwd");
 }
+namespace {
+bool quadtree_fast_ok(int qh, int qw, int cq, int cg, int ldf) {
+  const int pp = (qh / 2) * (qw / 2);
+  return cq % 8 == 0 && cg % 64 == 0 && ldf % 8 == 0 && (cq * pp) % 8 == 0 && pp > 0 &&
+         static_cast<size_t>(qh) * qw * cq * 2 <= 48 * 1024;
+}
+}  // namespace
 int qt_quadtree_pool_fwd(const void* q, const void* l4, void* feat, int b, int qh, int qw, int cq, int ghw, int cg,
                          int ldf, qt_stream_t stream) {
+  if (b < 1) return 0;
+  if (quadtree_fast_ok(qh, qw, cq, cg, ldf)) {
+    quadtree_pool_fwd_kernel<<<dim3(b, 5), kQtThreads, static_cast<size_t>(qh) * qw * cq * 2, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(l4), static_cast<__nv_bfloat16*>(feat), b, qh, qw,
+        cq, ghw, cg, ldf);
+    return cuda_status("quadtree_pool_fwd");
+  }
   const long long total = static_cast<long long>(b) * 4 * cq + static_cast<long long>(b) * cg;
-  quadtree_pool_fwd_kernel<<<grid_for(total, 128), 128, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(q),
-                                                                        static_cast<const __nv_bfloat16*>(l4),
-                                                                        static_cast<__nv_bfloat16*>(feat), b, qh, qw, cq,
-                                                                        ghw, cg, ldf);
+  quadtree_pool_fwd_generic_kernel<<<grid_for(total, 128), 128, 0, S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(l4), static_cast<__nv_bfloat16*>(feat), b, qh, qw, cq,
+      ghw, cg, ldf);
   return cuda_status("quadtree_pool_fwd");
 }
 int qt_quadtree_pool_bwd(const void* dfeat, const void* q, void* dq, void* dl4, int b, int qh, int qw, int cq,
                          int ghw, int cg, int ldf, qt_stream_t stream) {
+  if (b < 1) return 0;
+  if (quadtree_fast_ok(qh, qw, cq, cg, ldf)) {
+    quadtree_pool_bwd_kernel<<<dim3(b, 5), kQtThreads, static_cast<size_t>(cq) * (qh / 2) * (qw / 2) * 2, S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dfeat), static_cast<const __nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(dq),
+        static_cast<__nv_bfloat16*>(dl4), b, qh, qw, cq, ghw, cg, ldf);
+    return cuda_status("quadtree_pool_bwd");
+  }
   const long long total = static_cast<long long>(b) * 4 * qh * qw * cq + static_cast<long long>(b) * ghw * cg;
-  quadtree_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(
+  quadtree_pool_bwd_generic_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dfeat), static_cast<const __nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(dq),
       static_cast<__nv_bfloat16*>(dl4), b, qh, qw, cq, ghw, cg, ldf);
   return cuda_status("quadtree_pool_bwd");
@@ -1182,6 +1228,81 @@ int qt_relu_dropout_bwd(const float* dout, const float* act, float* dz, void* dz
   relu_dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(dout, act, dz, static_cast<__nv_bfloat16*>(dz16), n, drop_p, seed,
                                                                   relu);
   return cuda_status("relu_dropout_bwd");
+}
+
+
+// ---- loss + fused classifier tail -------------------------------------------------------------------------------
+int qt_cross_entropy(const float* logits, long long ld, const long long* labels, int b, int nc, float grad_scale,
+                     const float* upstream, float* loss_rows, float* loss_mean, float* dlogits, unsigned int* counter,
+                     qt_stream_t stream) {
+  if (b < 1 || nc < 1 || nc > kMaxClasses) return fail("cross_entropy: 1 <= classes <= %d (got %d)", kMaxClasses, nc);
+  if (!loss_rows || !loss_mean || !counter) return fail("cross_entropy: loss_rows / loss_mean / counter are required");
+  cross_entropy_kernel<<<(b + 7) / 8, 256, 0, S(stream)>>>(logits, ld, labels, b, nc, grad_scale, upstream, loss_rows, loss_mean, dlogits, counter);
+  return cuda_status("cross_entropy");
+}
+int qt_head_tail_fwd(float* h, void* h16, int nhid, const float* w3, const float* b3, int nc, const long long* labels, int b,
+                     float drop_p, unsigned long long seed, float* logits, float* loss_rows, float* loss_mean,
+                     unsigned int* counter, qt_stream_t stream) {
+  if (b < 1) return 0;
+  if (nc < 1 || nc > kMaxClasses) return fail("head_tail: 1 <= classes <= %d (got %d)", kMaxClasses, nc);
+  if (nhid < 1 || nhid > kHeadThreads * kHeadCols) return fail("head_tail: hidden width must be <= %d (got %d)", kHeadThreads * kHeadCols, nhid);
+  if (labels && (!loss_rows || !loss_mean || !counter)) return fail("head_tail: labels need loss_rows / loss_mean / counter");
+  head_tail_fwd_kernel<<<b, kHeadThreads, 0, S(stream)>>>(h, static_cast<__nv_bfloat16*>(h16), nhid, w3, b3, nc, labels, b, drop_p,
+                                                          seed, logits, loss_rows, loss_mean, counter);
+  return cuda_status("head_tail_fwd");
+}
+int qt_head_tail_bwd(const float* act, int nhid, const float* w3, int nc, const float* logits, const long long* labels,
+                     float grad_scale, const float* upstream, float drop_p, unsigned long long seed, float* dlogits, void* dh16,
+                     int b, qt_stream_t stream) {
+  if (b < 1) return 0;
+  if (nc < 1 || nc > kMaxClasses) return fail("head_tail: 1 <= classes <= %d (got %d)", kMaxClasses, nc);
+  if (!dlogits || !dh16) return fail("head_tail_bwd: dlogits and dh16 are required");
+  if (labels && !logits) return fail("head_tail_bwd: labels need the stored logits");
+  head_tail_bwd_kernel<<<b, kHeadThreads, 0, S(stream)>>>(act, nhid, w3, nc, logits, labels, grad_scale, upstream, drop_p, seed,
+                                                          dlogits, static_cast<__nv_bfloat16*>(dh16));
+  return cuda_status("head_tail_bwd");
+}
+
+// ---- optimizer ----------------------------------------------------------------------------------------------------
+int qt_adam_item_plan(qt_adam_item* item) {
+  static_assert(sizeof(qt_adam_item) == sizeof(AdamItem), "qt_adam_item layout");
+  static_assert(sizeof(qt_adam_group) == sizeof(AdamGroup), "qt_adam_group layout");
+  if (!item || item->n < 1) return fail("adam_item_plan: bad item");
+  if (item->wf) {
+    if (item->cout < 1 || item->cin < 1 || item->taps < 1 || item->taps > 32 ||
+        static_cast<long long>(item->cout) * item->cin * item->taps != item->n)
+      return fail("adam_item_plan: packed item needs cout*cin*taps == n and taps <= 32");
+    item->co_tile = wpack_co_tile(item->taps);
+    item->ci_tiles = (item->cin + 31) / 32;
+    return item->ci_tiles * ((item->cout + item->co_tile - 1) / item->co_tile);
+  }
+  item->co_tile = item->ci_tiles = 0;
+  const long long blocks = (item->n + kAdamElemsPerBlock - 1) / kAdamElemsPerBlock;
+  if (blocks > 0x7fffffff) return fail("adam_item_plan: tensor too large");
+  return static_cast<int>(blocks);
+}
+int qt_adam_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, const qt_adam_group* groups, int ngroups,
+                  const float* clip_coef, qt_stream_t stream) {
+  if (nitems < 1 || total_blocks < 1) return 0;
+  if (ngroups < 1 || ngroups > kAdamMaxGroups) return fail("adam_multi: 1..%d parameter groups", kAdamMaxGroups);
+  if (max_taps < 1 || max_taps > 32) return fail("adam_multi: taps must be 1..32");
+  AdamGroups g;
+  memset(&g, 0, sizeof(g));
+  memcpy(g.g, groups, sizeof(AdamGroup) * ngroups);
+  size_t smem = wpack_smem(1);
+  for (int t = 2; t <= max_taps; ++t) smem = wpack_smem(t) > smem ? wpack_smem(t) : smem;
+  adam_multi_kernel<<<total_blocks, 256, smem, S(stream)>>>(static_cast<const AdamItem*>(items_dev), nitems, g, clip_coef);
+  return cuda_status("adam_multi");
+}
+int qt_grad_norm_blocks(long long n) { return static_cast<int>((n + kAdamElemsPerBlock - 1) / kAdamElemsPerBlock); }
+int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float* partial, float* total_norm,
+                      float* coef, qt_stream_t stream) {
+  static_assert(sizeof(qt_norm_item) == sizeof(NormItem), "qt_norm_item layout");
+  if (nitems < 1 || total_blocks < 1) return fail("grad_clip_coef: no gradients");
+  grad_sqnorm_multi_kernel<<<total_blocks, 256, 0, S(stream)>>>(static_cast<const NormItem*>(items_dev), nitems, partial);
+  if (int rc = cuda_status("grad_sqnorm_multi")) return rc;
+  grad_clip_coef_kernel<<<1, 256, 0, S(stream)>>>(partial, total_blocks, max_norm, total_norm, coef);
+  return cuda_status("grad_clip_coef");
 }
 
 }  // extern "C"

@@ -306,9 +306,9 @@ class PackClip(torch.autograd.Function):
     @staticmethod
     def forward(ctx, clips):
         bsz, t, c, h, w = clips.shape
-        xf = clips.detach().float().contiguous()
+        xf, dtype, scale, shift = ops.stem_source(clips)
         out = torch.empty(bsz, t, h, w, 8, device=clips.device, dtype=BF16)
-        check(L().qt_nchw_f32_to_nhwc_bf16(ptr(xf), ptr(out), bsz * t, c, h * w, 8, stream()), "pack clip")
+        check(L().qt_nchw_to_nhwc_bf16_ex(ptr(xf), dtype, ptr(scale), ptr(shift), ptr(out), bsz * t, c, h * w, 8, stream()), "pack clip")
         ops._count()
         return out
 

@@ -51,10 +51,10 @@ class _StemFn(torch.autograd.Function):
         if conv_w.shape[1:] != (3, 7, 7) or c != 3:
             raise RuntimeError("stem: expected a 3-channel 7x7 stride-2 convolution (ResNet-18 conv1)")
         dev = x.device
-        xf = x.detach().float().contiguous()
         xp = torch.empty(n, h + 7, w + 8, 4, device=dev, dtype=BF16)
-        with ops.gemm_scope("stem_pack_input", 0.0, 4.0 * xf.numel() + 2.0 * xp.numel()):
-            check(L().qt_stem_pack_input(ptr(xf), ptr(xp), n, 3, h, w, stream()), "stem_pack_input")
+        xf, dtype, scale, shift = ops.stem_source(x)
+        with ops.gemm_scope("stem_pack_input", 0.0, float(xf.element_size()) * xf.numel() + 2.0 * xp.numel()):
+            check(L().qt_stem_pack_input_ex(ptr(xf), dtype, ptr(scale), ptr(shift), ptr(xp), n, 3, h, w, stream()), "stem_pack_input")
         w8 = ops.packed_stem(conv_w)
         ho, wo = h // 2, w // 2
         y = torch.empty(n, ho, wo, cout, device=dev, dtype=BF16)
@@ -299,7 +299,7 @@ def make_resnet18() -> nn.Module:
 # =================================================================================================
 class _QuadHeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, base, l4, numerical, qw, qb, m0w, m0b, m3w, m3b, c0w, c0b, c3w, c3b, mode, p_drop, training):
+    def forward(ctx, base, l4, numerical, qw, qb, m0w, m0b, m3w, m3b, c0w, c0b, c3w, c3b, mode, p_drop, training, labels=None):
         use_img = mode in ("fusion", "image_only")
         use_num = mode in ("fusion", "numerical_only")
         dev = (base if use_img else numerical).device
@@ -328,7 +328,9 @@ class _QuadHeadFn(torch.autograd.Function):
             dq = None
         feat = torch.empty(n, ldf, device=dev, dtype=BF16)
         if use_img:
-            check(L().qt_quadtree_pool_fwd(ptr(q), ptr(l4b), ptr(feat), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_fwd")
+            # algorithmic bytes: quadrant maps + layer4 map in, 5120 features out (110 KB per image)
+            with ops.gemm_scope("quadtree_pool_fwd", 0.0, 2.0 * (q.numel() + l4b.numel() + n * nimg)):
+                check(L().qt_quadtree_pool_fwd(ptr(q), ptr(l4b), ptr(feat), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_fwd")
             ops._count()
         numf = None
         if use_num:
@@ -341,41 +343,61 @@ class _QuadHeadFn(torch.autograd.Function):
             check(L().qt_small_linear_fwd(ptr(h1), 0, nh, ptr(m3w.detach()), ptr(m3b.detach()), n, nnum, nh, 0, 0.0, 0, None, 0,
                                           feat.data_ptr() + 2 * nimg, ldf, stream()), "numerical_mlp.3")
             ops._count(2)
-        # classifier.0 on the tensor cores, then ReLU + dropout, then classifier.3
+        # classifier.0 on the tensor cores; everything behind it (ReLU + dropout, classifier.3, and — when the caller hands
+        # over the labels — the cross-entropy loss) is ONE launch of the fused tail kernel
         nhid = c0w.shape[0]
         hbuf = torch.empty(n, nhid, device=dev)
-        h16 = torch.empty(n, nhid, device=dev, dtype=BF16)
         ws = ops.workspace(L().qt_linear_workspace_bytes(n, nhid, ldf), dev)
         wf0 = ops.packed_fprop(c0w)
         with ops.gemm_scope("linear_fprop", 2.0 * n * nhid * ldf):
             check(L().qt_linear_fprop(ptr(feat), ldf, ptr(wf0), ptr(c0b.detach()), ptr(hbuf), nhid,
                                       capi.QT_EPI_BIAS | capi.QT_EPI_OUT_F32, n, nhid, ldf, ptr(ws), ws.numel(), stream()), "classifier.0")
-        check(L().qt_relu_dropout(ptr(hbuf), ptr(h16), n * nhid, p, seed2, 1, stream()), "classifier relu/dropout")
         nc = c3w.shape[0]
         logits = torch.empty(n, nc, device=dev)
-        check(L().qt_small_linear_fwd(ptr(hbuf), 0, nhid, ptr(c3w.detach()), ptr(c3b.detach()), n, nc, nhid, 0, 0.0, 0, ptr(logits), nc,
-                                      None, 0, stream()), "classifier.3")
-        ops._count(4)
+        lab = lossbuf = None
+        if labels is not None:
+            lab = labels.detach().to(device=dev, dtype=torch.int64).contiguous()
+            lossbuf = torch.empty(n + 1, device=dev)  # [per-row losses | mean]
+        from .loss import _counter
+        # algorithmic bytes: hidden row read + written back activated (fp32), classifier.3 weights once per CTA from L2
+        with ops.gemm_scope("head_tail_fwd", 0.0, 8.0 * hbuf.numel() + 4.0 * c3w.numel()):
+            check(L().qt_head_tail_fwd(ptr(hbuf), None, nhid, ptr(c3w.detach()), ptr(c3b.detach()), nc, ptr(lab), n, p, seed2, ptr(logits),
+                                       ptr(lossbuf), lossbuf.data_ptr() + 4 * n if lossbuf is not None else None,
+                                       ptr(_counter(dev)) if lab is not None else None, stream()), "head_tail_fwd")
+        ops._count(3)
         if any(ctx.needs_input_grad):
-            ctx.saved = (bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b)
+            ctx.saved = (bb, q, feat, numf, h1, hbuf, logits, lab, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b)
             ctx.cfg = (mode, p, seed1, seed2, n, ldf, nimg, nnum, dq)
+        if labels is not None:
+            ctx.mark_non_differentiable(logits)
+            return lossbuf[n], logits
         return logits
 
     @staticmethod
-    def backward(ctx, dlogits):
-        bb, q, feat, numf, h1, hbuf, h16, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b = ctx.saved
+    def backward(ctx, dout, _dlogits_unused=None):
+        bb, q, feat, numf, h1, hbuf, logits, lab, qw, m0w, m3w, c0w, c3w, qb, m0b, m3b, c0b, c3b = ctx.saved
         mode, p, seed1, seed2, n, ldf, nimg, nnum, dq = ctx.cfg
         need = ctx.needs_input_grad
         dev = feat.device
-        dl = dlogits.detach().float().contiguous()
         nc, nhid = c3w.shape
-        # classifier.3
+        dh16 = torch.empty(n, nhid, device=dev, dtype=BF16)
+        # fused tail backward: (with labels) softmax cross-entropy gradient scaled by the incoming loss gradient on the
+        # device, classifier.3 dX through the ReLU / dropout gate -> bf16 operand of the classifier.0 gradient GEMMs
+        if lab is not None:
+            dl = torch.empty(n, nc, device=dev)
+            up = dout.detach().reshape(1).float().contiguous()
+            with ops.gemm_scope("head_tail_bwd", 0.0, 4.0 * hbuf.numel() + 2.0 * dh16.numel() + 4.0 * c3w.numel()):
+                check(L().qt_head_tail_bwd(ptr(hbuf), nhid, ptr(c3w.detach()), nc, ptr(logits), ptr(lab), 1.0 / n, ptr(up), p, seed2, ptr(dl),
+                                           ptr(dh16), n, stream()), "head_tail_bwd")
+        else:
+            dl = dout.detach().float().contiguous()
+            with ops.gemm_scope("head_tail_bwd", 0.0, 4.0 * hbuf.numel() + 2.0 * dh16.numel() + 4.0 * c3w.numel()):
+                check(L().qt_head_tail_bwd(ptr(hbuf), nhid, ptr(c3w.detach()), nc, None, None, 1.0, None, p, seed2, ptr(dl), ptr(dh16), n,
+                                           stream()), "head_tail_bwd")
+        # classifier.3 weight / bias gradient
         dc3w = ops.grad_out(c3w)
         dc3b = ops.grad_out(c3b)
         check(L().qt_small_linear_bwd_dw(ptr(dl), 0, nc, ptr(hbuf), 0, nhid, n, nc, nhid, ptr(dc3w), ptr(dc3b), 0, stream()), "classifier.3 dW")
-        dh16 = torch.empty(n, nhid, device=dev, dtype=BF16)
-        check(L().qt_small_linear_bwd_dx(ptr(dl), 0, nc, ptr(c3w.detach()), n, nc, nhid, ptr(hbuf), nhid, p, seed2, None, 0,
-                                         ptr(dh16), nhid, stream()), "classifier.3 dX")
         ops._count(2)
         # classifier.0
         ws = ops.workspace(L().qt_linear_workspace_bytes(n, nhid, ldf), dev)
@@ -408,7 +430,9 @@ class _QuadHeadFn(torch.autograd.Function):
         if nimg:
             dqt = torch.empty_like(q)
             dl4b = torch.empty(n, 7, 7, 512, device=dev, dtype=BF16)
-            check(L().qt_quadtree_pool_bwd(ptr(dfeat), ptr(q), ptr(dqt), ptr(dl4b), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_bwd")
+            # algorithmic bytes: feature-row gradient + quadrant maps in (arg-max recomputed), both gradients out
+            with ops.gemm_scope("quadtree_pool_bwd", 0.0, 2.0 * (n * nimg + q.numel() + dqt.numel() + dl4b.numel())):
+                check(L().qt_quadtree_pool_bwd(ptr(dfeat), ptr(q), ptr(dqt), ptr(dl4b), n, 7, 7, 128, 49, 512, ldf, stream()), "quadtree_pool_bwd")
             ops._count()
             dl4 = ops.as_nchw_view(dl4b) if need[1] else None
             if need[3]:
@@ -421,7 +445,7 @@ class _QuadHeadFn(torch.autograd.Function):
                 dbb = torch.empty_like(bb)
                 ops.conv_dgrad(dq, dqt, ops.packed_dgrad(qw), dbb)
                 dbase = ops.as_nchw_view(dbb)
-        return (dbase, dl4, None, dqw, dqb, dm0w, dm0b, dm3w, dm3b, dc0w, dc0b, dc3w, dc3b, None, None, None)
+        return (dbase, dl4, None, dqw, dqb, dm0w, dm0b, dm3w, dm3b, dc0w, dc0b, dc3w, dc3b, None, None, None, None)
 
 
 # =================================================================================================
@@ -478,7 +502,7 @@ class QuadtreeCNN(nn.Module):
     def save_activation_hook(self, module, input, output):
         self.activations = output
 
-    def forward(self, image_input, numerical_input):
+    def _run(self, image_input, numerical_input, labels):
         base = l4 = None
         if self.mode in ("fusion", "image_only"):
             base = self.features_extractor(image_input)
@@ -486,7 +510,19 @@ class QuadtreeCNN(nn.Module):
         qp, mlp, cls = self.quadrant_processor[0], self.numerical_mlp, self.classifier
         return _QuadHeadFn.apply(base, l4, numerical_input, qp.weight, qp.bias, mlp[0].weight, mlp[0].bias, mlp[3].weight,
                                  mlp[3].bias, cls[0].weight, cls[0].bias, cls[3].weight, cls[3].bias, self.mode,
-                                 self.dropout_rate, self.training)
+                                 self.dropout_rate, self.training, labels)
+
+    def forward(self, image_input, numerical_input):
+        """fp32 logits [B, num_classes] with a live autograd graph — the reference's signature; the scripts own the
+        criterion. `image_input` may be fp32 / bf16 (already normalised) or uint8 (decoded pixels, normalised on the
+        device with ImageNet mean / std like the reference's transform)."""
+        return self._run(image_input, numerical_input, None)
+
+    def training_loss(self, image_input, numerical_input, labels):
+        """(loss, logits): `nn.CrossEntropyLoss()(self(image_input, numerical_input), labels)` with the loss computed
+        inside the fused head-tail kernel (north star: fusion MLP + classifier + cross-entropy as one fused stage).
+        `loss` carries the autograd graph, `logits` is detached (accuracy bookkeeping as in Quadtree_train.py:67-69)."""
+        return self._run(image_input, numerical_input, labels)
 
 
 # =================================================================================================

@@ -388,6 +388,36 @@ def colsum(x2d, out, accumulate=False):
     _count(3)
 
 
+# ------------------------------------------------------------------------------------------------- input
+_norm_cache = {}
+
+
+def input_norm(device, mean=None, std=None):
+    """Per-channel (scale, shift) device tensors of ToTensor + Normalize for uint8 pixels: v/255 - mean over std."""
+    from .data import IMAGENET_MEAN, IMAGENET_STD
+    mean = tuple(IMAGENET_MEAN if mean is None else mean)
+    std = tuple(IMAGENET_STD if std is None else std)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), mean, std)
+    t = _norm_cache.get(key)
+    if t is None:
+        scale = torch.tensor([1.0 / (255.0 * s) for s in std] + [0.0], dtype=torch.float32)
+        shift = torch.tensor([-m / s for m, s in zip(mean, std)] + [0.0], dtype=torch.float32)
+        t = _norm_cache[key] = (scale.to(device), shift.to(device))
+    return t
+
+
+def stem_source(x: torch.Tensor):
+    """(contiguous NCHW tensor, QT_DTYPE_*, scale, shift) for the input-packing kernels: fp32 / bf16 inputs are taken as
+    already normalised (what the reference's DataLoader yields), uint8 inputs are decoded pixels normalised on the device."""
+    xd = x.detach()
+    if xd.dtype == torch.uint8:
+        scale, shift = input_norm(xd.device)
+        return xd.contiguous(), capi.QT_DTYPE_U8, scale, shift
+    if xd.dtype == BF16:
+        return xd.contiguous(), capi.QT_DTYPE_BF16, None, None
+    return xd.float().contiguous(), capi.QT_DTYPE_F32, None, None
+
+
 # ------------------------------------------------------------------------------------------------- misc
 def as_nhwc(t: torch.Tensor) -> torch.Tensor:
     """Logical NCHW tensor (any dtype / memory format) -> dense [N,H,W,C] bf16 buffer (no copy when it already

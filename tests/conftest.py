@@ -6,5 +6,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+os.environ.setdefault("QTCNN_QUIET_PRETRAINED", "1")  # tests load seeded oracle parameters on purpose
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")

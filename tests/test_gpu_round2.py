@@ -1,0 +1,264 @@
+"""Round-2 kernels through the C ABI / their Python mirrors: cross-entropy, the fused classifier tail, multi-tensor Adam with
+bf16 operand emission, global-norm clipping, uint8 input packing, the vectorised quadtree stage at other shapes, the prefetcher."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.loading import load_oracle_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import qtcnn_b200.capi as capi
+    capi.lib()
+    return capi
+
+
+def test_cross_entropy_matches_torch(C):
+    from qtcnn_b200.loss import CrossEntropyLoss
+    g = torch.Generator(device="cuda").manual_seed(0)
+    crit = CrossEntropyLoss()
+    for b, nc in ((1, 2), (7, 8), (256, 8), (33, 12), (300, 32)):
+        logits = (3.0 * torch.randn(b, nc, device="cuda", generator=g)).requires_grad_(True)
+        labels = torch.randint(0, nc, (b,), device="cuda", generator=g)
+        ref_in = logits.detach().clone().requires_grad_(True)
+        ref = F.cross_entropy(ref_in, labels)
+        out = crit(logits, labels)
+        assert out.shape == () and abs(float(out) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+        (0.37 * ref).backward()
+        (0.37 * out).backward()  # a non-unit incoming gradient is applied on the device
+        assert float((logits.grad - ref_in.grad).abs().max()) <= 1e-7 + 1e-5 * float(ref_in.grad.abs().max())
+    with pytest.raises(RuntimeError):
+        crit(torch.randn(4, 33, device="cuda"), torch.zeros(4, dtype=torch.int64, device="cuda"))  # > 32 classes: no fallback
+
+
+def test_head_tail_kernels(C):
+    lib = C.lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for b, nhid, nc, p in ((5, 2688, 8, 0.0), (64, 2688, 8, 0.5), (3, 1024, 12, 0.3), (2, 100, 5, 0.0)):
+        h = torch.randn(b, nhid, device="cuda", generator=g)
+        w3 = (torch.randn(nc, nhid, device="cuda", generator=g) / math.sqrt(nhid))
+        b3 = torch.randn(nc, device="cuda", generator=g)
+        labels = torch.randint(0, nc, (b,), device="cuda", generator=g)
+        seed = 12345
+        # reference of relu + dropout from the existing (tested) kernel, same seed / index convention
+        act_ref = h.clone()
+        C.check(lib.qt_relu_dropout(C.ptr(act_ref), None, b * nhid, p, seed, 1, C.stream()))
+        a = act_ref.clone().requires_grad_(True)
+        w = w3.clone().requires_grad_(True)
+        logits_ref = F.linear(a, w, b3)
+        loss_ref = F.cross_entropy(logits_ref, labels)
+        loss_ref.backward()
+        hh = h.clone()
+        logits = torch.empty(b, nc, device="cuda")
+        lossbuf = torch.zeros(b + 1, device="cuda")
+        counter = torch.zeros(1, device="cuda", dtype=torch.int32)
+        C.check(lib.qt_head_tail_fwd(C.ptr(hh), None, nhid, C.ptr(w3), C.ptr(b3), nc, C.ptr(labels), b, p, seed, C.ptr(logits),
+                                     lossbuf.data_ptr(), lossbuf.data_ptr() + 4 * b, C.ptr(counter), C.stream()))
+        assert torch.equal(hh, act_ref), "activated hidden row must equal relu_dropout's"
+        assert float((logits - logits_ref).abs().max()) <= 1e-5 * max(1.0, float(logits_ref.abs().max()))
+        assert abs(float(lossbuf[b]) - float(loss_ref)) <= 5e-6 * max(1.0, float(loss_ref))
+        assert int(counter) == 0
+        up = torch.tensor([0.5], device="cuda")
+        dl = torch.empty(b, nc, device="cuda")
+        dh16 = torch.empty(b, nhid, device="cuda", dtype=torch.bfloat16)
+        C.check(lib.qt_head_tail_bwd(C.ptr(hh), nhid, C.ptr(w3), nc, C.ptr(logits), C.ptr(labels), 1.0 / b, C.ptr(up), p, seed, C.ptr(dl),
+                                     C.ptr(dh16), b, C.stream()))
+        dl_ref = torch.autograd.grad(F.cross_entropy(logits_ref.detach().requires_grad_(True), labels), [], allow_unused=True) if False else None
+        lr = logits_ref.detach().clone().requires_grad_(True)
+        (0.5 * F.cross_entropy(lr, labels)).backward()
+        assert float((dl - lr.grad).abs().max()) <= 1e-6
+        # d hidden: through the gate recorded in act (zero where ReLU closed or dropped; dropout scale otherwise)
+        scale = torch.where(act_ref > 0, torch.full_like(h, 1.0 / (1.0 - p) if p > 0 else 1.0), torch.zeros_like(h))
+        dh_ref = (lr.grad @ w3) * scale
+        err = float((dh16.float() - dh_ref).abs().max())
+        assert err <= 2 ** -8 * float(dh_ref.abs().max()) + 1e-12
+        # logits-only mode (labels = NULL): the caller supplies dlogits
+        dl_in = torch.randn(b, nc, device="cuda", generator=g)
+        dh16b = torch.empty_like(dh16)
+        C.check(lib.qt_head_tail_bwd(C.ptr(hh), nhid, C.ptr(w3), nc, None, None, 1.0, None, p, seed, C.ptr(dl_in), C.ptr(dh16b), b,
+                                     C.stream()))
+        ref_b = (dl_in @ w3) * scale
+        assert float((dh16b.float() - ref_b).abs().max()) <= 2 ** -8 * float(ref_b.abs().max()) + 1e-12
+
+
+def test_training_loss_equals_forward_plus_criterion(C):
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import models as M
+    p = O.make_params("quadtree", 8, seed=0)
+    images, numerical, labels = O.synthetic_batch(6, 31)
+    grads = []
+    for fused in (False, True):
+        model = M.QuadtreeCNN(num_classes=8, dropout_rate=0.0)
+        load_oracle_params(model, p)
+        model = model.cuda().train()
+        if fused:
+            loss, logits = model.training_loss(images.cuda(), numerical.cuda(), labels.cuda())
+            assert not logits.requires_grad
+        else:
+            logits = model(images.cuda(), numerical.cuda())
+            loss = F.cross_entropy(logits, labels.cuda())
+        loss.backward()
+        grads.append((float(loss), logits.detach().clone(), {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None}))
+    (l0, lg0, g0), (l1, lg1, g1) = grads
+    assert torch.equal(lg0, lg1)
+    assert abs(l0 - l1) <= 2e-6 * max(1.0, abs(l0))
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        d = float((g0[n] - g1[n]).abs().max())
+        assert d <= 2e-3 * float(g0[n].abs().max()) + 1e-9, (n, d)  # dlogits differ by fp32 rounding before the bf16 cast
+
+
+def test_adam_matches_torch_and_emits_operand_copies(C):
+    from qtcnn_b200 import ops
+    from qtcnn_b200.optim import Adam
+    lib = C.lib()
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (128, 64, 1, 1), (32, 16, 3, 3, 3), (40, 24), (200,), (7, 5, 3, 3), (3000, 130)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.1) for s in shapes]
+    theirs = [torch.nn.Parameter(q.detach().clone()) for q in ours]
+    # register bf16 GEMM copies for the conv / linear weights, as a forward pass would
+    with torch.enable_grad():
+        for q in ours[:4] + ours[5:]:
+            ops.packed_fprop(q)
+    opt_a = Adam([{"params": ours[:3], "lr": 1e-3}, {"params": ours[3:], "lr": 3e-4, "weight_decay": 1e-2}], weight_decay=1e-4)
+    opt_b = torch.optim.Adam([{"params": theirs[:3], "lr": 1e-3}, {"params": theirs[3:], "lr": 3e-4, "weight_decay": 1e-2}], weight_decay=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(10):
+        for a, b in zip(ours, theirs):
+            gr = torch.randn(a.shape, device="cuda", generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if step == 4:
+            ours[4].grad = theirs[4].grad = None  # a parameter without gradient keeps its own step count
+        opt_a.step()
+        opt_b.step()
+        assert opt_a.launches_last_step == 1
+    for a, b in zip(ours, theirs):
+        assert float((a - b).abs().max()) <= 1e-6, float((a - b).abs().max())
+    sa, sb = opt_a.state_dict(), opt_b.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])
+        assert float((sa["state"][k]["exp_avg_sq"] - sb["state"][k]["exp_avg_sq"]).abs().max()) <= 1e-7
+    # the bf16 operand copies written by the optimizer launch equal a fresh pack of the updated weights, and the cache
+    # hands them out without another pack launch
+    for q in ours[:4] + ours[5:]:
+        cout, cin, taps = ops._w_dims(q)
+        wf = torch.empty(cout, taps, cin, device="cuda", dtype=torch.bfloat16)
+        wd = torch.empty(cin, taps, cout, device="cuda", dtype=torch.bfloat16)
+        C.check(lib.qt_wpack_both(C.ptr(q.detach().contiguous()), C.ptr(wf), C.ptr(wd), cout, cin, taps, C.stream()))
+        n0 = ops.launches()
+        with torch.enable_grad():
+            got_f, got_d = ops.packed_fprop(q), ops.packed_dgrad(q)
+        assert ops.launches() == n0, "operand copies must already be fresh after the fused step"
+        assert torch.equal(got_f, wf) and torch.equal(got_d, wd)
+    # torch's optimizer can resume from our state_dict (same layout)
+    opt_b.load_state_dict(sa)
+
+
+def test_clip_grad_norm(C):
+    from qtcnn_b200.optim import Adam, clip_grad_norm_
+    torch.manual_seed(1)
+    shapes = [(300, 70), (5,), (64, 3, 7, 7), (1,)]
+    for scale, max_norm in ((1.0, 1.0), (1e-3, 1.0)):  # clipped and not clipped
+        a = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+        b = [torch.nn.Parameter(q.detach().clone()) for q in a]
+        c = [torch.nn.Parameter(q.detach().clone()) for q in a]
+        for x, y, z in zip(a, b, c):
+            x.grad = torch.randn(x.shape, device="cuda") * scale
+            y.grad, z.grad = x.grad.clone(), x.grad.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_(b, max_norm)
+        norm = clip_grad_norm_(a, max_norm)
+        assert abs(float(norm) - float(ref_norm)) <= 1e-5 * float(ref_norm)
+        for x, y in zip(a, b):
+            assert float((x.grad - y.grad).abs().max()) <= 1e-6 * max(1.0, float(y.grad.abs().max()))
+        # deferred: gradients untouched, coefficient applied inside the optimizer launch
+        opt_c, opt_b = Adam(c, lr=1e-2), torch.optim.Adam(b, lr=1e-2)
+        before = [z.grad.clone() for z in c]
+        clip_grad_norm_(c, max_norm, optimizer=opt_c)
+        assert all(torch.equal(z.grad, g0) for z, g0 in zip(c, before))
+        opt_c.step()
+        opt_b.step()
+        for z, y in zip(c, b):
+            assert float((z - y).abs().max()) <= 2e-6
+
+
+def test_uint8_input_path(C):
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import data, ops
+    from qtcnn_b200 import models as M
+    lib = C.lib()
+    images, numerical, _ = O.synthetic_batch(3, 77, image_size=64)
+    u8 = data.quantize_images_u8(images).cuda()
+    norm = data.normalize_u8_reference(u8)  # the reference transform in fp32
+    n, c, h, w = u8.shape
+    xa = torch.empty(n, h + 7, w + 8, 4, device="cuda", dtype=torch.bfloat16)
+    xb = torch.empty_like(xa)
+    scale, shift = ops.input_norm(u8.device)
+    C.check(lib.qt_stem_pack_input_ex(C.ptr(u8), C.QT_DTYPE_U8, C.ptr(scale), C.ptr(shift), C.ptr(xa), n, c, h, w, C.stream()))
+    C.check(lib.qt_stem_pack_input(C.ptr(norm.contiguous()), C.ptr(xb), n, c, h, w, C.stream()))
+    # identical up to one bf16 ulp where fma(u8, 1/(255 std), -mean/std) and (u8/255 - mean)/std round differently
+    d = (xa.float() - xb.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(xb.float().abs().max())
+    assert float((d > 0).float().mean()) < 0.02
+    assert torch.equal(xa[:, :3], torch.zeros_like(xa[:, :3])) and torch.equal(xa[..., 3], torch.zeros_like(xa[..., 3]))
+    xc = torch.empty_like(xa)
+    C.check(lib.qt_stem_pack_input_ex(C.ptr(norm.to(torch.bfloat16).contiguous()), C.QT_DTYPE_BF16, None, None, C.ptr(xc), n, c, h, w, C.stream()))
+    assert torch.equal(xc, xb)
+    assert lib.qt_stem_pack_input_ex(C.ptr(u8), C.QT_DTYPE_U8, None, None, C.ptr(xa), n, c, h, w, C.stream()) < 0  # u8 needs scale/shift
+    # model level: uint8 pixels in, same logits as the normalised fp32 tensor (eval mode, 224x224)
+    images, numerical, _ = O.synthetic_batch(2, 78)
+    u8 = data.quantize_images_u8(images).cuda()
+    model = M.QuadtreeCNN(num_classes=8).cuda().eval()
+    with torch.no_grad():
+        a = model(u8, numerical.cuda())
+        b = model(data.normalize_u8_reference(u8), numerical.cuda())
+    assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-4
+
+
+def test_quadtree_stage_other_shapes(C):
+    """Vectorised kernels (16-byte aligned shapes) and the generic fallback against torch on non-reference shapes."""
+    lib = C.lib()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for b, qh, qw, cq, gh, cg, extra in ((3, 7, 7, 128, 7, 512, 256), (2, 6, 8, 64, 4, 128, 0), (2, 5, 5, 16, 3, 64, 8), (2, 7, 7, 12, 7, 24, 3)):
+        ph, pw = qh // 2, qw // 2
+        q = torch.randn(4, b, cq, qh, qw, device="cuda", generator=g).to(torch.bfloat16).relu()
+        l4 = torch.randn(b, cg, gh, gh, device="cuda", generator=g).to(torch.bfloat16).relu()
+        qf, lf = q.float().requires_grad_(True), l4.float().requires_grad_(True)
+        ref = torch.cat([F.adaptive_avg_pool2d(lf, 1).flatten(1)] + [F.max_pool2d(qf[i], 2, 2).flatten(1) for i in range(4)], dim=1)
+        nimg = cg + 4 * cq * ph * pw
+        ldf = nimg + extra
+        feat = torch.zeros(b, ldf, device="cuda", dtype=torch.bfloat16)
+        qn = q.permute(0, 1, 3, 4, 2).contiguous()
+        ln = l4.permute(0, 2, 3, 1).contiguous()
+        C.check(lib.qt_quadtree_pool_fwd(C.ptr(qn), C.ptr(ln), C.ptr(feat), b, qh, qw, cq, gh * gh, cg, ldf, C.stream()))
+        assert torch.equal(feat[:, cg:nimg].float(), ref[:, cg:].detach())
+        assert float((feat[:, :cg].float() - ref[:, :cg]).abs().max()) <= 2 ** -8 * float(ref[:, :cg].abs().max()) + 1e-6
+        assert float(feat[:, nimg:].abs().max() if extra else 0.0) == 0.0
+        dfeat = torch.randn(b, ldf, device="cuda", generator=g).to(torch.bfloat16)
+        ref.backward(dfeat[:, :nimg].float())
+        dq = torch.full_like(qn, float("nan"))
+        dl = torch.full_like(ln, float("nan"))
+        C.check(lib.qt_quadtree_pool_bwd(C.ptr(dfeat), C.ptr(qn), C.ptr(dq), C.ptr(dl), b, qh, qw, cq, gh * gh, cg, ldf, C.stream()))
+        assert torch.equal(dq.permute(0, 1, 4, 2, 3).float(), qf.grad * (q.float() > 0))
+        assert float((dl.permute(0, 3, 1, 2).float() - lf.grad).abs().max()) <= 2 ** -8 * float(lf.grad.abs().max()) + 1e-9
+
+
+def test_batch_prefetcher(C):
+    from qtcnn_b200.data import BatchPrefetcher
+    host = [(torch.full((4, 3, 8, 8), float(i)).pin_memory(), torch.full((4, 47), float(-i)).pin_memory(),
+             torch.full((4,), i, dtype=torch.int64).pin_memory()) for i in range(5)]
+    seen = []
+    pf = BatchPrefetcher(host, "cuda")
+    for x, nf, y in pf:
+        seen.append((float(x.mean()), float(nf.mean()), int(y[0])))
+        assert x.is_cuda and y.dtype == torch.int64
+    assert seen == [(float(i), float(-i), i) for i in range(5)]
+    assert pf.h2d_bytes_last == 4 * 3 * 8 * 8 * 4 + 4 * 47 * 4 + 4 * 8
+    assert list(BatchPrefetcher([], "cuda")) == []
