@@ -13,6 +13,7 @@
 #include "wgrad3x3.cuh"
 #include "head.cuh"
 #include "optim.cuh"
+#include "lstm.cuh"
 
 using namespace qt;
 
@@ -1303,6 +1304,49 @@ int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float
   if (int rc = cuda_status("grad_sqnorm_multi")) return rc;
   grad_clip_coef_kernel<<<1, 256, 0, S(stream)>>>(partial, total_blocks, max_norm, total_norm, coef);
   return cuda_status("grad_clip_coef");
+}
+
+
+// ---- LSTM (numeric-sequence branches) -------------------------------------------------------------------------------
+int qt_transpose_f32(const float* in, float* out, int rows, int cols, qt_stream_t stream) {
+  if (rows < 1 || cols < 1) return fail("transpose: empty matrix");
+  transpose_f32_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, S(stream)>>>(in, out, rows, cols);
+  return cuda_status("transpose_f32");
+}
+namespace {
+int lstm_threads(int h) { return ((4 * h + 31) / 32) * 32; }
+}  // namespace
+int qt_lstm_layer_fwd(const float* x, int in_dim, const float* wih_t, const float* whh_t, const float* bih, const float* bhh, int b,
+                      int t, int h, float in_drop_p, unsigned long long seed, float* hseq, float* hprev, float* cseq, float* gates,
+                      float* x_used, qt_stream_t stream) {
+  if (b < 1 || t < 1) return 0;
+  if (h < 1 || 4 * h > 1024) return fail("lstm: hidden size must be <= 256 (got %d)", h);
+  if (in_dim < 1) return fail("lstm: bad input size");
+  const size_t smem = sizeof(float) * kLstmBT * (static_cast<size_t>(in_dim) + 5 * h);
+  if (smem > 200 * 1024) return fail("lstm: input size %d too large for the shared-memory staging", in_dim);
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(lstm_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  lstm_layer_fwd_kernel<<<(b + kLstmBT - 1) / kLstmBT, lstm_threads(h), smem, S(stream)>>>(x, in_dim, wih_t, whh_t, bih, bhh, b, t, h,
+                                                                                           in_drop_p, seed, hseq, hprev, cseq, gates,
+                                                                                           x_used);
+  return cuda_status("lstm_layer_fwd");
+}
+int qt_lstm_layer_bwd(const float* dhseq, float out_drop_p, unsigned long long seed, const float* whh, const float* gates,
+                      const float* cseq, int b, int t, int h, float* dgates, qt_stream_t stream) {
+  if (b < 1 || t < 1) return 0;
+  if (h < 1 || 4 * h > 1024) return fail("lstm: hidden size must be <= 256 (got %d)", h);
+  const size_t smem = sizeof(float) * kLstmBT * (static_cast<size_t>(4 * h) + h + 4 * h);
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(lstm_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  lstm_layer_bwd_kernel<<<(b + kLstmBT - 1) / kLstmBT, lstm_threads(h), smem, S(stream)>>>(dhseq, out_drop_p, seed, whh, gates, cseq, b,
+                                                                                           t, h, dgates);
+  return cuda_status("lstm_layer_bwd");
 }
 
 }  // extern "C"

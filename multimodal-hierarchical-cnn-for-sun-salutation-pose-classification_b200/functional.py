@@ -192,6 +192,105 @@ class LinearTC(torch.autograd.Function):
         return dx, dw, db, None, None, None
 
 
+class LSTM(torch.autograd.Function):
+    """Multi-layer `nn.LSTM(batch_first=True)` forward over the whole sequence (zero initial state, inter-layer dropout in
+    training mode): x [B, T, I] fp32 -> top layer's output sequence [B, T, H] fp32. `weights` = (weight_ih, weight_hh,
+    bias_ih, bias_hh) per layer, torch layout and gate order (3dcnn/models.py:144-158, cnn+lstm/models.py:43-49)."""
+
+    @staticmethod
+    def forward(ctx, x, p_drop, training, *weights):
+        if not x.is_cuda:
+            raise RuntimeError("LSTM: the B200 path has no CPU implementation")
+        layers = len(weights) // 4
+        xin = x.detach().float().contiguous()
+        bsz, T, _ = xin.shape
+        dev = xin.device
+        p = float(p_drop) if training else 0.0
+        saved = []
+        cur = xin
+        for l in range(layers):
+            wih, whh, bih, bhh = weights[4 * l: 4 * l + 4]
+            G, I = wih.shape
+            H = whh.shape[1]
+            wih_t = torch.empty(I, G, device=dev)
+            whh_t = torch.empty(H, G, device=dev)
+            check(L().qt_transpose_f32(ptr(wih.detach().contiguous()), ptr(wih_t), G, I, stream()), "lstm transpose")
+            check(L().qt_transpose_f32(ptr(whh.detach().contiguous()), ptr(whh_t), G, H, stream()), "lstm transpose")
+            hseq = torch.empty(bsz, T, H, device=dev)
+            hprev = torch.empty_like(hseq)
+            cseq = torch.empty_like(hseq)
+            gates = torch.empty(bsz, T, G, device=dev)
+            in_p = p if l > 0 else 0.0
+            seed = ops.new_seed() if in_p > 0 else 0
+            x_used = torch.empty_like(cur) if in_p > 0 else None
+            check(L().qt_lstm_layer_fwd(ptr(cur), I, ptr(wih_t), ptr(whh_t), ptr(bih.detach()) if bih is not None else None,
+                                        ptr(bhh.detach()) if bhh is not None else None, bsz, T, H, in_p, seed, ptr(hseq), ptr(hprev),
+                                        ptr(cseq), ptr(gates), ptr(x_used), stream()), "lstm_layer_fwd")
+            ops._count(3)
+            saved.append((x_used if x_used is not None else cur, hprev, cseq, gates, in_p, seed))
+            cur = hseq
+        if any(ctx.needs_input_grad):
+            ctx.saved = saved
+            ctx.weights = weights
+            ctx.dims = (bsz, T)
+        return cur
+
+    @staticmethod
+    def backward(ctx, dout):
+        weights, saved = ctx.weights, ctx.saved
+        bsz, T = ctx.dims
+        layers = len(saved)
+        d = dout.detach().float().contiguous()
+        grads = [None] * len(weights)
+        out_p, out_seed = 0.0, 0
+        dx = None
+        for l in reversed(range(layers)):
+            wih, whh, bih, bhh = weights[4 * l: 4 * l + 4]
+            x_used, hprev, cseq, gates, in_p, seed = saved[l]
+            G, I = wih.shape
+            H = whh.shape[1]
+            dev = gates.device
+            dgates = torch.empty_like(gates)
+            check(L().qt_lstm_layer_bwd(ptr(d), out_p, out_seed, ptr(whh.detach().contiguous()), ptr(gates), ptr(cseq), bsz, T, H,
+                                        ptr(dgates), stream()), "lstm_layer_bwd")
+            rows = bsz * T
+            need_ih = ctx.needs_input_grad[3 + 4 * l] or (bih is not None and ctx.needs_input_grad[3 + 4 * l + 2])
+            if need_ih:
+                dwih = ops.grad_out(wih)
+                dbih = ops.grad_out(bih) if bih is not None else None
+                check(L().qt_small_linear_bwd_dw(ptr(dgates), 0, G, ptr(x_used), 0, I, rows, G, I, ptr(dwih), ptr(dbih), 0, stream()),
+                      "lstm dWih")
+                grads[4 * l], grads[4 * l + 2] = dwih, dbih
+            if ctx.needs_input_grad[3 + 4 * l + 1] or (bhh is not None and ctx.needs_input_grad[3 + 4 * l + 3]):
+                dwhh = ops.grad_out(whh)
+                dbhh = ops.grad_out(bhh) if bhh is not None else None
+                check(L().qt_small_linear_bwd_dw(ptr(dgates), 0, G, ptr(hprev), 0, H, rows, G, H, ptr(dwhh), ptr(dbhh), 0, stream()),
+                      "lstm dWhh")
+                grads[4 * l + 1], grads[4 * l + 3] = dwhh, dbhh
+            ops._count(3)
+            if l > 0 or ctx.needs_input_grad[0]:
+                dxl = torch.empty(bsz, T, I, device=dev)
+                check(L().qt_small_linear_bwd_dx(ptr(dgates), 0, G, ptr(wih.detach().contiguous()), rows, G, I, None, 0, 0.0, 0, ptr(dxl), I,
+                                                 None, 0, stream()), "lstm dX")
+                ops._count()
+                d, out_p, out_seed = dxl, in_p, seed  # gradient w.r.t. the (dropped-out) input = the layer below's output
+                if l == 0:
+                    dx = dxl
+        return (dx, None, None) + tuple(grads)
+
+
+def lstm_forward(module, x, training=None):
+    """Run an `nn.LSTM` module's parameters through the LSTM Function (same state_dict; batch_first, unidirectional)."""
+    if module.bidirectional or not module.batch_first or getattr(module, "proj_size", 0):
+        raise RuntimeError("LSTM: only batch_first, unidirectional, projection-free LSTMs (what the reference builds) are implemented")
+    ws = []
+    for l in range(module.num_layers):
+        ws += [getattr(module, f"weight_ih_l{l}"), getattr(module, f"weight_hh_l{l}"),
+               getattr(module, f"bias_ih_l{l}") if module.bias else None, getattr(module, f"bias_hh_l{l}") if module.bias else None]
+    tr = module.training if training is None else training
+    return LSTM.apply(x, float(module.dropout), tr, *ws)
+
+
 class AttnPool(torch.autograd.Function):
     """softmax(scores) weighted sum of R region vectors (QS/models.py:86-90): x fp32 [B,R,C], scores [B,R]."""
 

@@ -636,7 +636,7 @@ class StandardResNetCNN(nn.Module):
 
 
 # =================================================================================================
-# Quadtree3DCNN (3dcnn/models.py:96-214): Conv3d stack on the tensor cores; the LSTM stays torch
+# Quadtree3DCNN (3dcnn/models.py:96-214): Conv3d stack on the tensor cores, numeric LSTM on the persistent LSTM kernels
 # =================================================================================================
 class Quadtree3DCNN(nn.Module):
     _POOLS = {"conv3d_block1": (1, 2, 2), "conv3d_block2": (2, 2, 2), "conv3d_block3": (2, 2, 2),
@@ -700,7 +700,7 @@ class Quadtree3DCNN(nn.Module):
     def forward(self, image_sequence_input, numerical_sequence_input):
         image_features = self.conv_stack(image_sequence_input)
         if self.mode == "quadtree_3d_fusion":
-            lstm_out, _ = self.numerical_lstm(numerical_sequence_input.to(image_features.device).float())
+            lstm_out = Fn.lstm_forward(self.numerical_lstm, numerical_sequence_input.to(image_features.device).float())
             proj = self.numerical_projection[0]
             num = Fn.SmallLinear.apply(lstm_out[:, -1, :], proj.weight, proj.bias, True, self.dropout_rate, self.training)
             combined = torch.cat((image_features, num), dim=1)
@@ -713,7 +713,7 @@ class Quadtree3DCNN(nn.Module):
 
 # =================================================================================================
 # CnnLstm (cnn+lstm/models.py:14-89): every frame through the frozen ResNet-18 on the tensor cores; the temporal
-# LSTM stays torch
+# LSTM runs on the persistent LSTM kernels (functional.LSTM)
 # =================================================================================================
 class CnnLstm(nn.Module):
     def __init__(self, num_classes, sequence_length=4, numerical_feature_dim=47, dropout_rate=0.5, lstm_hidden_size=256):
@@ -739,7 +739,7 @@ class CnnLstm(nn.Module):
         num = numerical_sequence.to(c_out.device).float()
         n_out = Fn.SmallLinear.apply(num, mlp[0].weight, mlp[0].bias, True, 0.0, self.training)
         n_out = Fn.SmallLinear.apply(n_out, mlp[2].weight, mlp[2].bias, False, 0.0, self.training)
-        lstm_out, _ = self.lstm(torch.cat((c_out, n_out), dim=2))
+        lstm_out = Fn.lstm_forward(self.lstm, torch.cat((c_out, n_out), dim=2))
         final_state = lstm_out[:, -1, :]
         cls = self.classifier
         hdn = Fn.SmallLinear.apply(final_state, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)

@@ -262,3 +262,63 @@ def test_batch_prefetcher(C):
     assert seen == [(float(i), float(-i), i) for i in range(5)]
     assert pf.h2d_bytes_last == 4 * 3 * 8 * 8 * 4 + 4 * 47 * 4 + 4 * 8
     assert list(BatchPrefetcher([], "cuda")) == []
+
+
+@pytest.mark.parametrize("I,H,B,T", [(47, 188, 5, 16), (640, 256, 3, 6), (10, 8, 9, 3)])
+def test_lstm_kernels_match_torch(C, I, H, B, T):
+    """functional.LSTM (persistent per-layer kernels + BPTT) against torch's nn.LSTM evaluated in fp32 on the CPU: output
+    sequence, input gradient and every parameter gradient (2 layers, no dropout; both reference sizes)."""
+    from qtcnn_b200 import functional as Fn
+    torch.manual_seed(3)
+    ref = torch.nn.LSTM(input_size=I, hidden_size=H, num_layers=2, batch_first=True, dropout=0.0)
+    mine = torch.nn.LSTM(input_size=I, hidden_size=H, num_layers=2, batch_first=True, dropout=0.0)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    x = torch.randn(B, T, I)
+    xr = x.clone().requires_grad_(True)
+    xm = x.clone().cuda().requires_grad_(True)
+    out_r, _ = ref(xr)
+    out_m = Fn.lstm_forward(mine, xm)
+    assert out_m.shape == (B, T, H)
+    assert float((out_m.cpu() - out_r).abs().max()) <= 2e-5
+    w = torch.randn(B, H)
+    # the reference models read only the last time step (3dcnn/models.py:202, cnn+lstm/models.py:84)
+    (out_r[:, -1, :] * w).sum().backward()
+    (out_m[:, -1, :] * w.cuda()).sum().backward()
+    assert float((xm.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * max(1.0, float(xr.grad.abs().max()))
+    for (n, pr), (_, pm) in zip(ref.named_parameters(), mine.named_parameters()):
+        err = float((pm.grad.cpu() - pr.grad).abs().max())
+        assert err <= 2e-5 * max(1.0, float(pr.grad.abs().max())), (n, err)
+
+
+def test_lstm_dropout_between_layers(C):
+    """Training-mode inter-layer dropout: the mask is regenerated in the backward; with p > 0 the output differs from p = 0,
+    is reproducible under the same torch seed, and finite-difference consistent for a weight of layer 0."""
+    from qtcnn_b200 import functional as Fn
+    torch.manual_seed(4)
+    lstm = torch.nn.LSTM(input_size=12, hidden_size=16, num_layers=2, batch_first=True, dropout=0.5).cuda().train()
+    x = torch.randn(4, 5, 12, device="cuda")
+    torch.manual_seed(11)
+    a = Fn.lstm_forward(lstm, x)
+    torch.manual_seed(11)
+    b = Fn.lstm_forward(lstm, x)
+    assert torch.equal(a, b)
+    lstm.eval()
+    c = Fn.lstm_forward(lstm, x)
+    assert not torch.allclose(a, c)
+    lstm.train()
+    torch.manual_seed(11)
+    out = Fn.lstm_forward(lstm, x)
+    out[:, -1, :].sum().backward()
+    g = lstm.weight_ih_l0.grad[3, 2].item()
+    eps = 1e-2
+    with torch.no_grad():
+        lstm.weight_ih_l0[3, 2] += eps
+    torch.manual_seed(11)
+    up = Fn.lstm_forward(lstm, x)[:, -1, :].sum().item()
+    with torch.no_grad():
+        lstm.weight_ih_l0[3, 2] -= 2 * eps
+    torch.manual_seed(11)
+    dn = Fn.lstm_forward(lstm, x)[:, -1, :].sum().item()
+    fd = (up - dn) / (2 * eps)
+    assert abs(fd - g) <= 2e-2 * max(1.0, abs(g)), (fd, g)
