@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="quadtree_train", choices=["quadtree_train", "attention_infer", "quadtree3d_train", "cnn_lstm_train"],
-                    help="quadtree_train is the BASELINE.json headline (configs[2]); the other two time configs[1] / configs[3] "
-                         "for profiles/ and print an informational line with their own metric name")
+                    help="quadtree_train is the BASELINE.json headline (configs[2]); the others time configs[1] / [3] / [4] the same "
+                         "way (device-timed value, e2e with host inputs, roofline families; torchrun for N > 1) and print a line "
+                         "with their own metric name, kept under profiles/")
     return ap.parse_args()
 
 
@@ -182,10 +183,109 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
+WORKLOADS = {
+    # name: (BASELINE.json config index, metric, unit, default per-GPU batch)
+    "quadtree_train": (2, METRIC, UNIT, 256),
+    "attention_infer": (1, "AttentionHierarchicalCNN (level-1+2 quadtree) inference images/sec @224^2 bs256 bf16", "images/s", 256),
+    "quadtree3d_train": (3, "Quadtree3DCNN train clips/sec 16x112x112 bf16", "clips/s", 32),
+    "cnn_lstm_train": (4, "CnnLstm train frames/sec 16x224^2 bf16 (frozen ResNet-18 + MLP + LSTM)", "frames/s", 16),
+}
+
+
+def make_workload(name, batch, dev, world=1, rank=0):
+    """Model + optimizer + synthetic batch + step function of one BASELINE.json configuration. The step is the hot loop of the
+    reference script for that model (zero_grad / forward / criterion / backward / [clip] / Adam), through the package API."""
+    import torch
+    os.environ.setdefault("QTCNN_QUIET_PRETRAINED", "1")  # random init on purpose (no checkpoint offline)
+    from qtcnn_b200 import data as D
+    from qtcnn_b200 import loss as QL
+    from qtcnn_b200 import models as M
+    from qtcnn_b200 import optim, parallel
+    cfg_index, metric, unit, default_batch = WORKLOADS[name]
+    B = batch or default_batch
+    torch.manual_seed(0)
+    w = {"name": name, "metric": metric, "unit": unit, "batch": B, "config_index": cfg_index, "dp": None, "opt": None}
+    if name == "quadtree_train":
+        model = M.QuadtreeCNN(num_classes=8).to(dev).train()  # dropout 0.5 active, as in the reference script
+        images, numerical, labels = D.synthetic_batch(B, 1234 + rank)
+        w["units"], w["flops"] = B, TRAIN_GFLOP_PER_IMG * 1e9 * B
+        w["describe"] = (f"QuadtreeCNN level-1 (ResNet-18 + 2x2 quadtree + 47 pose features) fwd+bwd+Adam, 224x224, per-GPU batch {B}, "
+                         "dropout 0.5")
+        hyper = dict(lr=1e-4, weight_decay=1e-4)  # Quadtree_train.py:20-21
+    elif name == "attention_infer":
+        model = M.AttentionHierarchicalCNN(num_classes=8).to(dev).eval()
+        images, numerical, labels = D.synthetic_batch(B, 1234 + rank)
+        w["units"], w["flops"] = B, 3.977e9 * B  # SURVEY §8 a11
+        w["describe"] = f"AttentionHierarchicalCNN level-1 + level-2 quadtree inference (eval, no_grad), 224x224, per-GPU batch {B}"
+        hyper = None
+    elif name == "quadtree3d_train":
+        model = M.Quadtree3DCNN(num_classes=8, sequence_length=16).to(dev).train()
+        images, numerical, labels = D.synthetic_batch(B, 1234 + rank, seq_len=16, clip_size=112)
+        w["units"], w["flops"] = B, 39.5e9 * B  # SURVEY §8 a14
+        w["describe"] = (f"Quadtree3DCNN (5x Conv3d+BN3d+ReLU[+MaxPool3d], 2-layer LSTM on the pose sequence) fwd+bwd+clip+Adam, "
+                         f"16x112x112 clips, per-GPU batch {B}, dropout 0.6")
+        hyper = dict(lr=5e-5, weight_decay=5e-4)  # 3dcnn/train_3D_Quadtree_cnn_model.py:30-31
+    elif name == "cnn_lstm_train":
+        model = M.get_model_seq("cnn_lstm", 8, dev, seq_len=16).train()
+        images, numerical, labels = D.synthetic_batch(B, 1234 + rank, seq_len=16, clip_size=224)
+        w["units"], w["flops"] = B * 16, 3.63e9 * B * 16  # forward only through the frozen backbone (SURVEY §8 a17)
+        w["describe"] = f"CnnLstm (frozen ResNet-18 per frame, MLP, 2-layer LSTM) fwd+bwd+Adam, 16 frames of 224x224, per-GPU batch {B}"
+        hyper = dict(lr=1e-4, weight_decay=0.0)
+    else:
+        raise ValueError(name)
+    w["model"] = model
+    if hyper is not None:
+        w["dp"] = parallel.DataParallelGrads(model) if world > 1 else None
+        params = [p for p in model.parameters() if p.requires_grad]
+        # optim.Adam(model.parameters(), lr, weight_decay) of the scripts as ONE multi-tensor launch per step
+        w["opt"] = optim.Adam(params, **hyper)
+        w["optimizer"] = f"qtcnn_b200.optim.Adam (multi-tensor kernel, torch.optim.Adam semantics), {hyper}"
+    crit = QL.CrossEntropyLoss()
+    opt, dp = w["opt"], w["dp"]
+
+    if name == "quadtree_train":
+        def step(x, nf, y):
+            opt.zero_grad(set_to_none=True)
+            # forward + nn.CrossEntropyLoss (inside the fused head-tail kernel) + backward + Adam
+            loss, _ = model.training_loss(x, nf, y)
+            loss.backward()
+            if dp is not None:
+                dp.finish()
+            opt.step()
+            return loss
+    elif name == "attention_infer":
+        def step(x, nf, y):
+            with torch.no_grad():
+                return model(x, nf).sum()  # a 4-byte result to read back
+    elif name == "quadtree3d_train":
+        def step(x, nf, y):
+            opt.zero_grad(set_to_none=True)
+            loss = crit(model(x, nf), y)
+            loss.backward()
+            if dp is not None:
+                dp.finish()
+            optim.clip_grad_norm_(params, 1.0, optimizer=opt)  # 3dcnn/train_3D_Quadtree_cnn_model.py:123
+            opt.step()
+            return loss
+    else:
+        def step(x, nf, y):
+            opt.zero_grad(set_to_none=True)
+            loss = crit(model(x, nf), y)
+            loss.backward()
+            if dp is not None:
+                dp.finish()
+            opt.step()
+            return loss
+    w["step"] = step
+    # host batches: fp32 (what the reference DataLoader yields) and uint8 pixels (normalised on the device)
+    w["host_fp32"] = tuple(t.pin_memory() for t in (images, numerical, labels))
+    w["host_u8"] = (D.quantize_images_u8(images).pin_memory(),) + w["host_fp32"][1:]
+    return w
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,32 +296,14 @@ def run_ours(args):
         import datetime
         # a mismatched collective should end the run in minutes, not after NCCL's default 10-minute watchdog
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-    os.environ.setdefault("QTCNN_QUIET_PRETRAINED", "1")  # random init on purpose (no checkpoint offline)
-    from qtcnn_b200 import data as D  # synthetic-input recipe (the product arm never imports oracle/)
-    from qtcnn_b200 import models as M
-    from qtcnn_b200 import ops, optim, parallel
+    from qtcnn_b200 import data as D
+    from qtcnn_b200 import ops
 
-    B = args.batch
-    torch.manual_seed(0)
-    model = M.QuadtreeCNN(num_classes=8).to(dev).train()  # dropout 0.5 active, as in the reference script
-    dp = parallel.DataParallelGrads(model) if world > 1 else None
-    params = [p for p in model.parameters() if p.requires_grad]
-    # optim.Adam(model.parameters(), lr, weight_decay) of Quadtree_train.py:45 as one multi-tensor launch per step
-    opt = optim.Adam(params, lr=1e-4, weight_decay=1e-4)
-    images_h, numerical_h, labels_h = D.synthetic_batch(B, 1234 + rank)
-    images_u8_h = D.quantize_images_u8(images_h).pin_memory()  # decoded-pixel form of the same batch (e2e input path)
-    images_h, numerical_h, labels_h = images_h.pin_memory(), numerical_h.pin_memory(), labels_h.pin_memory()
-    images, numerical, labels = images_h.to(dev), numerical_h.to(dev), labels_h.to(dev)
-
-    def step(x, nf, y):
-        opt.zero_grad(set_to_none=True)
-        # forward + nn.CrossEntropyLoss (computed inside the fused head-tail kernel) + backward + Adam
-        loss, _ = model.training_loss(x, nf, y)
-        loss.backward()
-        if dp is not None:
-            dp.finish()
-        opt.step()
-        return loss
+    headline = args.workload == "quadtree_train"
+    batch = args.batch if (args.batch != 256 or headline) else None
+    w = make_workload(args.workload, batch, dev, world, rank)
+    B, step = w["batch"], w["step"]
+    dev_batch = tuple(t.to(dev) for t in w["host_fp32"])
 
     def barrier():
         if world > 1:
@@ -242,28 +324,26 @@ def run_ours(args):
         return float(ms)
 
     for _ in range(max(3, args.warmup)):
-        step(images, numerical, labels)
+        step(*dev_batch)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     n0 = ops.launches()
-    ms = timed(lambda: step(images, numerical, labels), args.steps)
+    ms = timed(lambda: step(*dev_batch), args.steps)
     launches = ops.launches() - n0
     clocks = sampler.stop() if sampler else None
-    value = B * world * args.steps / (ms * 1e-3)
+    value = w["units"] * world * args.steps / (ms * 1e-3)
 
-    # end to end through the package API (data.BatchPrefetcher + model.training_loss + optim.Adam): every step's inputs
-    # start in pinned HOST memory and are copied inside the timed region (side stream, double-buffered staging, so the
-    # copy of step i+1 overlaps the kernels of step i, like a DataLoader with pin_memory + non_blocking copies); the loss
-    # of every step is read back to the host (asynchronous 4-byte D2H, consumed one step later, the way a training loop
-    # logs losses without stalling the GPU). Headline e2e: images travel as uint8 pixels and are normalised on the device
-    # (ToTensor + Normalize fused into the stem's packing kernel); `e2e_fp32_inputs`: normalised fp32 tensors, exactly what
-    # the reference's DataLoader hands to `images.to(device)` (4x the PCIe bytes).
+    # end to end through the package API (data.BatchPrefetcher + the model + optim.Adam): every step's inputs start in
+    # pinned HOST memory and are copied inside the timed region (side stream, double-buffered staging, so the copy of step
+    # i+1 overlaps the kernels of step i, like a DataLoader with pin_memory + non_blocking copies); the loss of every step
+    # is read back to the host (asynchronous 4-byte D2H, consumed one step later, the way a training loop logs losses
+    # without stalling the GPU). Headline e2e: images travel as uint8 pixels and are normalised on the device (ToTensor +
+    # Normalize fused into the input-packing kernel); `e2e_fp32_inputs`: normalised fp32 tensors, exactly what the
+    # reference's DataLoader hands to `images.to(device)` (4x the PCIe bytes).
     loss_h = [{"buf": torch.zeros((), dtype=torch.float32).pin_memory(), "ev": torch.cuda.Event()} for _ in range(2)]
 
     def run_e2e(host_batch, steps):
-        state = {"last": None}
-
         def loop(nsteps):
             def batches():
                 for _ in range(nsteps):
@@ -274,169 +354,110 @@ def run_ours(args):
                 slot["buf"].copy_(loss, non_blocking=True)
                 slot["ev"].record()
                 if i > 0:
-                    prev = loss_h[(i + 1) & 1]
-                    prev["ev"].synchronize()
-                    state["last"] = float(prev["buf"])
+                    loss_h[(i + 1) & 1]["ev"].synchronize()
         loop(2)
         return timed(lambda: loop(steps), 1)
 
-    if args.no_e2e:
-        ms_e2e, e2e, ms_e2e32, e2e32 = float("nan"), None, float("nan"), None
-    else:
-        ms_e2e = run_e2e((images_u8_h, numerical_h, labels_h), args.steps)
-        e2e = B * world * args.steps / (ms_e2e * 1e-3)
-        ms_e2e32 = run_e2e((images_h, numerical_h, labels_h), args.steps)
-        e2e32 = B * world * args.steps / (ms_e2e32 * 1e-3)
-    h2d = images_u8_h.numel() + numerical_h.numel() * 4 + labels_h.numel() * 8
-    h2d32 = images_h.numel() * 4 + numerical_h.numel() * 4 + labels_h.numel() * 8
+    def nbytes(batch):
+        return sum(t.numel() * t.element_size() for t in batch)
+
+    e2e = e2e32 = None
+    if not args.no_e2e:
+        t = run_e2e(w["host_u8"], args.steps)
+        e2e = {"value": w["units"] * world * args.steps / (t * 1e-3), "unit": w["unit"], "h2d_bytes_per_step": nbytes(w["host_u8"]),
+               "d2h_bytes_per_step": 4, "ms_per_step": t / args.steps,
+               "inputs": "uint8 pixels + fp32 pose vectors + int64 labels from pinned host memory, normalised on the device"}
+        t = run_e2e(w["host_fp32"], args.steps)
+        e2e32 = {"value": w["units"] * world * args.steps / (t * 1e-3), "unit": w["unit"], "h2d_bytes_per_step": nbytes(w["host_fp32"]),
+                 "d2h_bytes_per_step": 4, "ms_per_step": t / args.steps}
 
     roofline = None
     if not args.no_roofline:
         # every rank runs the instrumented steps (their gradient all-reduces must match across ranks); rank 0 reports
+        nsteps = min(3, args.steps)
         ops.profile_begin()
-        for _ in range(min(3, args.steps)):
-            step(images, numerical, labels)
+        for _ in range(nsteps):
+            step(*dev_batch)
         torch.cuda.synchronize()
         prof = ops.profile_end()
-    if not args.no_roofline and rank == 0:
-        peaks = load_peaks()
-        gemm = {k: v for k, v in prof.items() if v["flops"] > 0}
-        nsteps = min(3, args.steps)
-        flops = sum(v["flops"] for v in gemm.values())
-        tms = sum(v["ms"] for v in gemm.values())
-        nlaunch = sum(v["n"] for v in gemm.values())
-        # dominant kernel = the persistent slab convolution (conv3x3_kernel: 3x3/s1 fprop + dgrad)
-        dom = {k: v for k, v in gemm.items() if k.startswith("conv3x3_kernel")}
-        dflops, dms, dn = (sum(v[x] for v in dom.values()) for x in ("flops", "ms", "n"))
-        ach = dflops / (dms * 1e-3) / 1e12 if dms > 0 else 0.0
-        ncu = {}
-        ncu_path = os.path.join(ROOT, "profiles", "ncu_gemm_summary.json")
-        if os.path.exists(ncu_path):
-            with open(ncu_path) as f:
-                ncu = json.load(f)
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "traffic": ncu.get("conv3x3_kernel", {}).get("dram_bytes_per_launch"), "peak_source": peaks["src"],
-                    "kernel": "conv3x3_kernel (persistent tcgen05 slab convolution, 3x3/s1 fprop + dgrad)",
-                    "launches_per_step": dn / nsteps, "ms_per_launch": dms / max(dn, 1), "ms_per_step": dms / nsteps,
-                    "step_share": (dms / nsteps) / (ms / args.steps),
-                    "algorithmic_flops_per_launch": dflops / max(dn, 1),
-                    "tensor_pipe_active_pct_ncu": ncu.get("conv3x3_kernel", {}).get("tensor_active_pct"),
-                    "conv_tc_util_pct_flop_weighted_ncu": ncu.get("flop_weighted_tensor_active_pct"),
-                    "all_gemm": {"achieved": flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0, "launches_per_step": nlaunch / nsteps,
-                                 "ms_per_step": tms / nsteps, "step_share": (tms / nsteps) / (ms / args.steps)},
-                    "per_family": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / nsteps,
-                                       "launches_per_step": v["n"] / nsteps}
-                                   for k, v in gemm.items() if v["ms"] > 0},
-                    # streaming kernels: algorithmic bytes / CUDA-event time vs the measured HBM copy peak
-                    "hbm_families": {k: {"GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "frac_of_hbm_peak": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                         "ms_per_step": v["ms"] / nsteps, "calls_per_step": v["n"] / nsteps}
-                                     for k, v in prof.items() if v.get("bytes", 0) > 0 and v["ms"] > 0},
-                    "hbm_peak_GBps": peaks["hbm_gbs"]}
+        if rank == 0:
+            roofline = make_roofline(prof, nsteps, ms / args.steps, headline)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and headline and not args.no_cpu_baseline:
         rate, spi, threads, kind = cpu_reference_rate(args.cpu_batch, 4, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"4 steps of batch {args.cpu_batch} (fwd+bwd+Adam, fp32) after 1 warm-up, {spi:.2f} s/step"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"QuadtreeCNN level-1 (ResNet-18 + 2x2 quadtree + 47 pose features) fwd+bwd+Adam, 224x224, "
-                                   f"per-GPU batch {B}, dropout 0.5", "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "per-step activations+grads (~3 GB) exceed the 126 MB L2, no explicit flush",
-                       "optimizer": "qtcnn_b200.optim.Adam (multi-tensor kernel, torch.optim.Adam semantics), lr 1e-4, wd 1e-4",
-                       "loss": "nn.CrossEntropyLoss semantics inside the fused head-tail kernel (model.training_loss)"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                    "inputs": "uint8 pixels + fp32 pose vectors + int64 labels from pinned host memory, normalised on the device"},
-            "e2e_fp32_inputs": {"value": e2e32, "unit": UNIT, "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": 4,
-                                "ms_per_step": ms_e2e32 / args.steps},
+            "config": {"workload": w["describe"], "baseline_config_index": w["config_index"], "global_batch": B * world,
+                       "parallelism": f"dp{world}",
+                       "l2": "per-step activations (+gradients) exceed the 126 MB L2, no explicit flush",
+                       "optimizer": w.get("optimizer"),
+                       "loss": ("nn.CrossEntropyLoss semantics inside the fused head-tail kernel (model.training_loss)" if headline
+                                else "qtcnn_b200.loss.CrossEntropyLoss kernel")},
+            "e2e": e2e, "e2e_fp32_inputs": e2e32,
             "gpu_launches": launches,
-            "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
+            "model_tflops": value / w["units"] * w["flops"] / 1e12 / world,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if not headline:
+            line["informational"] = "secondary BASELINE.json configuration; the driver's headline is --workload quadtree_train"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_secondary(args):
-    """Informational timings of BASELINE.json configs[1] (level-1+2 inference) and configs[3] (3-D model training)."""
-    import torch
-    import torch.nn.functional as F
-    from qtcnn_b200 import data as O
-    from qtcnn_b200 import models as M
-    from qtcnn_b200 import ops
-    dev = torch.device("cuda", 0)
-    torch.manual_seed(0)
-    if args.workload == "attention_infer":
-        B = args.batch
-        model = M.AttentionHierarchicalCNN(num_classes=8).to(dev).eval()
-        images, numerical, _ = O.synthetic_batch(B, 1234)
-        images, numerical = images.to(dev), numerical.to(dev)
-
-        def step():
-            with torch.no_grad():
-                return model(images, numerical)
-        metric, unit, per_step = "AttentionHierarchicalCNN (level-1+2) inference images/sec @224^2 bf16", "images/s", B
-        flops = 3.977e9 * B
-    elif args.workload == "cnn_lstm_train":
-        # BASELINE.json configs[4] / SURVEY §8 a17: 16 frames x 224^2 per sample, frozen ResNet-18 (3.63 GFLOP/frame forward)
-        B = 16 if args.batch == 256 else args.batch
-        model = M.get_model_seq("cnn_lstm", 8, dev, seq_len=16).train()
-        opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4, fused=True)
-        frames, numerical, labels = O.synthetic_batch(B, 1234, seq_len=16, clip_size=224)
-        frames, numerical, labels = frames.to(dev), numerical.to(dev), labels.to(dev)
-
-        def step():
-            opt.zero_grad(set_to_none=True)
-            loss = F.cross_entropy(model(frames, numerical), labels)
-            loss.backward()
-            opt.step()
-            return loss
-        metric, unit, per_step = "CnnLstm train frames/sec 16x224^2 bf16 (frozen ResNet-18 + LSTM)", "frames/s", B * 16
-        flops = 3.63e9 * B * 16
-    else:
-        B = 32 if args.batch == 256 else args.batch
-        model = M.Quadtree3DCNN(num_classes=8, sequence_length=16).to(dev).train()
-        opt = torch.optim.Adam(model.parameters(), lr=5e-5, weight_decay=5e-4, fused=True)
-        clips, numerical, labels = O.synthetic_batch(B, 1234, seq_len=16, clip_size=112)
-        clips, numerical, labels = clips.to(dev), numerical.to(dev), labels.to(dev)
-
-        def step():
-            opt.zero_grad(set_to_none=True)
-            loss = F.cross_entropy(model(clips, numerical), labels)
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)  # 3dcnn/train_3D_Quadtree_cnn_model.py:123
-            opt.step()
-            return loss
-        metric, unit, per_step = "Quadtree3DCNN train clips/sec 16x112x112 bf16", "clips/s", B
-        flops = 39.5e9 * B
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    n0 = ops.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    value = per_step * args.steps / (ms * 1e-3)
-    print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
-                      "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": args.workload, "batch": B}, "gpu_launches": ops.launches() - n0,
-                      "model_tflops": flops * args.steps / (ms * 1e-3) / 1e12, "informational": True}), flush=True)
+def make_roofline(prof, nsteps, ms_step, headline):
+    """Roofline object from the event-instrumented pass: dominant tensor-core family against the measured bf16 peak, plus every
+    GEMM family (TFLOP/s) and every streaming family (algorithmic bytes / time against the measured HBM copy peak)."""
+    peaks = load_peaks()
+    gemm = {k: v for k, v in prof.items() if v["flops"] > 0}
+    flops = sum(v["flops"] for v in gemm.values())
+    tms = sum(v["ms"] for v in gemm.values())
+    nlaunch = sum(v["n"] for v in gemm.values())
+    # dominant kernel: the persistent slab convolution (conv3x3_kernel: 3x3/s1 fprop + dgrad) for the 2-D models, else the
+    # GEMM family with the largest share of the step
+    kernels = {}
+    for k, v in gemm.items():
+        d = kernels.setdefault(k.split(":")[0], {"flops": 0.0, "ms": 0.0, "n": 0})
+        for x in ("flops", "ms", "n"):
+            d[x] += v[x]
+    dom_name = "conv3x3_kernel" if (headline and "conv3x3_kernel" in kernels) else max(kernels, key=lambda k: kernels[k]["ms"])
+    dom = kernels[dom_name]
+    ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
+    ncu = {}
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_gemm_summary.json")
+    if os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            ncu = json.load(f)
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+            "traffic": ncu.get(dom_name, {}).get("dram_bytes_per_launch") if headline else None, "peak_source": peaks["src"],
+            "kernel": dom_name, "launches_per_step": dom["n"] / nsteps, "ms_per_launch": dom["ms"] / max(dom["n"], 1),
+            "ms_per_step": dom["ms"] / nsteps, "step_share": (dom["ms"] / nsteps) / ms_step,
+            "algorithmic_flops_per_launch": dom["flops"] / max(dom["n"], 1),
+            # static reads of the committed ncu summary (profiles/ncu_gemm_summary.json, regenerated per round by tools/ncu_summary.py)
+            "committed_ncu_tensor_pipe_active_pct": ncu.get(dom_name, {}).get("tensor_active_pct") if headline else None,
+            "committed_ncu_conv_tc_util_pct_flop_weighted": ncu.get("flop_weighted_tensor_active_pct") if headline else None,
+            "all_gemm": {"achieved": flops / (tms * 1e-3) / 1e12 if tms > 0 else 0.0, "launches_per_step": nlaunch / nsteps,
+                         "ms_per_step": tms / nsteps, "step_share": (tms / nsteps) / ms_step},
+            "per_family": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / nsteps,
+                               "launches_per_step": v["n"] / nsteps} for k, v in gemm.items() if v["ms"] > 0},
+            # streaming kernels (SURVEY 8d): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+            "hbm_families": {k: {"GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "ms_per_step": v["ms"] / nsteps, "calls_per_step": v["n"] / nsteps}
+                             for k, v in prof.items() if v.get("bytes", 0) > 0 and v["ms"] > 0},
+            "hbm_peak_GBps": peaks["hbm_gbs"]}
 
 
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
-    elif a.workload != "quadtree_train":
-        run_secondary(a)
     else:
         run_ours(a)

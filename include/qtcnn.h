@@ -243,6 +243,7 @@ typedef struct qt_adam_group {
   float eps;
   float weight_decay; /* L2, added to the gradient (torch.optim.Adam, not AdamW) */
   float inv_bc2_sqrt; /* 1 / sqrt(1 - beta2^t) */
+  float omb1, omb2;   /* 1 - beta1, 1 - beta2, rounded from double like torch's scalar arguments */
 } qt_adam_group;
 typedef struct qt_adam_item {
   float* p;       /* fp32 parameter, updated in place */

@@ -43,7 +43,7 @@ class ConvDesc(ctypes.Structure):
 class AdamGroup(ctypes.Structure):
     """Mirror of `qt_adam_group`."""
     _fields_ = [("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("weight_decay", c_float),
-                ("inv_bc2_sqrt", c_float)]
+                ("inv_bc2_sqrt", c_float), ("omb1", c_float), ("omb2", c_float)]
 
 
 class AdamItem(ctypes.Structure):

@@ -99,6 +99,24 @@ __global__ void stem_pack_input_kernel(const TIn* __restrict__ x, __nv_bfloat16*
 }
 
 // NCHW fp32 -> NHWC bf16 with channel padding to Cp (generic; used by the 3-D stack and tests).
+// Cp == 8 (3-channel clips padded to one 16-byte chunk per pixel): one thread per pixel, each channel plane read coalesced,
+// one 16-byte store per pixel.
+template <typename TIn>
+__global__ void nchw_to_nhwc8_bf16_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long long HW,
+                                          const float* __restrict__ scale, const float* __restrict__ shift) {
+  const long long total = static_cast<long long>(N) * HW;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { sc[c] = (scale && c < C) ? scale[c] : 1.f; sh[c] = (scale && c < C) ? shift[c] : 0.f; }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? stem_in<TIn>(x + (n * C + c) * HW + p, sc[c], sh[c]) : 0.f;
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
+  }
+}
 template <typename TIn>
 __global__ void nchw_to_nhwc_bf16_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, long long HW,
                                          int Cp, const float* __restrict__ scale, const float* __restrict__ shift) {

@@ -13,7 +13,7 @@
 
 namespace qt {
 
-constexpr int kLstmBT = 4;
+constexpr int kLstmBT = 2;  // samples per CTA: more CTAs matter more than weight reuse at the reference batch sizes (8-32)
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -68,11 +68,13 @@ __global__ void __launch_bounds__(1024) lstm_layer_fwd_kernel(const float* __res
       float acc[kLstmBT];
 #pragma unroll
       for (int s = 0; s < kLstmBT; ++s) acc[s] = bias;
-      for (int k = 0; k < I; ++k) {
+#pragma unroll 8
+      for (int k = 0; k < I; ++k) {  // unrolled: eight independent L2 loads in flight per thread (the loop is latency bound)
         const float w = __ldg(WihT + static_cast<long long>(k) * G + j);
 #pragma unroll
         for (int s = 0; s < kLstmBT; ++s) acc[s] = fmaf(w, xs[s * I + k], acc[s]);
       }
+#pragma unroll 8
       for (int k = 0; k < H; ++k) {
         const float w = __ldg(WhhT + static_cast<long long>(k) * G + j);
 #pragma unroll
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(1024) lstm_layer_bwd_kernel(const float* __res
       float acc[kLstmBT];
 #pragma unroll
       for (int s = 0; s < kLstmBT; ++s) acc[s] = 0.f;
+#pragma unroll 8
       for (int r = q * H; r < (q + 1) * H; ++r) {
         const float w = __ldg(Whh + static_cast<long long>(r) * H + k);
 #pragma unroll

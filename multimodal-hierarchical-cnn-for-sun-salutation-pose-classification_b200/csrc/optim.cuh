@@ -15,6 +15,7 @@ struct AdamGroup {  // one torch param_group; step-dependent factors are folded 
   float eps;
   float weight_decay;
   float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+  float omb1, omb2;     // 1 - beta1, 1 - beta2 rounded from double (torch passes them as double scalars; 1.f - 0.999f is 5e-5 off)
 };
 constexpr int kAdamMaxGroups = 8;
 struct AdamGroups {
@@ -37,8 +38,8 @@ constexpr int kAdamElemsPerBlock = 256 * 8;
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, const AdamGroup& G, float clip) {
   g = g * clip;
   g = fmaf(G.weight_decay, p, g);               // grad + wd * param (torch: grad.add(param, alpha=weight_decay))
-  m = m + (1.f - G.beta1) * (g - m);            // exp_avg.lerp_(grad, 1 - beta1)
-  v = fmaf(G.beta2, v, (1.f - G.beta2) * g * g);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  m = m + G.omb1 * (g - m);                     // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * G.beta2 + G.omb2 * (g * g);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) * G.inv_bc2_sqrt + G.eps;
   return p - G.step_size * (m / denom);
 }

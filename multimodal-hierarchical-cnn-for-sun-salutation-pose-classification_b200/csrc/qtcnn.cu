@@ -536,6 +536,14 @@ int qt_nchw_to_nhwc_bf16_ex(const void* x, int dtype, const float* scale, const 
   if ((scale == nullptr) != (shift == nullptr)) return fail("nchw_to_nhwc: scale and shift come together");
   if (dtype == QT_DTYPE_U8 && !scale) return fail("nchw_to_nhwc: uint8 input needs per-channel scale / shift");
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (c_pad == 8 && c <= 8 && (dtype == QT_DTYPE_F32 || dtype == QT_DTYPE_BF16 || dtype == QT_DTYPE_U8)) {
+    const int g8 = grid_for(static_cast<long long>(n) * hw, 256, 148 * 32);
+    if (dtype == QT_DTYPE_F32) nchw_to_nhwc8_bf16_kernel<float><<<g8, 256, 0, S(stream)>>>(static_cast<const float*>(x), o, n, c, hw, scale, shift);
+    else if (dtype == QT_DTYPE_BF16)
+      nchw_to_nhwc8_bf16_kernel<__nv_bfloat16><<<g8, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), o, n, c, hw, scale, shift);
+    else nchw_to_nhwc8_bf16_kernel<uint8_t><<<g8, 256, 0, S(stream)>>>(static_cast<const uint8_t*>(x), o, n, c, hw, scale, shift);
+    return cuda_status("nchw_to_nhwc8_bf16");
+  }
   const int grid = grid_for(total, 256, 1 << 20);
   if (dtype == QT_DTYPE_F32) nchw_to_nhwc_bf16_kernel<float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(x), o, n, c, hw, c_pad, scale, shift);
   else if (dtype == QT_DTYPE_BF16)

@@ -100,6 +100,7 @@ class Adam(torch.optim.Optimizer):
             g.step_size = lr / (1.0 - b1 ** t)
             g.beta1, g.beta2, g.eps, g.weight_decay = b1, b2, eps, wd
             g.inv_bc2_sqrt = 1.0 / math.sqrt(1.0 - b2 ** t)
+            g.omb1, g.omb2 = 1.0 - b1, 1.0 - b2
         arr = (capi.AdamItem * len(todo))()
         first, max_taps, packed_entries, key = 0, 1, [], []
         for i, (p, st, gidx) in enumerate(todo):

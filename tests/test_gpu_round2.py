@@ -145,7 +145,7 @@ def test_adam_matches_torch_and_emits_operand_copies(C):
     assert sa["state"].keys() == sb["state"].keys()
     for k in sa["state"]:
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])
-        assert float((sa["state"][k]["exp_avg_sq"] - sb["state"][k]["exp_avg_sq"]).abs().max()) <= 1e-7
+        assert float((sa["state"][k]["exp_avg_sq"] - sb["state"][k]["exp_avg_sq"]).abs().max()) <= 1e-7 + 1e-6 * float(sb["state"][k]["exp_avg_sq"].abs().max())
     # the bf16 operand copies written by the optimizer launch equal a fresh pack of the updated weights, and the cache
     # hands them out without another pack launch
     for q in ours[:4] + ours[5:]:
@@ -257,7 +257,8 @@ def test_batch_prefetcher(C):
     seen = []
     pf = BatchPrefetcher(host, "cuda")
     for x, nf, y in pf:
-        seen.append((float(x.mean()), float(nf.mean()), int(y[0])))
+        seen.append((float(x[1, 2, 3, 4]), float(nf[3, 46]), int(y[0])))
+        assert float(x.min()) == float(x.max())
         assert x.is_cuda and y.dtype == torch.int64
     assert seen == [(float(i), float(-i), i) for i in range(5)]
     assert pf.h2d_bytes_last == 4 * 3 * 8 * 8 * 4 + 4 * 47 * 4 + 4 * 8
