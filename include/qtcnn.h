@@ -58,7 +58,7 @@ void qt_set_conv3x3_enabled(int on);
 /* Developer knobs (value 0 = default everywhere). key 0 / 1: pipeline shape of the generic weight-gradient / K-major
  * kernels; 2: generic gather for the stem; 3: generic weight-gradient kernel for 3x3 convs; 4: 7x7 maps through the
  * generic kernels; 5: staged (coalesced) conv3x3 write-out 1 = never, 2 = always (default: maps at least 20 wide);
- * 6: weight tiles by cp.async instead of TMA. Also settable through the QTCNN_TUNE="k=v,..." environment variable
+ * 6: weight tiles by cp.async instead of TMA; 7: Conv3d through the generic gather kernels. Also settable through the QTCNN_TUNE="k=v,..." environment variable
  * of the Python binding. */
 void qt_set_tuning(int key, int value);
 
@@ -84,6 +84,9 @@ int qt_wpack_dgrad(const float* w, void* wd, int cout, int cin, int taps, qt_str
 /* both GEMM layouts from one read of the parameter (wd may be NULL). */
 int qt_wpack_both(const float* w, void* wf, void* wd, int cout, int cin, int taps, qt_stream_t stream);
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream);
+/* Conv3d forward weights with 32 input channels ([cout][32][3][3][3] fp32) -> bf16 [cout][2][9][64]: the operand of the
+ * slab kernel's pair mode (qt_conv_plan(d, 0) == 2), where one 128-byte slab row carries two depth planes. */
+int qt_wpack_conv3d_pair(const float* w, void* wp, int cout, qt_stream_t stream);
 /* Every weight of a model repacked in ONE launch (what the training loop needs after optimizer.step(),
  * QS/Quadtree_train.py:72): fill w/wf/wd/cout/cin/taps of each item, call qt_wpack_item_plan (fills co_tile and
  * ci_tiles, returns the item's block count or -1), set first_block to the running sum of the block counts, copy the
@@ -104,7 +107,8 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
  * quadrant_processor.0 QS/models.py:234-238 & 284-287, 3dcnn/models.py:107-139).
  * y = conv(x, wf) [+ bias] [ReLU]; with QT_EPI_STATS also writes per-tile column sum / sum-of-squares
  * partials [qt_conv_stat_rows][2][out_c] for the train-mode BatchNorm that follows. */
-/* kernel selection of a pass (0 = fprop, 1 = dgrad, 2 = wgrad): 0 generic gather GEMM, 1 persistent slab kernel. */
+/* kernel selection of a pass (0 = fprop, 1 = dgrad, 2 = wgrad): 0 generic gather GEMM, 1 persistent slab kernel,
+ * 2 (fprop of a 32-channel Conv3d only) slab kernel reading pair-packed weights (qt_wpack_conv3d_pair). */
 int qt_conv_plan(const qt_conv_desc* d, int pass);
 int qt_conv_stat_rows(const qt_conv_desc* d);
 size_t qt_conv_fprop_workspace_bytes(const qt_conv_desc* d);

@@ -24,7 +24,8 @@
 
 namespace qt {
 
-constexpr int kC3Threads = 352;  // 4 epilogue + 4 A-slab producer + 2 MMA-issuer warps + 1 TMA (weights) warp
+constexpr int kC3Threads = 352;
+constexpr int kNoPlane = 1 << 20;  // depth offset of a slab half that has no source plane (zero filled)  // 4 epilogue + 4 A-slab producer + 2 MMA-issuer warps + 1 TMA (weights) warp
 
 struct Conv3x3Params {
   const __nv_bfloat16* a;   // dense NHWC input  [N][H][W][cin]
@@ -42,6 +43,18 @@ struct Conv3x3Params {
   int b_tma;                // 1: weight tiles arrive by TMA (cp.async.bulk.tensor.2d through `wmap`), else cp.async
   signed char off_h[9], off_w[9];
   short wtap[9];
+  // 3-D convolutions (Conv3d 3x3x3 / stride 1 / pad 1, 3dcnn/models.py:107-139): N counts depth PLANES (clips * D); a
+  // depth tap is a whole-plane shift of the source, zero when it leaves the clip. A tile walks `slabs` = kdn * (cin/64)
+  // staged slabs (depth tap major). pair = 1 (cin == 32): one 128-byte slab row holds TWO depth planes of the same pixel
+  // (32 channels each), so slab 0 covers depth taps 0 and 1, slab 1 depth tap 2 (+ a zero half) against weights packed
+  // [nout][2][9][64] (qt_wpack_conv3d_pair).
+  int D;                    // planes per clip (1: plain 2-D convolution)
+  int kdn;                  // depth taps: 1 or 3
+  int pair;
+  int bias_on;              // EPI_BIAS: bias[nout] added before the store / statistics (Conv3d has bias=True)
+  const float* bias;
+  signed char dplane[4];    // source plane offset of depth tap kd (fprop: kd-1, dgrad: 1-kd)
+  signed char wkd[4];       // depth index of that tap inside the weight tensor
 };
 
 template <int BN, int MT, int NSLAB, int NB, bool STAGED>
@@ -116,11 +129,13 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
     const int adv_w = 16 % Wp, adv_h = 16 / Wp;
     // kernel parameters used in the gather loop live in registers (the cp.async asm has a memory clobber, which would
     // otherwise make the compiler re-read them from the constant bank every iteration)
-    const int pW = p.W, pH = p.H, pN = p.N, pR = p.R;
+    const int pW = p.W, pH = p.H, pN = p.N, pR = p.R, pD = p.D;
     const long long pix_bytes = static_cast<long long>(p.cin) * 2;
     const long long row_bytes = pW * pix_bytes;
+    const long long plane_bytes = static_cast<long long>(pH) * row_bytes;
     const long long adv_off = (static_cast<long long>(adv_h) * pW + adv_w) * pix_bytes;
     const void* dummy = p.a;
+    const int cs = p.pair ? 1 : p.cin / 64;  // 64-channel chunks per depth tap
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
@@ -129,23 +144,36 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
         {  // ---- A slab: rows j <-> virtual pixel q0 - (W+3) + j
           const int s = a_cnt % NSLAB;
           if (a_cnt >= NSLAB) QT_TRACE_WAIT(tr_a_empty, mbar_wait(&a_empty[s], ((a_cnt / NSLAB) - 1) & 1));
-          const __nv_bfloat16* src_c = p.a + c * 64 + chunk * 8;
+          // depth tap of this slab and the channel chunk inside it (2-D: kd = 0, dd = 0). Pair mode: this thread's 16-byte
+          // chunk column decides which of the slab's two planes it copies (chunks 0-3: first plane, 4-7: second plane).
+          int dd, ch_off;
+          if (p.pair) {
+            const int kd = 2 * c + (chunk >> 2);
+            dd = kd < 3 ? p.dplane[kd] : kNoPlane;  // the zero half of the second pair slab
+            ch_off = (chunk & 3) * 8;
+          } else {
+            const int kd = c / cs;
+            dd = p.dplane[kd];
+            ch_off = (c - kd * cs) * 64 + chunk * 8;
+          }
+          const __nv_bfloat16* src_c = p.a + ch_off;
           // first row of this thread: virtual pixel v0 (shifted by one image so the decomposition is non-negative),
           // then advance 16 virtual pixels per iteration with carries instead of dividing per row
-          int n, hp, wp;
+          int n, hp, wp, dz;  // n: plane index (image for 2-D), dz: its depth inside the clip
           {
             const int vv = q0 - (pW + 3) + rbase + Wp * Hp;
             wp = vv % Wp;
             const int rest = vv / Wp;
             hp = rest % Hp;
             n = rest / Hp - 1;
+            dz = (n + pD) % pD;
           }
           // byte address of real pixel (n, hp-1, wp-1), kept incrementally (only dereferenced when the row is real):
           // +16 virtual pixels = adv_off; a w-carry skips the 2 pad columns, an h-carry the shared zero row.
           // Addresses are produced in batches of kBatch into distinct registers and only then handed to cp.async:
           // the LSU releases a cp.async's address registers late, so reusing one register pair per copy would
           // serialise the copies on that release.
-          const char* srcb = reinterpret_cast<const char*>(src_c) +
+          const char* srcb = reinterpret_cast<const char*>(src_c) + (dd == kNoPlane ? 0 : dd) * plane_bytes +
                              (static_cast<long long>(n * pH + (hp - 1)) * pW + (wp - 1)) * pix_bytes;
           // slab row j holds virtual pixel q0 - (W+3) + j; a thread's rows are 16 apart, so its swizzle phase is fixed
           uint32_t dst = smem_u32(slab_base + s * slab_bytes) + rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
@@ -157,13 +185,14 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
               const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(pN)) &&
-                              (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
+                              (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1) &&
+                              (static_cast<unsigned>(dz + dd) < static_cast<unsigned>(pD));
               sp[b] = ok ? static_cast<const void*>(srcb) : dummy;
               sz[b] = ok ? 16u : 0u;
               srcb += adv_off;
               wp += adv_w; hp += adv_h;
               if (wp >= Wp) { wp -= Wp; ++hp; srcb -= 2 * pix_bytes; }
-              if (hp >= Hp) { hp -= Hp; ++n; srcb -= row_bytes; }
+              if (hp >= Hp) { hp -= Hp; ++n; srcb -= row_bytes; dz = (dz + 1 == pD) ? 0 : dz + 1; }
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b)
@@ -178,12 +207,14 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
             const int s = b_cnt % NB;
             if (!p.b_resident && b_cnt >= NB) mbar_wait(&b_empty[s], ((b_cnt / NB) - 1) & 1);
             const uint32_t dst0 = smem_u32(b_ring + s * L::kBTile) + rbase * 128 + b_sw;
-            const long long woff = static_cast<long long>(p.wtap[tp]) * p.cin + c * 64 + chunk * 8;
+            const int kd_w = p.pair ? 0 : c / cs;
+            const long long woff = p.pair ? (static_cast<long long>(c) * 9 + p.wtap[tp]) * 64 + chunk * 8
+                                          : (static_cast<long long>(p.wkd[kd_w]) * 9 + p.wtap[tp]) * p.cin + (c - kd_w * cs) * 64 + chunk * 8;
 #pragma unroll
             for (int i = 0; i < BN / 16; ++i) {
               const int n = n0 + rbase + 16 * i;
               const bool ok = n < p.nout;
-              const __nv_bfloat16* src = ok ? (p.b + static_cast<long long>(n) * p.wtaps * p.cin + woff) : p.b;
+              const __nv_bfloat16* src = ok ? (p.b + static_cast<long long>(n) * (p.pair ? 2 * 9 * 64 : p.wtaps * p.cin) + woff) : p.b;
               cp_async16(dst0 + i * 16 * 128, src, ok ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(&b_full[s]);
@@ -211,7 +242,9 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
               const int s = b_cnt % NB;
               if (!p.b_resident && b_cnt >= NB) mbar_wait(&b_empty[s], ((b_cnt / NB) - 1) & 1);
               mbar_arrive_expect_tx(&b_full[s], L::kBTile);
-              const int kx = p.wtap[tp] * p.cin + c * 64;
+              const int cs_w = p.pair ? 1 : p.cin / 64;
+              const int kd_w = p.pair ? 0 : c / cs_w;
+              const int kx = p.pair ? (c * 9 + p.wtap[tp]) * 64 : (p.wkd[kd_w] * 9 + p.wtap[tp]) * p.cin + (c - kd_w * cs_w) * 64;
               asm volatile(
                   "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
                       smem_u32(b_ring + s * L::kBTile)),
@@ -419,6 +452,10 @@ __global__ void __launch_bounds__(kC3Threads, MT == 1 ? 2 : 1) conv3x3_kernel(co
                 vv[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
               }
             }
+          }
+          if (p.bias_on) {  // Conv3d(bias=True): same value for every row of the tile (broadcast loads)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vv[j] += __ldg(p.bias + ncol + j);
           }
           uint32_t pk[16];
 #pragma unroll

@@ -246,6 +246,20 @@ __global__ void wpack_multi_kernel(const WpackItem* __restrict__ items, int nite
   const int local = b - it.first_block;
   wpack_tile(it.w, it.wf, it.wd, it.cout, it.cin, it.taps, it.co_tile, local % it.ci_tiles, local / it.ci_tiles, tile);
 }
+// Conv3d weights with 32 input channels [Cout][32][3][3][3] -> pair layout [Cout][2][9][64] for the slab kernel: K chunk
+// (item, tap) = [depth tap 2*item, 32 channels | depth tap 2*item + 1, 32 channels] (the missing fourth depth tap is zero).
+__global__ void wpack_conv3d_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout) {
+  const long long total = static_cast<long long>(Cout) * 2 * 9 * 64;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = i & 63;
+    const int tp = (i >> 6) % 9;
+    const int item = (i / (64 * 9)) & 1;
+    const long long co = i / (2 * 9 * 64);
+    const int kd = 2 * item + (k >> 5), ci = k & 31;
+    out[i] = __float2bfloat16_rn(kd < 3 ? w[(co * 32 + ci) * 27 + kd * 9 + tp] : 0.f);
+  }
+}
 // Stem 7x7x3 filter -> [Cout][8 row-taps][32 = (s, c4)] with zero padding (s == 7, c == 3, r == 7).
 __global__ void wpack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int Cin,
                                   int R, int S) {

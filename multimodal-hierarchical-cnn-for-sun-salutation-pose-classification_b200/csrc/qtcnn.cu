@@ -249,12 +249,19 @@ int fill_forward(IgemmParams& p, const qt_conv_desc* d) {
 bool g_use_conv3x3 = true;
 
 bool dense_nhwc(const long long* st, int d, int h, int w, int c) {
-  (void)d;
-  return st[3] == c && st[2] == static_cast<long long>(w) * c && st[0] == static_cast<long long>(h) * w * c;
+  if (d > 1 && st[1] != static_cast<long long>(h) * w * c) return false;
+  return st[3] == c && st[2] == static_cast<long long>(w) * c && st[0] == static_cast<long long>(d) * h * w * c;
+}
+// 3x3 (k_d == 1, one plane) or 3x3x3 (Conv3d) stride-1 pad-1 geometry of the slab kernels
+bool slab_geometry(const qt_conv_desc* d) {
+  if (d->k_h != 3 || d->k_w != 3 || d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1) return false;
+  if (d->k_d == 1) return d->in_d == 1 && d->pad_d == 0 && d->stride_d == 1;
+  return d->k_d == 3 && d->pad_d == 1 && d->stride_d == 1 && d->in_d >= 1;
 }
 
 struct C3Plan {
   bool ok;
+  int pair;  // cin == 32 Conv3d forward: two depth planes per 128-byte slab row (weights from qt_wpack_conv3d_pair)
   int bn, mt, nslab, nb, R, resident, staged;
   int num_m_tiles, num_n_tiles, V;
   size_t smem;
@@ -265,16 +272,19 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   C3Plan pl{};
   pl.ok = false;
   if (!g_use_conv3x3) return pl;
-  if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->pad_d != 0) return pl;
+  if (!slab_geometry(d)) return pl;
   if (d->groups != 1) return pl;
+  const bool is3d = d->k_d == 3;
+  if (is3d && g_tune[7] == 1) return pl;  // knob 7: Conv3d through the generic gather kernel
   if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
   // the producers advance 16 virtual pixels with ONE row carry and ONE image carry: needs 16/(W+2) < H+1 (fails for 2x2 maps)
   if (16 / (d->in_w + 2) >= d->in_h + 1) return pl;
-  if (cin % 64 || nout % 32) return pl;
-  if (flags & (EPI_BIAS | EPI_RELU | EPI_OUT_F32)) return pl;
-  if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
-  const long long V = static_cast<long long>(d->n) * (d->in_h + 1) * (d->in_w + 2);
+  pl.pair = (is3d && cin == 32 && !(flags & EPI_ADDEND)) ? 1 : 0;
+  if ((cin % 64 && !pl.pair) || nout % 32) return pl;
+  if (flags & (EPI_RELU | EPI_OUT_F32)) return pl;
+  if ((flags & EPI_BIAS) && !is3d) return pl;
+  if (!dense_nhwc(d->x_stride, d->in_d, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, d->in_d, d->in_h, d->in_w, d->out_c)) return pl;
+  const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.bn = nout <= 64 ? 64 : 128;
@@ -282,7 +292,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   const int bm = kBM * pl.mt;
   pl.R = ((bm + 2 * (d->in_w + 3)) + 7) / 8 * 8;
   const int slab_bytes = (pl.R * 128 + 1023) / 1024 * 1024;
-  const int slabs = cin / 64;
+  const int slabs = pl.pair ? 2 : d->k_d * (cin / 64);
   const int btile = pl.bn * 128;
   // staged (coalesced) write-out pays off on long image rows; on 14x14 / 7x7 maps the extra epilogue work costs more
   // than the scattered 16-byte stores (profiles/r01_conv_tuning.md). Knob 5: 1 never, 2 always.
@@ -295,7 +305,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (pl.bn == 64) {
     // try the resident-filter configuration (NB = 9, 64->64 layers)
     pl.nb = 9;
-    pl.resident = (slabs == 1 && pl.num_n_tiles == 1) ? 1 : 0;
+    pl.resident = (slabs == 1 && pl.num_n_tiles == 1 && !is3d) ? 1 : 0;
     pl.nslab = 3;
     if (fixed + pl.nb * btile + pl.nslab * slab_bytes > budget) pl.nslab = 2;
   } else {
@@ -350,7 +360,7 @@ int launch_conv3x3(Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
   alignas(64) CUtensorMap wmap;
   memset(&wmap, 0, sizeof(wmap));
   p.b_tma = (g_tune[6] == 0 && (reinterpret_cast<uintptr_t>(p.b) & 15) == 0 &&
-             make_weight_tmap(&wmap, p.b, p.nout, static_cast<long long>(p.wtaps) * p.cin, BN))
+             make_weight_tmap(&wmap, p.b, p.nout, p.pair ? 2LL * 9 * 64 : static_cast<long long>(p.wtaps) * p.cin, BN))
                 ? 1 : 0;
   conv3x3_kernel<BN, MT, NSLAB, NB, STAGED><<<grid, kC3Threads, smem, st>>>(p, wmap);
   return cuda_status("conv3x3_kernel");
@@ -358,7 +368,7 @@ int launch_conv3x3(Conv3x3Params& p, size_t smem, int grid, cudaStream_t st) {
 
 // taps: per filter tap the input offset (dh, dw) and its index in the weight tensor.
 int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, const void* a, const void* b, void* out,
-                const void* addend, float* stats, int flags, bool dgrad, cudaStream_t st) {
+                const void* addend, float* stats, int flags, bool dgrad, cudaStream_t st, const float* bias = nullptr) {
   Conv3x3Params p;
   memset(&p, 0, sizeof(p));
   p.a = static_cast<const __nv_bfloat16*>(a);
@@ -366,10 +376,17 @@ int run_conv3x3(const C3Plan& pl, const qt_conv_desc* d, int cin, int nout, cons
   p.out = out;
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.stats = stats;
-  p.N = d->n; p.H = d->in_h; p.W = d->in_w;
-  p.cin = cin; p.nout = nout; p.wtaps = 9;
+  p.N = d->n * d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.D = d->in_d; p.kdn = d->k_d; p.pair = pl.pair;
+  p.cin = cin; p.nout = nout; p.wtaps = 9 * d->k_d;
   p.flags = flags;
-  p.slabs = cin / 64;
+  p.bias_on = (flags & EPI_BIAS) ? 1 : 0;
+  p.bias = bias;
+  p.slabs = pl.pair ? 2 : d->k_d * (cin / 64);
+  for (int kd = 0; kd < 3; ++kd) {
+    p.dplane[kd] = static_cast<signed char>(d->k_d == 3 ? (dgrad ? 1 - kd : kd - 1) : 0);
+    p.wkd[kd] = static_cast<signed char>(d->k_d == 3 ? kd : 0);
+  }
   p.V = pl.V;
   p.num_m_tiles = pl.num_m_tiles; p.num_n_tiles = pl.num_n_tiles;
   p.R = pl.R; p.b_resident = pl.resident;
@@ -414,26 +431,27 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   W3Plan pl{};
   pl.ok = false;
   if (g_tune[3] != 0) return pl;
-  if (d->in_d != 1 || d->k_d != 1 || d->k_h != 3 || d->k_w != 3) return pl;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->pad_h != 1 || d->pad_w != 1 || d->groups != 1) return pl;
-  if (!dense_nhwc(d->x_stride, 1, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, 1, d->in_h, d->in_w, d->out_c)) return pl;
+  if (!slab_geometry(d) || d->groups != 1) return pl;
+  if (d->k_d == 3 && g_tune[7] == 1) return pl;
+  if (!dense_nhwc(d->x_stride, d->in_d, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, d->in_d, d->in_h, d->in_w, d->out_c)) return pl;
   if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
   if (16 / (d->in_w + 2) >= d->in_h + 1) return pl;  // single-carry coordinate advance (see plan_conv3x3)
-  if (d->in_c == 64 && d->out_c == 64) pl.cfg = 0;
+  if (d->in_c == 64 && d->out_c == 64 && d->k_d == 1) pl.cfg = 0;
   else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
+  else if (d->in_c == 64 && d->out_c % 128 == 0) pl.cfg = 2;  // 64 -> 128k (Conv3d block3): one 64-channel slab, 128-cout dy tiles
   else return pl;
-  const long long V = static_cast<long long>(d->n) * (d->in_h + 1) * (d->in_w + 2);
+  const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
   if (V > (1ll << 30)) return pl;
   pl.V = static_cast<int>(V);
   pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);
   pl.R = (kW3KP + 2 * (d->in_w + 3) + 7) / 8 * 8;
   // cfg 0 pairs horizontally adjacent taps in one MMA (wgrad3x3.cuh): 6 MMA groups cover all 9 taps in a single CTA
-  const int nslab = pl.cfg == 0 ? 1 : 2, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 4 : 2, taps = pl.cfg == 0 ? 9 : 3;
+  const int nslab = pl.cfg == 1 ? 2 : 1, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 4 : (pl.cfg == 1 ? 2 : 3), taps = pl.cfg == 0 ? 9 : 3;
   const int dy_rows = pl.cfg == 0 ? kW3KP + 8 : kW3KP;
   pl.cout_tiles = d->out_c / (64 * cb);
   pl.cin_groups = d->in_c / (64 * nslab);
   pl.tap_groups = (9 + taps - 1) / taps;
-  const int types = pl.cout_tiles * pl.cin_groups * pl.tap_groups;
+  const int types = pl.cout_tiles * pl.cin_groups * pl.tap_groups * d->k_d;
   int splits = kNumSMs / types;
   if (splits < 1) splits = 1;
   if (splits > pl.num_kt / 4) splits = pl.num_kt / 4;
@@ -443,7 +461,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   const size_t slab_bytes = static_cast<size_t>(nslab) * ((static_cast<size_t>(pl.R) * 128 + 1023) / 1024 * 1024);
   pl.smem = 1024 + stages * (static_cast<size_t>(cb) * dy_rows * 128 + slab_bytes) + 256;
   if (pl.smem > 227 * 1024) return pl;
-  pl.ws_bytes = static_cast<size_t>(pl.splits) * 9 * d->in_c * d->out_c * sizeof(float);
+  pl.ws_bytes = static_cast<size_t>(pl.splits) * 9 * d->k_d * d->in_c * d->out_c * sizeof(float);
   pl.ok = true;
   return pl;
 }
@@ -455,7 +473,7 @@ int launch_wgrad3x3(const Wgrad3x3Params& p, const W3Plan& pl, cudaStream_t st) 
     cudaFuncSetAttribute(wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     configured = pl.smem;
   }
-  dim3 grid(pl.cout_tiles * pl.cin_groups * pl.tap_groups, pl.splits);
+  dim3 grid(pl.cout_tiles * pl.cin_groups * pl.tap_groups, pl.splits, p.kdn);
   wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA><<<grid, 192, pl.smem, st>>>(p);
   return cuda_status("wgrad3x3_kernel");
 }
@@ -468,16 +486,19 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.dy = static_cast<const __nv_bfloat16*>(dy);
   p.ws = static_cast<float*>(ws);
-  p.N = d->n; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
+  p.N = d->n * d->in_d; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
+  p.D = d->in_d; p.kdn = d->k_d;
   p.V = pl.V; p.num_kt = pl.num_kt; p.kt_per_split = pl.kt_per_split;
   p.R = pl.R;
   p.cout_tiles = pl.cout_tiles; p.cin_groups = pl.cin_groups; p.tap_groups = pl.tap_groups;
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
     for (int kw = 0; kw < 3; ++kw, ++t) { p.off_h[t] = static_cast<signed char>(kh - 1); p.off_w[t] = static_cast<signed char>(kw - 1); }
-  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 6, 1, 4, 2>(p, pl, st) : launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st);
+  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 6, 1, 4, 2>(p, pl, st)
+                       : (pl.cfg == 1 ? launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st) : launch_wgrad3x3<1, 3, 2, 3, 2>(p, pl, st));
   if (rc) return rc;
-  launch_splitk_reduce_wgrad(p.ws, pl.splits, 9 * d->in_c, d->out_c, 9 * d->in_c, d->out_c, d->in_c, 9, dw, accumulate, st);
+  const int taps = 9 * d->k_d;
+  launch_splitk_reduce_wgrad(p.ws, pl.splits, taps * d->in_c, d->out_c, taps * d->in_c, d->out_c, d->in_c, taps, dw, accumulate, st);
   return cuda_status("splitk_reduce_wgrad_kernel");
 }
 
@@ -597,6 +618,11 @@ int qt_wpack_multi(const void* items_dev, int nitems, int total_blocks, int max_
   wpack_multi_kernel<<<total_blocks, 256, smem, S(stream)>>>(static_cast<const WpackItem*>(items_dev), nitems);
   return cuda_status("wpack_multi");
 }
+int qt_wpack_conv3d_pair(const float* w, void* wp, int cout, qt_stream_t stream) {
+  const long long total = static_cast<long long>(cout) * 2 * 9 * 64;
+  wpack_conv3d_pair_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wp), cout);
+  return cuda_status("wpack_conv3d_pair");
+}
 int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_stream_t stream) {
   if (cin > 4 || r > 8 || s > 8) return fail("wpack_stem: filter does not fit the 8x(8x4) packing");
   wpack_stem_kernel<<<grid_for(cout * 256, 256), 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(w8), cout, cin, r, s);
@@ -611,13 +637,16 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 /* which kernel a pass will use: 0 generic gather GEMM, 1 persistent slab kernel (conv3x3 / wgrad3x3) */
 int qt_conv_plan(const qt_conv_desc* d, int pass) {
   if (check_desc(d)) return -1;
-  if (pass == 0) return plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS).ok ? 1 : 0;
+  if (pass == 0) {
+    const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS | (d->k_d == 3 ? EPI_BIAS : 0));
+    return pl.ok ? (pl.pair ? 2 : 1) : 0;  // 2: slab kernel on pair-packed weights (qt_wpack_conv3d_pair)
+  }
   if (pass == 1) return plan_conv3x3(d, d->out_c, d->in_c, 0).ok ? 1 : 0;
   return plan_wgrad3x3(d).ok ? 1 : 0;
 }
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
-  const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS);
+  const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS | (d->k_d == 3 ? EPI_BIAS : 0));
   if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; return tiles < kNumSMs ? tiles : kNumSMs; }
   const OutDims o = conv_out_dims(d);
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
@@ -639,7 +668,7 @@ int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y,
   if ((p.flags & EPI_BIAS) && !bias) return fail("conv_fprop: QT_EPI_BIAS without bias");
   if ((p.flags & EPI_STATS) && !stats) return fail("conv_fprop: QT_EPI_STATS without stats buffer");
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, p.flags);
-  if (pl.ok) return run_conv3x3(pl, d, d->in_c, d->out_c, x, wf, y, nullptr, stats, p.flags, false, S(stream));
+  if (pl.ok) return run_conv3x3(pl, d, d->in_c, d->out_c, x, wf, y, nullptr, stats, p.flags, false, S(stream), bias);
   return run_kmajor(p, S(stream), ws, ws_bytes, 0);
 }
 

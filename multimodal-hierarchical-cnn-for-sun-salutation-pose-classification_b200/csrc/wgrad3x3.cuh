@@ -29,6 +29,9 @@ struct Wgrad3x3Params {
   int R;                     // slab rows (multiple of 8)
   int cout_tiles, cin_groups, tap_groups;
   signed char off_h[9], off_w[9];
+  // Conv3d (3x3x3 / s1 / p1): N counts depth planes (clips * D); blockIdx.z = depth tap kd, whose x slab is the plane
+  // kd - 1 away (zero outside the clip); partials land at tap index kd * 9 + tap of the [27 * cin][cout] workspace.
+  int D, kdn;
 };
 
 template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
@@ -96,7 +99,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     // loop-invariant kernel parameters in registers (the cp.async asm carries a memory clobber); real-pixel byte
     // offsets are kept incrementally: +16 virtual pixels = adv, a w-carry skips the 2 pad columns, an h-carry the
     // shared zero row
-    const int pW = p.W, pN = p.N, pR = p.R;
+    const int pW = p.W, pN = p.N, pR = p.R, pD = p.D;
+    const int dd = p.kdn > 1 ? static_cast<int>(blockIdx.z) - 1 : 0;  // source plane offset of this CTA's depth tap
     const long long dy_pix = static_cast<long long>(p.cout) * 2, x_pix = static_cast<long long>(p.cin) * 2;
     const long long dy_adv = (static_cast<long long>(adv_h) * pW + adv_w) * dy_pix, x_adv = (static_cast<long long>(adv_h) * pW + adv_w) * x_pix;
     const long long dy_row = pW * dy_pix, x_row = pW * x_pix;
@@ -135,20 +139,22 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
         }
       }
       {  // ---- x slab: row j <-> virtual pixel q0 - (W+3) + j
-        int n, hp, wp;
+        int n, hp, wp, dz;
         {
           const int vv = q0 - (pW + 3) + rbase + Wp * Hp;
           wp = vv % Wp;
           const int rest = vv / Wp;
           hp = rest % Hp;
           n = rest / Hp - 1;
+          dz = (n + pD) % pD;
         }
-        const char* src = x_c + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
+        const char* src = x_c + dd * (static_cast<long long>(p.H) * x_row) + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
         uint32_t dst = smem_u32(st + dy_bytes) + rbase * 128 + dsw;  // rows 16 apart keep the swizzle phase (row & 7)
 #pragma unroll 2
         for (int j = rbase; j < pR; j += 16) {
           const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(pN)) &&
-                          (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1);
+                          (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(pW)) && (hp >= 1) &&
+                          (static_cast<unsigned>(dz + dd) < static_cast<unsigned>(pD));
 #pragma unroll
           for (int sl = 0; sl < NSLAB; ++sl)
             cp_async16(dst + sl * xblk_bytes, ok ? static_cast<const void*>(src + sl * 128) : dummy_x, ok ? 16u : 0u);
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           src += x_adv;
           wp += adv_w; hp += adv_h;
           if (wp >= Wp) { wp -= Wp; ++hp; src -= 2 * x_pix; }
-          if (hp >= Hp) { hp -= Hp; ++n; src -= x_row; }
+          if (hp >= Hp) { hp -= Hp; ++n; src -= x_row; dz = (dz + 1 == pD) ? 0 : dz + 1; }
         }
       }
       // completion is tracked by the mbarrier itself (no wait_group): the producers run ahead by up to STAGES
@@ -220,7 +226,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       tc_fence_after();
     }
     const int crow = warp * 32 + lane;            // row of the 128-row accumulator
-    const long long Mpad = 9LL * p.cin;
+    const long long Mpad = 9LL * p.kdn * p.cin;
+    const int tap_base = p.kdn > 1 ? static_cast<int>(blockIdx.z) * 9 : 0;
     for (int tp = 0; tp < ntap; ++tp) {
       // PAIR: rows 0..63 of group tp belong to the tap the slab was started at, rows 64..127 (pair groups only) to its
       // left neighbour (kh, 1); otherwise row == cout and the accumulator is tap0 + tp
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tp * NCH + c0, r);
         tmem_ld_wait();
         if (row_ok) {
-          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap) * p.cin + cin0 + c0) * p.cout +
+          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap_base + tap) * p.cin + cin0 + c0) * p.cout +
                        cout0 + co;
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.cout] = nit > 0 ? __uint_as_float(r[j]) : 0.f;

@@ -321,19 +321,31 @@ class AttnPool(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------
 # Conv3d + BatchNorm3d + ReLU (+ MaxPool3d) block of Quadtree3DCNN (3dcnn/models.py:107-141)
 # ------------------------------------------------------------------------------------------------------------
-def _pad_cin(w, cin_pad):
-    """fp32 [cout, cin, taps...] -> [cout, cin_pad, taps] (zero channels) for cin = 3 -> 8."""
+def _conv3d_weights(w, cin_pad, need_dgrad, pair):
+    """bf16 GEMM operands of a Conv3d weight [cout, cin, 3, 3, 3], cached per parameter version (ops._entry): the forward
+    layout [cout][27][cin_pad] (or the pair layout [cout][2][9][64] of the 32-channel slab path) and, when the input needs a
+    gradient, the data-gradient layout [cin_pad][27][cout]. Channel-padded weights (cin = 3 -> 8) are packed from a padded
+    fp32 copy; everything else goes through ops.packed_* (and is refreshed by the optimizer kernel)."""
     cout, cin = w.shape[:2]
-    taps = w[0, 0].numel()
     if cin == cin_pad:
-        return w.detach().reshape(cout, cin, taps)
-    out = torch.zeros(cout, cin_pad, taps, device=w.device, dtype=w.dtype)
-    out[:, :cin] = w.detach().reshape(cout, cin, taps)
-    return out
+        wf = ops.packed_pair(w) if pair else ops.packed_fprop(w)
+        wd = ops.packed_dgrad(w) if need_dgrad else None
+        return wf, wd
+    e = ops._entry(w)
+    if getattr(e, "w8", None) is None:  # (the stem slot doubles as the cache of the padded pack)
+        wp = torch.zeros(cout, cin_pad, 27, device=w.device, dtype=torch.float32)
+        wp[:, :cin] = w.detach().reshape(cout, cin, 27)
+        wf = torch.empty(cout, 27, cin_pad, device=w.device, dtype=BF16)
+        check(L().qt_wpack_both(ptr(wp), ptr(wf), None, cout, cin_pad, 27, stream()), "wpack_both")
+        ops._count()
+        e.w8 = wf
+    return e.w8, None
 
 
 class Conv3dBnReluPool(torch.autograd.Function):
-    """x: NDHWC bf16 [N,D,H,W,Cin_pad] -> NDHWC bf16 after Conv3d(3x3x3, pad 1, bias) + BN3d(train/eval) + ReLU + pool."""
+    """x: NDHWC bf16 [N,D,H,W,Cin_pad] -> NDHWC bf16 after Conv3d(3x3x3, pad 1, bias) + BN3d(train/eval) + ReLU + pool
+    (3dcnn/models.py:107-141). Layers with 32 / 64k input channels run on the persistent slab kernels (conv3x3.cuh /
+    wgrad3x3.cuh with three depth taps); the 3-channel first layer is HBM bound and uses the gather kernel."""
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, bn_mod, pool, training):
@@ -341,11 +353,9 @@ class Conv3dBnReluPool(torch.autograd.Function):
         cout = w.shape[0]
         dev = x.device
         d = capi.conv_desc(n, (D, H, W), cin_pad, cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))
-        wp = _pad_cin(w, cin_pad)
-        wf = torch.empty(cout, 27, cin_pad, device=dev, dtype=BF16)
         need_x_grad = ctx.needs_input_grad[0]
-        wd = torch.empty(cin_pad, 27, cout, device=dev, dtype=BF16) if need_x_grad else None
-        check(L().qt_wpack_both(ptr(wp), ptr(wf), ptr(wd), cout, cin_pad, 27, stream()), "wpack_both")
+        pair = L().qt_conv_plan(d, 0) == 2
+        wf, wd = _conv3d_weights(w, cin_pad, need_x_grad, pair)
         y = torch.empty(n, D, H, W, cout, device=dev, dtype=BF16)
         stats = ops.conv_fprop(d, x, wf, y, bias=b.detach(), relu=False, want_stats=training)
         m = n * D * H * W
@@ -362,13 +372,13 @@ class Conv3dBnReluPool(torch.autograd.Function):
         else:
             out = a
         if any(ctx.needs_input_grad):
-            ctx.saved = (x, y, a, am, st, w, wd, gamma, d)
+            ctx.saved = (x, y, a, am, st, w, wd, gamma, beta, b, d)
             ctx.cfg = (pool, training, cin_pad)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, a, am, st, w, wd, gamma, d = ctx.saved
+        x, y, a, am, st, w, wd, gamma, beta, b, d = ctx.saved
         pool, training, cin_pad = ctx.cfg
         n, D, H, W, cout = y.shape
         dev = y.device
@@ -380,17 +390,21 @@ class Conv3dBnReluPool(torch.autograd.Function):
             ops._count()
         else:
             da = dout
-        dgamma, dbeta = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+        dgamma, dbeta = ops.grad_out(gamma), ops.grad_out(beta)
         dy = torch.empty_like(y)
         ops.bn_backward(da, a, y, st, gamma.detach(), dgamma, dbeta, dy, None, eval_mode=not training)
-        db = torch.empty(cout, device=dev)
+        db = ops.grad_out(b)
         ops.colsum(dy.view(-1, cout), db)  # conv bias before train-mode BN: analytically ~0, computed faithfully
         dw = None
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty(cout, cin_pad, 27, device=dev)
-            ops.conv_wgrad(d, x, dy, dwp)
             cin = w.shape[1]
-            dw = dwp[:, :cin].reshape(w.shape).contiguous()
+            if cin == cin_pad:
+                dw = ops.grad_out(w)
+                ops.conv_wgrad(d, x, dy, dw)
+            else:
+                dwp = torch.empty(cout, cin_pad, 27, device=dev)
+                ops.conv_wgrad(d, x, dy, dwp)
+                dw = dwp[:, :cin].reshape(w.shape).contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)

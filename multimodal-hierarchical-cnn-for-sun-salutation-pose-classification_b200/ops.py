@@ -235,6 +235,20 @@ def packed_dgrad(w: torch.Tensor) -> torch.Tensor:
     return e.wd
 
 
+def packed_pair(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [cout][2][9][64] pair layout of a 32-input-channel Conv3d weight (slab kernel, two depth planes per slab row);
+    kept in the entry's `w8` slot, re-made lazily after the parameter changes."""
+    e = _entry(w)
+    if e.w8 is None:
+        cout = w.shape[0]
+        if tuple(w.shape[1:]) != (32, 3, 3, 3):
+            raise RuntimeError("packed_pair: expects a [cout, 32, 3, 3, 3] Conv3d weight")
+        e.w8 = torch.empty(cout, 2, 9, 64, device=w.device, dtype=BF16)
+        check(L().qt_wpack_conv3d_pair(ptr(w.detach().contiguous()), ptr(e.w8), cout, stream()), "wpack_conv3d_pair")
+        _count()
+    return e.w8
+
+
 def packed_stem(w: torch.Tensor) -> torch.Tensor:
     e = _entry(w)
     if e.w8 is None:
@@ -281,9 +295,9 @@ def _fam(d, which, name):
     """Profiling family: the kernel the C dispatch will pick for this pass + the pass name."""
     if _prof is None:
         return name
-    slab = L().qt_conv_plan(d, which) == 1
+    slab = L().qt_conv_plan(d, which) >= 1
     kern = ("wgrad3x3_kernel" if which == 2 else "conv3x3_kernel") if slab else ("igemm_wgrad_kernel" if which == 2 else "igemm_kmajor_kernel")
-    return f"{kern}:{name}"
+    return f"{kern}{'[conv3d]' if d.k_d == 3 else ''}:{name}"
 
 
 def conv_out_hw(d) -> Tuple[int, int, int]:

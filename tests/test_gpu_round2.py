@@ -323,3 +323,88 @@ def test_lstm_dropout_between_layers(C):
     dn = Fn.lstm_forward(lstm, x)[:, -1, :].sum().item()
     fd = (up - dn) / (2 * eps)
     assert abs(fd - g) <= 2e-2 * max(1.0, abs(g)), (fd, g)
+
+
+# Conv3d layers of Quadtree3DCNN at the BASELINE config-4 shapes (16 x 112 x 112 clips; maps after the pools), B = 2:
+# (cin, cout, D, H, W, expected forward plan: 0 gather kernel, 1 slab kernel, 2 slab kernel in pair mode)
+CONV3D_SHAPES = [(8, 32, 16, 112, 112, 0), (32, 64, 16, 56, 56, 2), (64, 128, 8, 28, 28, 1), (128, 256, 4, 14, 14, 1),
+                 (256, 1024, 4, 7, 7, 1), (64, 64, 3, 5, 6, 1), (32, 32, 1, 4, 9, 2)]
+
+
+@pytest.mark.parametrize("cin,cout,D,H,W,plan", CONV3D_SHAPES)
+def test_conv3d_kernels(C, cin, cout, D, H, W, plan):
+    """Conv3d 3x3x3 / stride 1 / pad 1 forward (+bias, +BatchNorm partial sums), data gradient and weight gradient through
+    the C ABI against torch's fp32 conv3d on the same bf16-rounded operands (per-kernel contract of SURVEY §8d: bf16
+    outputs rel_L2 <= 4e-3, fp32 outputs <= 1e-4 ... weight gradients accumulate bf16 products in fp32)."""
+    from qtcnn_b200 import ops
+    lib = C.lib()
+    torch.backends.cudnn.allow_tf32 = False
+    n = 2
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+    x = torch.randn(n, cin, D, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / math.sqrt(27 * cin))
+    wb = w.to(torch.bfloat16).float()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    d = C.conv_desc(n, (D, H, W), cin, cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    assert lib.qt_conv_plan(d, 0) == plan
+    xr = x.float().requires_grad_(True)
+    wr = wb.clone().requires_grad_(True)
+    ref = F.conv3d(xr, wr, bias, padding=1)
+    xn = x.permute(0, 2, 3, 4, 1).contiguous()
+    wparam = torch.nn.Parameter(wb.clone())
+    with torch.enable_grad():
+        wf = ops.packed_pair(wparam) if plan == 2 else ops.packed_fprop(wparam)
+        wd = ops.packed_dgrad(wparam)
+    y = torch.full((n, D, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = ops.conv_fprop(d, xn, wf, y, bias=bias, want_stats=True)
+    yf = y.permute(0, 4, 1, 2, 3).float()
+    rel = float((yf - ref).norm() / ref.norm())
+    assert rel <= 4e-3, rel
+    assert float((yf - ref.detach()).abs().max()) <= 2 ** -7 * float(ref.abs().max())
+    # BatchNorm partial sums of the stored (rounded) values
+    s = stats.double().sum(0)
+    ysum = y.float().double().reshape(-1, cout)
+    assert float((s[0] - ysum.sum(0)).abs().max()) <= 1e-3 * float(ysum.abs().sum(0).max())
+    assert float((s[1] - (ysum * ysum).sum(0)).abs().max()) <= 1e-3 * float((ysum * ysum).sum(0).max())
+    # backward
+    dy = torch.randn(ref.shape, device="cuda", generator=g).to(torch.bfloat16)
+    ref.backward(dy.float())
+    dyn = dy.permute(0, 2, 3, 4, 1).contiguous()
+    if cin >= 32:
+        dx = torch.full_like(xn, float("nan"))
+        ops.conv_dgrad(d, dyn, wd, dx)
+        dxf = dx.permute(0, 4, 1, 2, 3).float()
+        rel = float((dxf - xr.grad).norm() / xr.grad.norm())
+        assert rel <= 4e-3, rel
+    dw = torch.full((cout, cin, 27), float("nan"), device="cuda")
+    ops.conv_wgrad(d, xn, dyn, dw)
+    rel = float((dw.view_as(wr.grad) - wr.grad).norm() / wr.grad.norm())
+    assert rel <= 1e-4 * math.sqrt(D * H * W / 49.0) + 2e-4, rel  # fp32 accumulation of n*D*H*W bf16 products
+    assert lib.qt_take_timeout_flag() == 0
+
+
+def test_quadtree3d_full_clip_size(C):
+    """Quadtree3DCNN at the BASELINE config-4 clip size (16 x 112 x 112, B = 2) against the oracle with the autocast-relative
+    gradient contract (tests/parity.py) — the slab Conv3d kernels, the LSTM kernels and the fused loss path together."""
+    import parity
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import models as M
+    p = O.make_params("quadtree3d", 8, seed=6, mode="quadtree_3d_fusion")
+    clips, numerical, labels = O.synthetic_batch(2, 11, seq_len=16, clip_size=112)
+    model = M.Quadtree3DCNN(num_classes=8, sequence_length=16, dropout_rate=0.0)
+    model.numerical_lstm.dropout = 0.0
+    load_oracle_params(model, p)
+    model = model.cuda().train()
+    (ref_logits, ref_loss, ref_g, _), (_, _, ac_g, _) = parity.oracle_fp32_and_autocast(O, "quadtree3d", p, (clips, numerical), labels,
+                                                                                     mode="quadtree_3d_fusion")
+    logits = model(clips.cuda(), numerical.cuda())
+    loss = F.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    parity.assert_logits_loss(logits, loss.detach(), ref_logits, ref_loss)
+    report, checked = [], 0
+    for name, prm in model.named_parameters():
+        if name in ref_g:
+            assert prm.grad is not None, name
+            checked += parity.assert_grad(name, prm.grad, ref_g[name], ac_g[name], report)
+    parity.print_worst(report)
+    assert checked >= 20
