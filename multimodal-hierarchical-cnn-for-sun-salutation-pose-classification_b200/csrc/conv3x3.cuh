@@ -61,7 +61,7 @@ template <int BN, int MT, int NSLAB, int NB, bool STAGED>
 struct C3Smem {
   static constexpr int kBTile = BN * 128;
   static constexpr int kBBytes = NB * kBTile;
-  static constexpr int kScratch = 2 * 4 * BN * 4 + 4 * 2 * BN * 4;  // cross-warp combine + running sums (<= 4 n-tiles)
+  static constexpr int kScratch = 2 * 4 * BN * 4 + 8 * 2 * BN * 4;  // cross-warp combine + running sums (<= 8 n-tiles)
   static constexpr int kStage = STAGED ? 4 * 32 * 64 : 0;  // per epilogue warp: 32 rows x 64 B output staging (coalesced write-out)
   static constexpr int kBarBytes = 1024;  // keeps the slabs 1024-byte aligned
   // slab bytes depend on W (runtime): computed on the host; layout = [B ring][scratch][staging][barriers][slabs...]

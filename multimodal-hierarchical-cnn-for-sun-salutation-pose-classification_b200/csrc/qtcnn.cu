@@ -268,7 +268,7 @@ struct C3Plan {
 };
 
 // cin/nout are the GEMM-side channel counts (swapped for dgrad).
-C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
+C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags, bool dgrad = false) {
   C3Plan pl{};
   pl.ok = false;
   if (!g_use_conv3x3) return pl;
@@ -279,7 +279,7 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   if (d->in_w < 10 && g_tune[4] == 1) return pl;  // knob 4: send small maps (7x7) to the gather kernel instead
   // the producers advance 16 virtual pixels with ONE row carry and ONE image carry: needs 16/(W+2) < H+1 (fails for 2x2 maps)
   if (16 / (d->in_w + 2) >= d->in_h + 1) return pl;
-  pl.pair = (is3d && cin == 32 && !(flags & EPI_ADDEND)) ? 1 : 0;
+  pl.pair = (is3d && cin == 32 && !dgrad) ? 1 : 0;  // forward only: the pair-packed operand exists for the forward weights
   if ((cin % 64 && !pl.pair) || nout % 32) return pl;
   if (flags & (EPI_RELU | EPI_OUT_F32)) return pl;
   if ((flags & EPI_BIAS) && !is3d) return pl;
@@ -297,8 +297,8 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags) {
   // staged (coalesced) write-out pays off on long image rows; on 14x14 / 7x7 maps the extra epilogue work costs more
   // than the scattered 16-byte stores (profiles/r01_conv_tuning.md). Knob 5: 1 never, 2 always.
   pl.staged = (g_tune[5] == 1) ? 0 : (g_tune[5] == 2 ? 1 : (d->in_w >= 20 ? 1 : 0));
-  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 4 * 2 * pl.bn * 4) + (pl.staged ? 4 * 32 * 64 : 0) + 1024;  // align slack + scratch + staging + barriers
-  if ((nout + pl.bn - 1) / pl.bn > 4) return pl;
+  const int fixed = 1024 + (2 * 4 * pl.bn * 4 + 8 * 2 * pl.bn * 4) + (pl.staged ? 4 * 32 * 64 : 0) + 1024;  // align slack + scratch + staging + barriers
+  if ((nout + pl.bn - 1) / pl.bn > 8) return pl;
   const int budget = 227 * 1024;
   pl.num_m_tiles = static_cast<int>((V + bm - 1) / bm);
   pl.num_n_tiles = (nout + pl.bn - 1) / pl.bn;
@@ -641,7 +641,7 @@ int qt_conv_plan(const qt_conv_desc* d, int pass) {
     const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS | (d->k_d == 3 ? EPI_BIAS : 0));
     return pl.ok ? (pl.pair ? 2 : 1) : 0;  // 2: slab kernel on pair-packed weights (qt_wpack_conv3d_pair)
   }
-  if (pass == 1) return plan_conv3x3(d, d->out_c, d->in_c, 0).ok ? 1 : 0;
+  if (pass == 1) return plan_conv3x3(d, d->out_c, d->in_c, 0, true).ok ? 1 : 0;
   return plan_wgrad3x3(d).ok ? 1 : 0;
 }
 int qt_conv_stat_rows(const qt_conv_desc* d) {
@@ -679,7 +679,7 @@ int qt_conv_dgrad(const qt_conv_desc* d, const void* dy, const void* wd, void* d
   const int sd = d->stride_d, sh = d->stride_h, sw = d->stride_w;
   if (ilog2_exact(d->out_c) < 0 && d->k_d * d->k_h * d->k_w > 1) return fail("conv_dgrad: out_c must be a power of two");
   {
-    const C3Plan pl = plan_conv3x3(d, d->out_c, d->in_c, accumulate ? EPI_ADDEND : 0);
+    const C3Plan pl = plan_conv3x3(d, d->out_c, d->in_c, accumulate ? EPI_ADDEND : 0, true);
     if (pl.ok)
       return run_conv3x3(pl, d, d->out_c, d->in_c, dy, wd, dx, accumulate ? dx : nullptr, nullptr, accumulate ? EPI_ADDEND : 0,
                          true, S(stream));

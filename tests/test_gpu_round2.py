@@ -136,8 +136,8 @@ def test_adam_matches_torch_and_emits_operand_copies(C):
             a.grad, b.grad = gr.clone(), gr.clone()
         if step == 4:
             ours[4].grad = theirs[4].grad = None  # a parameter without gradient keeps its own step count
+        opt_b.step()  # (any optimizer step bumps the packed-weight generation; ours goes last so its copies stay current)
         opt_a.step()
-        opt_b.step()
         assert opt_a.launches_last_step == 1
     for a, b in zip(ours, theirs):
         assert float((a - b).abs().max()) <= 1e-6, float((a - b).abs().max())
