@@ -239,6 +239,8 @@ def make_workload(name, batch, dev, world=1, rank=0):
         params = [p for p in model.parameters() if p.requires_grad]
         # optim.Adam(model.parameters(), lr, weight_decay) of the scripts as ONE multi-tensor launch per step
         w["opt"] = optim.Adam(params, **hyper)
+        if w["dp"] is not None and os.environ.get("QTCNN_DP_AVG", "") != "1":
+            w["dp"].attach(w["opt"])  # SUM all-reduce (NVLS-capable), 1/world applied inside the Adam kernel
         w["optimizer"] = f"qtcnn_b200.optim.Adam (multi-tensor kernel, torch.optim.Adam semantics), {hyper}"
     crit = QL.CrossEntropyLoss()
     opt, dp = w["opt"], w["dp"]

@@ -263,19 +263,20 @@ typedef struct qt_adam_item {
 } qt_adam_item;
 /* returns the item's block count (or -1); first_block = running sum of the counts, table copied to device memory */
 int qt_adam_item_plan(qt_adam_item* item);
-/* clip_coef: device scalar multiplied into every gradient (from qt_grad_clip_coef), or NULL */
+/* clip_coef: device scalar multiplied into every gradient (from qt_grad_clip_coef), or NULL; grad_scale: host scalar
+ * multiplied into every gradient as well (1/world after a SUM all-reduce of the gradients, else 1) */
 int qt_adam_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, const qt_adam_group* groups, int ngroups,
-                  const float* clip_coef, qt_stream_t stream);
+                  const float* clip_coef, float grad_scale, qt_stream_t stream);
 typedef struct qt_norm_item {
   const float* g;
   long long n;
   int first_block, pad;
 } qt_norm_item;
 int qt_grad_norm_blocks(long long n);
-/* total_norm = ||all gradients||_2 (fixed-order reduction), coef = min(1, max_norm / (total_norm + 1e-6));
+/* total_norm = grad_scale * ||all gradients||_2 (fixed-order reduction), coef = min(1, max_norm / (total_norm + 1e-6));
  * partial: fp32 scratch [total_blocks]. */
-int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float* partial, float* total_norm,
-                      float* coef, qt_stream_t stream);
+int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float grad_scale, float* partial,
+                      float* total_norm, float* coef, qt_stream_t stream);
 
 
 /* ---- nn.LSTM(batch_first=True) layers (3dcnn/models.py:144-158,200-203; cnn+lstm/models.py:43-49,82-85) ---------------- */

@@ -116,9 +116,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qt_lstm_layer_bwd": (c_int, [c_void_p, c_float, c_ulonglong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qt_adam_item_plan": (c_int, [ctypes.POINTER(AdamItem)]),
-    "qt_adam_multi": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdamGroup), c_int, c_void_p, c_void_p]),
+    "qt_adam_multi": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdamGroup), c_int, c_void_p, c_float, c_void_p]),
     "qt_grad_norm_blocks": (c_int, [c_longlong]),
-    "qt_grad_clip_coef": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qt_grad_clip_coef": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qt_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p]),
     "qt_wpack_fprop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

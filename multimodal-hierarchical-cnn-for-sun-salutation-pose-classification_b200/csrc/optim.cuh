@@ -20,6 +20,7 @@ struct AdamGroup {  // one torch param_group; step-dependent factors are folded 
 constexpr int kAdamMaxGroups = 8;
 struct AdamGroups {
   AdamGroup g[kAdamMaxGroups];
+  float grad_scale;  // every gradient is multiplied by this first (1/world after a SUM all-reduce; 1 otherwise)
 };
 struct AdamItem {
   float* p;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamItem* __restr
   extern __shared__ float tile[];
   const AdamItem it = items[find_item(items, nitems, blockIdx.x)];
   const AdamGroup G = groups.g[it.group];
-  const float cc = clip ? *clip : 1.f;
+  const float cc = (clip ? *clip : 1.f) * groups.grad_scale;
   const int local = blockIdx.x - it.first_block;
   if (it.wf) {
     adam_pack_tile(it, G, cc, local % it.ci_tiles, local / it.ci_tiles, tile);
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(256) grad_sqnorm_multi_kernel(const NormItem* 
 }
 // total_norm = sqrt(sum partial); coef = min(1, max_norm / (total_norm + 1e-6)) (clip_grad_norm_'s clamp).
 __global__ void __launch_bounds__(256) grad_clip_coef_kernel(const float* __restrict__ partial, int n, float max_norm,
-                                                             float* __restrict__ total_norm, float* __restrict__ coef) {
+                                                             float grad_scale, float* __restrict__ total_norm,
+                                                             float* __restrict__ coef) {
   __shared__ double sh[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) acc += static_cast<double>(partial[i]);
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256) grad_clip_coef_kernel(const float* __rest
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float tn = static_cast<float>(sqrt(sh[0]));
+    const float tn = static_cast<float>(sqrt(sh[0])) * grad_scale;  // norm of the gradients as the optimizer will see them
     *total_norm = tn;
     const float c = max_norm / (tn + 1e-6f);
     *coef = c < 1.f ? c : 1.f;

@@ -1320,26 +1320,27 @@ int qt_adam_item_plan(qt_adam_item* item) {
   return static_cast<int>(blocks);
 }
 int qt_adam_multi(const void* items_dev, int nitems, int total_blocks, int max_taps, const qt_adam_group* groups, int ngroups,
-                  const float* clip_coef, qt_stream_t stream) {
+                  const float* clip_coef, float grad_scale, qt_stream_t stream) {
   if (nitems < 1 || total_blocks < 1) return 0;
   if (ngroups < 1 || ngroups > kAdamMaxGroups) return fail("adam_multi: 1..%d parameter groups", kAdamMaxGroups);
   if (max_taps < 1 || max_taps > 32) return fail("adam_multi: taps must be 1..32");
   AdamGroups g;
   memset(&g, 0, sizeof(g));
   memcpy(g.g, groups, sizeof(AdamGroup) * ngroups);
+  g.grad_scale = grad_scale;
   size_t smem = wpack_smem(1);
   for (int t = 2; t <= max_taps; ++t) smem = wpack_smem(t) > smem ? wpack_smem(t) : smem;
   adam_multi_kernel<<<total_blocks, 256, smem, S(stream)>>>(static_cast<const AdamItem*>(items_dev), nitems, g, clip_coef);
   return cuda_status("adam_multi");
 }
 int qt_grad_norm_blocks(long long n) { return static_cast<int>((n + kAdamElemsPerBlock - 1) / kAdamElemsPerBlock); }
-int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float* partial, float* total_norm,
-                      float* coef, qt_stream_t stream) {
+int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float max_norm, float grad_scale, float* partial,
+                      float* total_norm, float* coef, qt_stream_t stream) {
   static_assert(sizeof(qt_norm_item) == sizeof(NormItem), "qt_norm_item layout");
   if (nitems < 1 || total_blocks < 1) return fail("grad_clip_coef: no gradients");
   grad_sqnorm_multi_kernel<<<total_blocks, 256, 0, S(stream)>>>(static_cast<const NormItem*>(items_dev), nitems, partial);
   if (int rc = cuda_status("grad_sqnorm_multi")) return rc;
-  grad_clip_coef_kernel<<<1, 256, 0, S(stream)>>>(partial, total_blocks, max_norm, total_norm, coef);
+  grad_clip_coef_kernel<<<1, 256, 0, S(stream)>>>(partial, total_blocks, max_norm, grad_scale, total_norm, coef);
   return cuda_status("grad_clip_coef");
 }
 

@@ -54,6 +54,7 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._table = _DeviceTable()
         self._pending_clip = None  # device scalar set by clip_grad_norm_(..., optimizer=self)
+        self.grad_scale = 1.0      # multiplied into every gradient inside the kernel (parallel.DataParallelGrads.attach: 1/world)
         self.launches_last_step = 0
 
     @torch.no_grad()
@@ -125,7 +126,7 @@ class Adam(torch.optim.Optimizer):
         table = self._table.update(tuple(key), arr, device)
         clip = self._pending_clip
         self._pending_clip = None
-        check(L.qt_adam_multi(ptr(table), len(todo), first, max_taps, garr, len(eff_groups), ptr(clip), stream()), "adam_multi")
+        check(L.qt_adam_multi(ptr(table), len(todo), first, max_taps, garr, len(eff_groups), ptr(clip), float(self.grad_scale), stream()), "adam_multi")
         ops._count()
         self.launches_last_step = 1
         # the bf16 GEMM copies were rewritten by the same launch: mark them fresh for the generation the optimizer
@@ -169,7 +170,8 @@ def clip_grad_norm_(parameters: Iterable[torch.Tensor], max_norm: float, norm_ty
     table = tbl.update(tuple((a.g, a.n) for a in arr), arr, device)
     out = torch.empty(2, device=device, dtype=torch.float32)  # [total_norm, coef]
     partial = ops.workspace(4 * first, device, "gradnorm")
-    check(L.qt_grad_clip_coef(ptr(table), len(grads), first, float(max_norm), ptr(partial), out.data_ptr(), out.data_ptr() + 4,
+    gscale = float(optimizer.grad_scale) if isinstance(optimizer, Adam) else 1.0
+    check(L.qt_grad_clip_coef(ptr(table), len(grads), first, float(max_norm), gscale, ptr(partial), out.data_ptr(), out.data_ptr() + 4,
                               stream()), "grad_clip_coef")
     ops._count(2)
     if optimizer is not None:

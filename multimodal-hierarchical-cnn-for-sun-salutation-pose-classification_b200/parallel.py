@@ -59,6 +59,7 @@ class DataParallelGrads:
         self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.collectives_last_step = 0
         self.avg = dist.get_backend() == "nccl"  # gloo has no AVG
+        self._scaled_by = None  # optimizer that applies the 1/world factor (attach)
         self._sync = True
 
     # ------------------------------------------------------------------------------------------
@@ -79,6 +80,16 @@ class DataParallelGrads:
             for p in b.params:
                 self.bucket_of[p] = b
                 ops.register_grad_view(p, b.views[p])
+
+    def attach(self, optimizer):
+        """Let `optimizer` (qtcnn_b200.optim.Adam) apply the 1/world factor inside its update kernel: the buckets are then
+        all-reduced with SUM — the one fp32 reduction NVSwitch can do in the switch (NVLS; NCCL offers no in-switch AVG) — and
+        `p.grad` holds the SUM over ranks between finish() and step()."""
+        if not hasattr(optimizer, "grad_scale"):
+            raise TypeError("attach() needs an optimizer with a grad_scale attribute (qtcnn_b200.optim.Adam)")
+        optimizer.grad_scale = 1.0 / self.world
+        self._scaled_by = optimizer
+        return self
 
     def no_sync(self):
         """Context manager for gradient accumulation: backward passes inside it only accumulate into `p.grad` (the
@@ -111,7 +122,8 @@ class DataParallelGrads:
                                "wrap all but the last micro-batch backward in `with dp.no_sync():`")
         b.pending -= 1
         if b.pending == 0:
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True)
+            op = dist.ReduceOp.AVG if (self.avg and self._scaled_by is None) else dist.ReduceOp.SUM
+            b.work = dist.all_reduce(b.flat, op=op, async_op=True)
 
     def finish(self):
         """Call after backward(), before optimizer.step()."""
@@ -120,7 +132,8 @@ class DataParallelGrads:
             # first step: plain per-tensor all-reduce, then freeze the bucket plan
             for p in self._order:
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.div_(self.world)
+                if self._scaled_by is None:
+                    p.grad.div_(self.world)
                 n += 1
             self._build_buckets()
         else:
@@ -129,7 +142,7 @@ class DataParallelGrads:
                     raise RuntimeError("DataParallelGrads: a bucket did not fill; the set of parameters receiving "
                                        "gradients changed after the first step")
                 b.work.wait()
-                if not self.avg:
+                if not self.avg and self._scaled_by is None:
                     b.flat.div_(self.world)
                 b.work = None
                 b.pending = len(b.params)
