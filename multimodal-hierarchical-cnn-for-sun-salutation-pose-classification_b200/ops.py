@@ -484,7 +484,10 @@ def grad_out(p: torch.Tensor) -> torch.Tensor:
     the view instead of a kernel overwriting it and the sum doubling."""
     v = _grad_views.get(p)
     if v is not None and getattr(p, "grad", None) is None:
-        return v
+        # a FRESH tensor object over the bucket storage: autograd's AccumulateGrad only adopts ("steals") a gradient whose
+        # TensorImpl nobody else references; handing out the registered view object itself made it clone the gradient and
+        # the hook copy it back — two device copies per parameter per step (round 1's hidden data-parallel overhead)
+        return v.detach()
     return torch.empty_like(p, memory_format=torch.contiguous_format)
 
 

@@ -35,12 +35,17 @@ class _Bucket:
 
 
 class DataParallelGrads:
-    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 25 << 20, broadcast: bool = True):
+    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 25 << 20, broadcast: bool = True, overlap: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("DataParallelGrads needs an initialised process group")
         self.model = model
         self.world = dist.get_world_size()
         self.bucket_bytes = bucket_bytes
+        # overlap=True: a bucket's all-reduce starts from the hook of its last gradient and runs beside the rest of backward.
+        # overlap=False: all buckets are reduced in finish(), after backward. The persistent conv kernels own every SM (one
+        # 223 KB CTA each), so a concurrent NCCL kernel takes SMs away from them and stretches those launches; measured on
+        # B200 the exposed all-reduce (NVLink 5: ~0.3 ms for 104 MB) costs less than the interference (profiles/r02_scaling.md).
+        self.overlap = overlap
         self.params = []
         seen = set()
         for p in model.parameters():
@@ -121,9 +126,11 @@ class DataParallelGrads:
             raise RuntimeError("DataParallelGrads: a second backward reached an already reduced bucket before finish(); "
                                "wrap all but the last micro-batch backward in `with dp.no_sync():`")
         b.pending -= 1
-        if b.pending == 0:
-            op = dist.ReduceOp.AVG if (self.avg and self._scaled_by is None) else dist.ReduceOp.SUM
-            b.work = dist.all_reduce(b.flat, op=op, async_op=True)
+        if b.pending == 0 and self.overlap:
+            b.work = dist.all_reduce(b.flat, op=self._op(), async_op=True)
+
+    def _op(self):
+        return dist.ReduceOp.AVG if (self.avg and self._scaled_by is None) else dist.ReduceOp.SUM
 
     def finish(self):
         """Call after backward(), before optimizer.step()."""
@@ -141,6 +148,9 @@ class DataParallelGrads:
                 if b.pending != 0:
                     raise RuntimeError("DataParallelGrads: a bucket did not fill; the set of parameters receiving "
                                        "gradients changed after the first step")
+                if b.work is None:  # overlap=False: every bucket is reduced here, back to back
+                    b.work = dist.all_reduce(b.flat, op=self._op(), async_op=True)
+            for b in self.buckets:
                 b.work.wait()
                 if not self.avg and self._scaled_by is None:
                     b.flat.div_(self.world)
