@@ -235,7 +235,7 @@ def make_workload(name, batch, dev, world=1, rank=0):
         raise ValueError(name)
     w["model"] = model
     if hyper is not None:
-        w["dp"] = parallel.DataParallelGrads(model, overlap=os.environ.get("QTCNN_DP_OVERLAP", "0") == "1") if world > 1 else None
+        w["dp"] = parallel.DataParallelGrads(model, overlap=os.environ.get("QTCNN_DP_OVERLAP", "1") == "1") if world > 1 else None
         params = [p for p in model.parameters() if p.requires_grad]
         # optim.Adam(model.parameters(), lr, weight_decay) of the scripts as ONE multi-tensor launch per step
         w["opt"] = optim.Adam(params, **hyper)
