@@ -125,6 +125,12 @@ int qt_conv_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* d
 int qt_stem_stat_rows(int n, int h, int w);
 int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, int h, int w, int cout,
                   qt_stream_t stream);
+/* r3d_18 stem (3dcnn/models.py:224,268 -> torchvision video/resnet.py BasicStem: Conv3d(3,64,(3,7,7), stride (1,2,2), pad (1,3,3)))
+ * on packed frames [n*t][h+7][w+8][4] (qt_stem_pack_input_ex per frame) with weights [cout][3][8][32] (qt_wpack_stem per depth
+ * tap); y is NDHWC bf16 [n][t][h/2][w/2][cout]. The reference keeps this stem frozen: forward only. */
+int qt_stem3d_stat_rows(int n, int t, int h, int w);
+int qt_stem3d_fprop(const void* xp, const void* w24, void* y, float* stats, int n, int t, int h, int w, int cout,
+                    qt_stream_t stream);
 size_t qt_stem_wgrad_workspace_bytes(int n, int h, int w, int cout);
 int qt_stem_wgrad(const void* xp, const void* dy, float* dw, int accumulate, int n, int h, int w, int cout, int cin,
                   void* ws, size_t ws_bytes, qt_stream_t stream);

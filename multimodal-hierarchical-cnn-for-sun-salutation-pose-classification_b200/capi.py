@@ -140,6 +140,8 @@ _SIGNATURES = {
                               c_void_p]),
     "qt_stem_stat_rows": (c_int, [c_int, c_int, c_int]),
     "qt_stem_fprop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "qt_stem3d_stat_rows": (c_int, [c_int, c_int, c_int, c_int]),
+    "qt_stem3d_fprop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_stem_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "qt_stem_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_size_t, c_void_p]),

@@ -820,6 +820,44 @@ int qt_stem_fprop(const void* xp, const void* w8, void* y, float* stats, int n, 
   p.flags = stats ? EPI_STATS : 0;
   return run_kmajor(p, S(stream), nullptr, 0, 0);
 }
+/* r3d_18 stem (torchvision video/resnet.py BasicStem: Conv3d(3, 64, (3,7,7), stride (1,2,2), pad (1,3,3), no bias)) on the packed
+ * frames [n*t][h+7][w+8][4]: the 7x7 part is the 8-row x (8 pixels x 4 channels) form of the 2-D stem, the three depth taps
+ * are whole-frame shifts with zero fill outside the clip -> a 24-tap x 32-"channel" gather GEMM. */
+int qt_stem3d_stat_rows(int n, int t, int h, int w) {
+  return static_cast<int>((static_cast<long long>(n) * t * (h / 2) * (w / 2) + kBM - 1) / kBM);
+}
+int qt_stem3d_fprop(const void* xp, const void* w24, void* y, float* stats, int n, int t, int h, int w, int cout,
+                    qt_stream_t stream) {
+  if (h % 2 || w % 2) return fail("stem3d: even frame sizes only");
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Hp = h + 7, Wp = w + 8;
+  const long long frame = static_cast<long long>(Hp) * Wp * 4;
+  p.av = {frame * t, frame, static_cast<long long>(Wp) * 4, 4};
+  p.id = t; p.ih = Hp; p.iw = Wp;  // the packed frames already hold the spatial zero padding; depth padding = zero fill
+  p.nb = n; p.od = t; p.oh = h / 2; p.ow = w / 2;
+  p.mult_d = 1; p.mult_h = 2; p.mult_w = 2;
+  p.ntaps = 24; p.wtaps = 24; p.cin = 32; p.cin_log2 = 5;
+  for (int kd = 0; kd < 3; ++kd)
+    for (int r = 0; r < 8; ++r) {
+      const int tp = kd * 8 + r;
+      p.off_d[tp] = static_cast<signed char>(kd - 1);
+      p.off_h[tp] = static_cast<signed char>(r);
+      p.off_w[tp] = 0;
+      p.wtap[tp] = static_cast<short>(tp);
+    }
+  p.nout = cout;
+  const long long ohw = static_cast<long long>(p.oh) * p.ow;
+  p.ov = {ohw * t * cout, ohw * cout, static_cast<long long>(p.ow) * cout, cout};
+  p.M = n * t * p.oh * p.ow;
+  p.groups = 1;
+  p.a = static_cast<const __nv_bfloat16*>(xp);
+  p.b = static_cast<const __nv_bfloat16*>(w24);
+  p.out = y;
+  p.stats = stats;
+  p.flags = stats ? EPI_STATS : 0;
+  return run_kmajor(p, S(stream), nullptr, 0, 0);
+}
 size_t qt_stem_wgrad_workspace_bytes(int n, int h, int w, int cout) {
   const size_t generic = wgrad_ws_bytes(256, cout, 1, static_cast<long long>(n) * (h / 2) * (w / 2), nullptr) +
                          static_cast<size_t>(cout) * 256 * sizeof(float);

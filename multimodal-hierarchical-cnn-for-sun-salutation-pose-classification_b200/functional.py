@@ -162,7 +162,7 @@ class LinearTC(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             ctx.saved = (x16, w, out)
             ctx.cfg = (relu, p, seed)
-        return out
+        return out.view(out.shape)  # not the saved object itself (no ctx <-> output reference cycle)
 
     @staticmethod
     def backward(ctx, dout):
@@ -370,7 +370,10 @@ class Conv3dBnReluPool(torch.autograd.Function):
             check(L().qt_maxpool3d_fwd(ptr(a), ptr(out), ptr(am), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_fwd")
             ops._count(2)
         else:
-            out = a
+            # a distinct tensor object: returning `a` itself would make ctx.saved reference the Function's own output
+            # (output -> grad_fn -> ctx -> saved -> output), a cycle only Python's GC can break — the whole step's
+            # activations would stay allocated until it runs
+            out = a.view(a.shape)
         if any(ctx.needs_input_grad):
             ctx.saved = (x, y, a, am, st, w, wd, gamma, beta, b, d)
             ctx.cfg = (pool, training, cin_pad)

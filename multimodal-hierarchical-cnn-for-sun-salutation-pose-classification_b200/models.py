@@ -122,31 +122,37 @@ class _StemFn(torch.autograd.Function):
 class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, wd, gd, bd, blk, training):
+        """blk: (bn1 module, bn2 module, downsample-bn module | None, stride, downsample kernel, stride, padding). 4-D inputs
+        are torchvision's 2-D BasicBlock (resnet.py:59-105), 5-D inputs the video BasicBlock of r3d_18 (video/resnet.py)."""
         _require_cuda(x, "BasicBlock")
-        xb = ops.as_nhwc(x)
-        n, h, w, cin = xb.shape
+        bn1_mod, bn2_mod, bnd_mod, stride, ds_k, ds_s, ds_p = blk
+        is3d = x.dim() == 5
+        xb = ops.as_channels_last(x)
+        n, cin = xb.shape[0], xb.shape[-1]
+        sp = tuple(xb.shape[1:-1]) if is3d else (1,) + tuple(xb.shape[1:-1])  # (D, H, W)
         cout = w1.shape[0]
-        stride = blk.conv1.stride[0]
         dev = xb.device
-        d1 = ops.conv2d_desc(n, h, w, cin, cout, 3, stride, 1)
-        _, ho, wo = ops.conv_out_hw(d1)
-        d2 = ops.conv2d_desc(n, ho, wo, cout, cout, 3, 1, 1)
-        m = n * ho * wo
-        y1 = torch.empty(n, ho, wo, cout, device=dev, dtype=BF16)
+        kd = 3 if is3d else 1
+        d1 = ops.conv_nd_desc(n, sp, cin, cout, (kd, 3, 3), (stride if is3d else 1, stride, stride), (1 if is3d else 0, 1, 1))
+        so = ops.conv_out_hw(d1)
+        d2 = ops.conv_nd_desc(n, so, cout, cout, (kd, 3, 3), (1, 1, 1), (1 if is3d else 0, 1, 1))
+        m = n * so[0] * so[1] * so[2]
+        oshape = (n,) + (so if is3d else so[1:]) + (cout,)
+        y1 = torch.empty(oshape, device=dev, dtype=BF16)
         s1 = ops.conv_fprop(d1, xb, ops.packed_fprop(w1), y1, want_stats=training)
-        st1 = ops.bn_finalize(s1, m, blk.bn1, cout, dev, training)
+        st1 = ops.bn_finalize(s1, m, bn1_mod, cout, dev, training)
         a1 = torch.empty_like(y1)
         ops.bn_apply(y1, st1, a1, None, True)
         y2 = torch.empty_like(y1)
         s2 = ops.conv_fprop(d2, a1, ops.packed_fprop(w2), y2, want_stats=training)
-        st2 = ops.bn_finalize(s2, m, blk.bn2, cout, dev, training)
+        st2 = ops.bn_finalize(s2, m, bn2_mod, cout, dev, training)
         dd = yd = std = None
         if wd is not None:
-            ds_conv = blk.downsample[0]
-            dd = ops.conv2d_desc(n, h, w, cin, cout, ds_conv.kernel_size[0], ds_conv.stride[0], ds_conv.padding[0])
+            dd = ops.conv_nd_desc(n, sp, cin, cout, (ds_k if is3d else 1, ds_k, ds_k), (ds_s if is3d else 1, ds_s, ds_s),
+                                  (ds_p if is3d else 0, ds_p, ds_p))
             yd = torch.empty_like(y1)
             sd = ops.conv_fprop(dd, xb, ops.packed_fprop(wd), yd, want_stats=training)
-            std = ops.bn_finalize(sd, m, blk.downsample[1], cout, dev, training)
+            std = ops.bn_finalize(sd, m, bnd_mod, cout, dev, training)
             idn = torch.empty_like(y1)
             ops.bn_apply(yd, std, idn, None, False)
         else:
@@ -157,7 +163,7 @@ class _BlockFn(torch.autograd.Function):
             ctx.saved = (xb, y1, a1, y2, yd, out, st1, st2, std, w1, w2, wd, g1, g2, gd, b1, b2, bd)
             ctx.descs = (d1, d2, dd)
             ctx.training = training
-        return ops.as_nchw_view(out)
+        return ops.as_channels_first_view(out)
 
     @staticmethod
     def backward(ctx, dout):
@@ -167,7 +173,7 @@ class _BlockFn(torch.autograd.Function):
         dev = xb.device
         cout = y1.shape[-1]
         need = ctx.needs_input_grad
-        dout = ops.as_nhwc(dout)
+        dout = ops.as_channels_last(dout)
 
         def vec():
             return torch.empty(cout, device=dev)
@@ -201,13 +207,15 @@ class _BlockFn(torch.autograd.Function):
                 dwd = _zeros_like_param(wd)
                 ops.conv_wgrad(dd, xb, dyd, dwd)
             if need[0]:
+                # strided 1x1 downsample: its data gradient touches only the even positions, so the main-branch gradient
+                # is written first and the downsample gradient accumulated onto it
                 dx = torch.empty_like(xb)
                 ops.conv_dgrad(d1, dy1, ops.packed_dgrad(w1), dx)
                 ops.conv_dgrad(dd, dyd, ops.packed_dgrad(wd), dx, accumulate=True)
         elif need[0]:
             dx = dz  # identity branch gradient; the main-branch dgrad accumulates onto it in place
             ops.conv_dgrad(d1, dy1, ops.packed_dgrad(w1), dx, accumulate=True)
-        return (ops.as_nchw_view(dx) if dx is not None else None, dw1, dg1 if need[2] else None, db1 if need[3] else None,
+        return (ops.as_channels_first_view(dx) if dx is not None else None, dw1, dg1 if need[2] else None, db1 if need[3] else None,
                 dw2, dg2 if need[5] else None, db2 if need[6] else None, dwd, dgd if need[8] else None,
                 dbd if need[9] else None, None, None)
 
@@ -217,9 +225,12 @@ class FusedBasicBlock(BasicBlock):
 
     def forward(self, x):
         ds = self.downsample
+        geom = (self.bn1, self.bn2, ds[1] if ds is not None else None, self.conv1.stride[0],
+                ds[0].kernel_size[0] if ds is not None else 1, ds[0].stride[0] if ds is not None else 1,
+                ds[0].padding[0] if ds is not None else 0)
         return _BlockFn.apply(x, self.conv1.weight, self.bn1.weight, self.bn1.bias, self.conv2.weight, self.bn2.weight,
                               self.bn2.bias, ds[0].weight if ds is not None else None,
-                              ds[1].weight if ds is not None else None, ds[1].bias if ds is not None else None, self,
+                              ds[1].weight if ds is not None else None, ds[1].bias if ds is not None else None, geom,
                               self.training)
 
 
@@ -371,7 +382,7 @@ class _QuadHeadFn(torch.autograd.Function):
         if labels is not None:
             ctx.mark_non_differentiable(logits)
             return lossbuf[n], logits
-        return logits
+        return logits.view(logits.shape)  # not the saved object itself (no ctx <-> output reference cycle)
 
     @staticmethod
     def backward(ctx, dout, _dlogits_unused=None):
@@ -712,6 +723,184 @@ class Quadtree3DCNN(nn.Module):
 
 
 # =================================================================================================
+# r3d_18 backbone models (3dcnn/models.py:220-375): torchvision's VideoResNet module tree (same state_dict keys) with the
+# stem and every 3-D BasicBlock executed on libqtcnn. As in the reference the backbone is frozen except layer4.
+# =================================================================================================
+class _VideoStemFn(torch.autograd.Function):
+    """BasicStem of r3d_18: Conv3d(3,64,(3,7,7),s=(1,2,2),p=(1,3,3), no bias) + BatchNorm3d + ReLU. clips: [B,T,3,H,W] in the
+    loader's layout (the permute of 3dcnn/models.py:258,345 only renames axes). Forward only — the reference freezes it."""
+
+    @staticmethod
+    def forward(ctx, clips, conv_w, bn_mod, training):
+        _require_cuda(clips, "r3d_18 stem")
+        if conv_w.requires_grad or (bn_mod.weight is not None and bn_mod.weight.requires_grad):
+            raise RuntimeError("r3d_18 stem: the reference keeps the stem frozen; training it is not implemented")
+        b, t, c, h, w = clips.shape
+        cout = conv_w.shape[0]
+        if tuple(conv_w.shape[1:]) != (3, 3, 7, 7) or c != 3:
+            raise RuntimeError("r3d_18 stem: expected Conv3d(3, C, (3,7,7))")
+        dev = clips.device
+        xf, dtype, scale, shift = ops.stem_source(clips.reshape(b * t, c, h, w))
+        xp = torch.empty(b * t, h + 7, w + 8, 4, device=dev, dtype=BF16)
+        check(L().qt_stem_pack_input_ex(ptr(xf), dtype, ptr(scale), ptr(shift), ptr(xp), b * t, 3, h, w, stream()), "stem_pack_input")
+        e = ops._entry(conv_w)
+        if e.w8 is None:  # [cout][3 depth taps][8 row taps][32]
+            w24 = torch.empty(cout, 3, 8, 32, device=dev, dtype=BF16)
+            tmp = torch.empty(cout, 8, 32, device=dev, dtype=BF16)
+            for kd in range(3):
+                wk = conv_w.detach()[:, :, kd].contiguous()
+                check(L().qt_wpack_stem(ptr(wk), ptr(tmp), cout, 3, 7, 7, stream()), "wpack_stem")
+                w24[:, kd] = tmp
+            e.w8 = w24
+        ho, wo = h // 2, w // 2
+        y = torch.empty(b, t, ho, wo, cout, device=dev, dtype=BF16)
+        stats = torch.empty(L().qt_stem3d_stat_rows(b, t, h, w), 2, cout, device=dev) if training else None
+        with ops.gemm_scope("stem3d_fprop", 2.0 * b * t * ho * wo * 441 * cout):
+            check(L().qt_stem3d_fprop(ptr(xp), ptr(e.w8), ptr(y), ptr(stats), b, t, h, w, cout, stream()), "stem3d_fprop")
+        ops._count(2)
+        st = ops.bn_finalize(stats, b * t * ho * wo, bn_mod, cout, dev, training)
+        out = torch.empty_like(y)
+        ops.bn_apply(y, st, out, None, True)
+        return ops.as_channels_first_view(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None, None, None
+
+
+class FusedVideoBlock(nn.Module):
+    """torchvision.models.video.resnet.BasicBlock (conv1 = Sequential(conv, bn, relu), conv2 = Sequential(conv, bn)) on
+    libqtcnn; instances are retargeted in place, so parameters / state_dict keys are torchvision's."""
+
+    def forward(self, x):
+        ds = self.downsample
+        c1, c2 = self.conv1, self.conv2
+        geom = (c1[1], c2[1], ds[1] if ds is not None else None, c1[0].stride[0],
+                ds[0].kernel_size[0] if ds is not None else 1, ds[0].stride[0] if ds is not None else 1,
+                ds[0].padding[0] if ds is not None else 0)
+        return _BlockFn.apply(x, c1[0].weight, c1[1].weight, c1[1].bias, c2[0].weight, c2[1].weight, c2[1].bias,
+                              ds[0].weight if ds is not None else None, ds[1].weight if ds is not None else None,
+                              ds[1].bias if ds is not None else None, geom, self.training)
+
+
+class FusedVideoStem(nn.Sequential):
+    def forward(self, clips_btchw):
+        return _VideoStemFn.apply(clips_btchw, self[0].weight, self[1], self[1].training)
+
+
+def make_r3d18() -> nn.Module:
+    """torchvision's r3d_18 module tree (what the reference builds with `video_models.r3d_18(weights=KINETICS400_V1)`) with
+    fused stem / blocks. Kinetics weights only if the checkpoint is already in the torch hub cache (no network here)."""
+    from torchvision.models import video as video_models
+    from torchvision.models.video.resnet import BasicBlock as VideoBasicBlock
+    net = video_models.r3d_18(weights=None)
+    ckpt = None
+    try:
+        url = video_models.R3D_18_Weights.KINETICS400_V1.url
+        ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(url))
+    except Exception:  # pragma: no cover
+        ckpt = None
+    if ckpt is not None and os.path.exists(ckpt):
+        net.load_state_dict(torch.load(ckpt, map_location="cpu"))
+    elif not _quiet_pretrained[0]:
+        warnings.warn("r3d_18 KINETICS400_V1 weights are not in the torch hub cache (no network): the frozen backbone starts from "
+                      "random initialisation; load real weights with load_state_dict.", RuntimeWarning, stacklevel=3)
+    for mod in net.modules():
+        if type(mod) is VideoBasicBlock:
+            mod.__class__ = FusedVideoBlock
+    net.stem.__class__ = FusedVideoStem
+    return net
+
+
+class _VideoFeatures(nn.Sequential):
+    """`nn.Sequential(stem, layer1..layer4)` of HybridQuadtree3DCNN (3dcnn/models.py:276-282): fed with the loader's
+    [B,T,3,H,W] clips directly (the stem reads that layout; the reference's permute is a view)."""
+
+
+class ResNet3DVideo(nn.Module):
+    """Drop-in for 3dcnn/models.py:220-262 (r3d_18 fine-tuning: everything frozen except layer4 and the new fc head)."""
+
+    def __init__(self, num_classes, dropout_rate=0.5):
+        super().__init__()
+        self.r3d_model = make_r3d18()
+        for param in self.r3d_model.parameters():
+            param.requires_grad = False
+        for param in self.r3d_model.layer4.parameters():
+            param.requires_grad = True
+        num_ftrs = self.r3d_model.fc.in_features
+        self.r3d_model.fc = nn.Sequential(nn.Linear(num_ftrs, num_ftrs // 2), nn.ReLU(inplace=True), nn.Dropout(dropout_rate),
+                                          nn.Linear(num_ftrs // 2, num_classes))
+        self.dropout_rate = dropout_rate
+
+    def forward(self, image_sequence_input, numerical_input=None):
+        r = self.r3d_model
+        x = r.stem(image_sequence_input)
+        for layer in (r.layer1, r.layer2, r.layer3, r.layer4):
+            x = layer(x)
+        f = Fn.GlobalAvgPoolND.apply(ops.as_channels_last(x))
+        fc = r.fc
+        h = Fn.SmallLinear.apply(f, fc[0].weight, fc[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(h, fc[3].weight, fc[3].bias, False, 0.0, self.training)
+
+
+class HybridQuadtree3DCNN(nn.Module):
+    """Drop-in for 3dcnn/models.py:266-375: frozen r3d_18 extractor (layer4 trainable) + numeric LSTM + fusion classifier."""
+
+    def __init__(self, num_classes, sequence_length=8, numerical_feature_dim=47, dropout_rate=0.6, mode="hybrid_quadtree_3d_fusion"):
+        super().__init__()
+        self.mode = mode
+        self.sequence_length = sequence_length
+        self.numerical_feature_dim = numerical_feature_dim
+        r3d_base = make_r3d18()
+        self.pretrained_image_extractor = _VideoFeatures(r3d_base.stem, r3d_base.layer1, r3d_base.layer2, r3d_base.layer3,
+                                                         r3d_base.layer4)
+        for param in self.pretrained_image_extractor.parameters():
+            param.requires_grad = False
+        for param in self.pretrained_image_extractor[4].parameters():
+            param.requires_grad = True
+        self.cnn_3d_feature_dim = 512
+        self.global_avg_pool_3d = nn.AdaptiveAvgPool3d((1, 1, 1))
+        self.numerical_lstm = nn.LSTM(input_size=numerical_feature_dim, hidden_size=numerical_feature_dim * 4, num_layers=2,
+                                      batch_first=True, dropout=dropout_rate)
+        self.numerical_lstm_output_dim = numerical_feature_dim * 4
+        self.numerical_projection = nn.Sequential(nn.Linear(self.numerical_lstm_output_dim, self.cnn_3d_feature_dim // 2),
+                                                  nn.ReLU(inplace=True), nn.Dropout(dropout_rate))
+        self.numerical_final_dim = self.cnn_3d_feature_dim // 2
+        if mode == "hybrid_quadtree_3d_fusion":
+            self.final_classifier_input_dim = self.cnn_3d_feature_dim + self.numerical_final_dim
+        elif mode == "hybrid_quadtree_3d_image_only":
+            self.final_classifier_input_dim = self.cnn_3d_feature_dim
+        else:
+            raise ValueError(f"Invalid mode for HybridQuadtree3DCNN: {mode}. Choose from 'hybrid_quadtree_3d_fusion', "
+                             "'hybrid_quadtree_3d_image_only'.")
+        d = self.final_classifier_input_dim
+        self.classifier = nn.Sequential(nn.Linear(d, d // 2), nn.ReLU(inplace=True), nn.Dropout(dropout_rate), nn.Linear(d // 2, num_classes))
+        self.dropout_rate = dropout_rate
+        self.gradients = None
+        self.activations = None
+
+    def save_gradient_hook(self, module, grad_input, grad_output):
+        self.gradients = grad_output[0]
+
+    def save_activation_hook(self, module, input, output):
+        self.activations = output
+
+    def forward(self, image_sequence_input, numerical_sequence_input):
+        x = self.pretrained_image_extractor(image_sequence_input)
+        image_features = Fn.GlobalAvgPoolND.apply(ops.as_channels_last(x))
+        if self.mode == "hybrid_quadtree_3d_fusion":
+            lstm_out = Fn.lstm_forward(self.numerical_lstm, numerical_sequence_input.to(image_features.device).float())
+            proj = self.numerical_projection[0]
+            num = Fn.SmallLinear.apply(lstm_out[:, -1, :], proj.weight, proj.bias, True, self.dropout_rate, self.training)
+            combined = torch.cat((image_features, num), dim=1)
+        else:
+            combined = image_features
+        cls = self.classifier
+        h = Fn.SmallLinear.apply(combined, cls[0].weight, cls[0].bias, True, self.dropout_rate, self.training)
+        return Fn.SmallLinear.apply(h, cls[3].weight, cls[3].bias, False, 0.0, self.training)
+
+
+# =================================================================================================
 # CnnLstm (cnn+lstm/models.py:14-89): every frame through the frozen ResNet-18 on the tensor cores; the temporal
 # LSTM runs on the persistent LSTM kernels (functional.LSTM)
 # =================================================================================================
@@ -796,8 +985,11 @@ def get_model_3d(num_classes, device, numerical_feature_dim=47, mode="fusion", s
     elif mode in ("quadtree_3d_fusion", "quadtree_3d_image_only"):
         model = Quadtree3DCNN(num_classes=num_classes, sequence_length=sequence_length,
                               numerical_feature_dim=numerical_feature_dim, mode=mode, cnn_3d_feature_dim=1024).to(device)
-    elif mode in ("resnet_3d_video_only", "hybrid_quadtree_3d_fusion", "hybrid_quadtree_3d_image_only"):
-        raise ValueError(f"get_model: mode '{mode}' (torchvision r3d_18 backbone) is SURVEY.md §8f 'next', not built yet")
+    elif mode == "resnet_3d_video_only":
+        model = ResNet3DVideo(num_classes=num_classes).to(device)
+    elif mode in ("hybrid_quadtree_3d_fusion", "hybrid_quadtree_3d_image_only"):
+        model = HybridQuadtree3DCNN(num_classes=num_classes, sequence_length=sequence_length,
+                                    numerical_feature_dim=numerical_feature_dim, mode=mode).to(device)
     else:
         model = QuadtreeCNN(num_classes=num_classes, numerical_feature_dim=numerical_feature_dim, mode=mode,
                             freeze_backbone=True).to(device)

@@ -442,6 +442,31 @@ def as_nhwc(t: torch.Tensor) -> torch.Tensor:
     return b if b.is_contiguous() else b.contiguous()
 
 
+def as_channels_last(t: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW / NCDHW tensor -> dense channels-last bf16 buffer [N,H,W,C] / [N,D,H,W,C] (no copy when it already is a
+    channels-last bf16 tensor produced by this package)."""
+    if t.dim() == 4:
+        return as_nhwc(t)
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    b = t.permute(0, 2, 3, 4, 1)
+    return b if b.is_contiguous() else b.contiguous()
+
+
+def as_channels_first_view(buf: torch.Tensor) -> torch.Tensor:
+    """Dense channels-last buffer -> logical NCHW / NCDHW view."""
+    return buf.permute(0, 3, 1, 2) if buf.dim() == 4 else buf.permute(0, 4, 1, 2, 3)
+
+
+def conv_nd_desc(n, dhw, cin, cout, k, stride, pad):
+    key = ("nd", n, tuple(dhw), cin, cout, tuple(k), tuple(stride), tuple(pad))
+    d = _desc_cache.get(key)
+    if d is None:
+        d = capi.conv_desc(n, tuple(dhw), cin, cout, tuple(k), tuple(stride), tuple(pad))
+        _desc_cache[key] = d
+    return d
+
+
 def as_nchw_view(buf: torch.Tensor) -> torch.Tensor:
     """Dense [N,H,W,C] buffer -> logical NCHW (channels_last) view."""
     return buf.permute(0, 3, 1, 2)

@@ -16,6 +16,7 @@ Reference files restated here (paths relative to the reference root; "QS" = "Qua
   QS/models.py:105-210   HierarchicalQuadtreeCNN (intended slicing) -> hier_forward
   resnet/models.py:7-180 StandardResNetCNN / QuadtreeCNN(mode=...) -> standard_resnet_forward / quadtree_forward(mode=)
   3dcnn/models.py:96-214 Quadtree3DCNN          -> quadtree3d_forward
+  3dcnn/models.py:220-375 ResNet3DVideo / HybridQuadtree3DCNN (torchvision video r3d_18) -> resnet3d_video_forward / hybrid3d_forward
   torchvision/models/resnet.py:59-105,266-284 (BasicBlock, ResNet._forward_impl; torchvision 0.26.0)
 """
 from __future__ import annotations
@@ -126,6 +127,41 @@ def make_params(kind: str, num_classes: int = 8, seed: int = 0, numerical_featur
             p[f"numerical_lstm.bias_hh_l{layer}"] = (torch.rand(4 * hid, generator=g) * 2 - 1) * bound
         _linear(g, p, "numerical_projection.0", cnn_3d_feature_dim // 2, hid)
         din = cnn_3d_feature_dim + cnn_3d_feature_dim // 2 if mode == "quadtree_3d_fusion" else cnn_3d_feature_dim
+        _linear(g, p, "classifier.0", din // 2, din)
+        _linear(g, p, "classifier.3", num_classes, din // 2)
+        return p
+    if kind in ("resnet3d_video", "hybrid3d"):  # 3dcnn/models.py:220-262, 266-340 (torchvision r3d_18 names)
+        pre = "r3d_model." if kind == "resnet3d_video" else "pretrained_image_extractor."
+        p = {}
+        stem = pre + ("stem." if kind == "resnet3d_video" else "0.")
+        p[stem + "0.weight"] = _conv_w(g, 64, 3, 3, 7, 7)
+        _bn(g, p, stem + "1", 64)
+        cin = 64
+        for li, cout in enumerate([64, 128, 256, 512], start=1):
+            for bi in range(2):
+                stride = 2 if (li > 1 and bi == 0) else 1
+                b = f"{pre}layer{li}.{bi}." if kind == "resnet3d_video" else f"{pre}{li}.{bi}."
+                p[b + "conv1.0.weight"] = _conv_w(g, cout, cin, 3, 3, 3)
+                _bn(g, p, b + "conv1.1", cout)
+                p[b + "conv2.0.weight"] = _conv_w(g, cout, cout, 3, 3, 3)
+                _bn(g, p, b + "conv2.1", cout)
+                if stride != 1 or cin != cout:
+                    p[b + "downsample.0.weight"] = _conv_w(g, cout, cin, 1, 1, 1)
+                    _bn(g, p, b + "downsample.1", cout)
+                cin = cout
+        if kind == "resnet3d_video":
+            _linear(g, p, pre + "fc.0", 256, 512)
+            _linear(g, p, pre + "fc.3", num_classes, 256)
+            return p
+        hid = numerical_feature_dim * 4
+        for layer, nin in ((0, numerical_feature_dim), (1, hid)):
+            bound = 1.0 / math.sqrt(hid)
+            p[f"numerical_lstm.weight_ih_l{layer}"] = (torch.rand(4 * hid, nin, generator=g) * 2 - 1) * bound
+            p[f"numerical_lstm.weight_hh_l{layer}"] = (torch.rand(4 * hid, hid, generator=g) * 2 - 1) * bound
+            p[f"numerical_lstm.bias_ih_l{layer}"] = (torch.rand(4 * hid, generator=g) * 2 - 1) * bound
+            p[f"numerical_lstm.bias_hh_l{layer}"] = (torch.rand(4 * hid, generator=g) * 2 - 1) * bound
+        _linear(g, p, "numerical_projection.0", 256, hid)
+        din = 768 if mode == "hybrid_quadtree_3d_fusion" else 512
         _linear(g, p, "classifier.0", din // 2, din)
         _linear(g, p, "classifier.3", num_classes, din // 2)
         return p
@@ -418,7 +454,54 @@ def cnn_lstm_forward(p: Params, image_sequence, numerical_sequence, training=Tru
     return F.linear(hdn, p["classifier.3.weight"], p["classifier.3.bias"])
 
 
+def _r3d_features(p: Params, pre: str, hybrid: bool, clips, training, nb):
+    """torchvision r3d_18 up to layer4 (video/resnet.py: BasicStem, BasicBlock with Conv3DSimple) on [B,T,3,H,W] clips."""
+    x = clips.permute(0, 2, 1, 3, 4)
+    stem = pre + ("0." if hybrid else "stem.")
+    x = F.conv3d(x, p[stem + "0.weight"], None, stride=(1, 2, 2), padding=(1, 3, 3))
+    x = F.relu(_bn_apply(p, stem + "1", x, training, nb))
+    for li in (1, 2, 3, 4):
+        for bi in (0, 1):
+            b = f"{pre}{li}.{bi}." if hybrid else f"{pre}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            out = F.conv3d(x, p[b + "conv1.0.weight"], None, stride=stride, padding=1)
+            out = F.relu(_bn_apply(p, b + "conv1.1", out, training, nb))
+            out = F.conv3d(out, p[b + "conv2.0.weight"], None, stride=1, padding=1)
+            out = _bn_apply(p, b + "conv2.1", out, training, nb)
+            if b + "downsample.0.weight" in p:
+                idt = F.conv3d(x, p[b + "downsample.0.weight"], None, stride=stride)
+                idt = _bn_apply(p, b + "downsample.1", idt, training, nb)
+            else:
+                idt = x
+            x = F.relu(out + idt)
+    return F.adaptive_avg_pool3d(x, 1).flatten(1)
+
+
+def resnet3d_video_forward(p: Params, clips, numerical_seq=None, training=True, dropout_rate=0.0, new_buffers=None):
+    """ResNet3DVideo.forward — 3dcnn/models.py:255-262 (r3d_18 with the 512 -> 256 -> nc head as `fc`)."""
+    f = _r3d_features(p, "r3d_model.", False, clips, training, new_buffers)
+    h = _dropout(F.relu(F.linear(f, p["r3d_model.fc.0.weight"], p["r3d_model.fc.0.bias"])), p, training, dropout_rate)
+    return F.linear(h, p["r3d_model.fc.3.weight"], p["r3d_model.fc.3.bias"])
+
+
+def hybrid3d_forward(p: Params, clips, numerical_seq, training=True, mode="hybrid_quadtree_3d_fusion", dropout_rate=0.0,
+                     new_buffers=None):
+    """HybridQuadtree3DCNN.forward — 3dcnn/models.py:335-372."""
+    img = _r3d_features(p, "pretrained_image_extractor.", True, clips, training, new_buffers)
+    if mode == "hybrid_quadtree_3d_fusion":
+        last = _lstm_last(p, numerical_seq)
+        num = _dropout(F.relu(F.linear(last, p["numerical_projection.0.weight"], p["numerical_projection.0.bias"])), p,
+                       training, dropout_rate)
+        comb = torch.cat((img, num), dim=1)
+    else:
+        comb = img
+    h = _dropout(F.relu(F.linear(comb, p["classifier.0.weight"], p["classifier.0.bias"])), p, training, dropout_rate)
+    return F.linear(h, p["classifier.3.weight"], p["classifier.3.bias"])
+
+
 FORWARDS = {
+    "resnet3d_video": resnet3d_video_forward,
+    "hybrid3d": hybrid3d_forward,
     "cnn_lstm": cnn_lstm_forward,
     "quadtree": quadtree_forward,
     "attention_hierarchical": attention_hier_forward,

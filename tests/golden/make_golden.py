@@ -23,6 +23,9 @@ from oracle import quadtree_oracle as O  # noqa: E402
 REF = "/root/reference"
 _r18 = torchvision.models.resnet18
 torchvision.models.resnet18 = lambda weights=None, **kw: _r18(weights=None, **kw)
+import torchvision.models.video as _video  # noqa: E402
+_r3d = _video.r3d_18
+_video.r3d_18 = lambda weights=None, **kw: _r3d(weights=None, **kw)  # KINETICS400 download is impossible offline too
 
 
 def load_ref(relpath, name):
@@ -100,6 +103,12 @@ def run_case(case):
     elif kind == "quadtree3d":
         mod = load_ref("3dcnn/models.py", "ref_3d")
         model = mod.Quadtree3DCNN(num_classes=8, sequence_length=case["seq_len"], dropout_rate=0.0, mode=mode)
+    elif kind == "resnet3d_video":
+        mod = load_ref("3dcnn/models.py", "ref_3d")
+        model = mod.ResNet3DVideo(num_classes=8, dropout_rate=0.0)
+    elif kind == "hybrid3d":
+        mod = load_ref("3dcnn/models.py", "ref_3d")
+        model = mod.HybridQuadtree3DCNN(num_classes=8, sequence_length=case["seq_len"], dropout_rate=0.0, mode=mode)
     elif kind == "cnn_lstm":
         mod = load_ref("cnn+lstm/models.py", "ref_cnnlstm")
         model = mod.CnnLstm(num_classes=8, sequence_length=case["seq_len"], dropout_rate=0.0)
@@ -110,7 +119,7 @@ def run_case(case):
     res = model.load_state_dict(sd, strict=False)
     own_missing = [k for k in res.missing_keys if not k.startswith(("features_extractor.", "global_processor."))]
     assert not own_missing and not res.unexpected_keys, (own_missing[:5], res.unexpected_keys[:5])
-    if kind in ("quadtree3d", "cnn_lstm"):
+    if kind in ("quadtree3d", "cnn_lstm", "resnet3d_video", "hybrid3d"):
         images, numerical, labels = O.synthetic_batch(batch, seed, seq_len=case["seq_len"], clip_size=case["clip"])
     else:
         images, numerical, labels = O.synthetic_batch(batch, seed)
@@ -160,6 +169,9 @@ CASES = [
     {"name": "quadtree3d_image_only_b2", "kind": "quadtree3d", "mode": "quadtree_3d_image_only", "batch": 2, "seed": 12,
      "param_seed": 7, "seq_len": 4, "clip": 32},
     {"name": "cnn_lstm_train_b2", "kind": "cnn_lstm", "batch": 2, "seed": 21, "param_seed": 8, "seq_len": 3, "clip": 64},
+    {"name": "resnet3d_video_b2", "kind": "resnet3d_video", "batch": 2, "seed": 31, "param_seed": 9, "seq_len": 8, "clip": 64},
+    {"name": "hybrid3d_fusion_b2", "kind": "hybrid3d", "mode": "hybrid_quadtree_3d_fusion", "batch": 2, "seed": 32,
+     "param_seed": 10, "seq_len": 8, "clip": 64},
 ]
 
 

@@ -172,3 +172,29 @@ def test_maxpool3d_exact(env):
     C.check(C.lib().qt_maxpool3d_bwd(C.ptr(dout.permute(0, 2, 3, 4, 1).contiguous()), C.ptr(am), C.ptr(dx), n, d, h, w, c, 2, 2, 2,
                                      C.stream()))
     assert torch.equal(dx.permute(0, 4, 1, 2, 3).float(), xf.grad)
+
+
+@pytest.mark.parametrize("kind", ["resnet3d_video", "hybrid3d"])
+def test_r3d18_models(env, kind):
+    """ResNet3DVideo / HybridQuadtree3DCNN (3dcnn/models.py:220-375; torchvision r3d_18, frozen except layer4): the stem's
+    3x7x7 strided Conv3d, the 3-D BasicBlocks (3x3x3 stride 1 on the slab kernels, stride 2 and 1x1x1 downsample on the gather
+    kernels), BatchNorm3d in train mode on the frozen layers, logits and every trainable gradient against the oracle."""
+    O, M = env
+    mode = "hybrid_quadtree_3d_fusion"
+    p = O.make_params(kind, 8, seed=9, mode=mode)
+    clips, numerical, labels = O.synthetic_batch(2, 31, seq_len=8, clip_size=64)
+    if kind == "resnet3d_video":
+        model = M.get_model_3d(8, "cuda", mode="resnet_3d_video_only", print_num_params=False)
+        kw = {}
+    else:
+        model = M.get_model_3d(8, "cuda", mode=mode, sequence_length=8, print_num_params=False)
+        model.numerical_lstm.dropout = 0.0
+        kw = {"mode": mode}
+    model.dropout_rate = 0.0
+    load_oracle_params(model, p)
+    model.train()
+    sd = model.state_dict()
+    assert all(k in sd for k in p), [k for k in p if k not in sd][:4]  # torchvision's r3d_18 key names
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    assert any("layer4" in n or ".4." in n for n in trainable) and not any("layer3" in n or ".3.0.conv" in n for n in trainable)
+    check_train_step(O, kind, model, p, (clips, numerical), labels, **kw)

@@ -408,3 +408,34 @@ def test_quadtree3d_full_clip_size(C):
             checked += parity.assert_grad(name, prm.grad, ref_g[name], ac_g[name], report)
     parity.print_worst(report)
     assert checked >= 20
+
+
+@pytest.mark.parametrize("which", ["quadtree_forward_api", "quadtree3d"])
+def test_no_reference_cycles_keep_activations_alive(C, which):
+    """A Function that stores its own output in ctx creates output -> grad_fn -> ctx -> output, which only Python's cyclic GC
+    frees: a whole step of activations per iteration stays allocated (seen as 1.6 GB/step on the 3-D model). With the GC
+    switched off, allocated memory must be flat from step to step."""
+    import gc
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import models as M
+    torch.manual_seed(0)
+    if which == "quadtree3d":
+        model = M.Quadtree3DCNN(num_classes=8, sequence_length=4).cuda().train()
+        x, nf, y = (t.cuda() for t in O.synthetic_batch(2, 3, seq_len=4, clip_size=32))
+    else:
+        model = M.QuadtreeCNN(num_classes=8).cuda().train()
+        x, nf, y = (t.cuda() for t in O.synthetic_batch(2, 3))
+    gc.collect()
+    gc.disable()
+    try:
+        seen = []
+        for _ in range(6):
+            model.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(model(x, nf), y)
+            loss.backward()
+            del loss
+            torch.cuda.synchronize()
+            seen.append(torch.cuda.memory_allocated())
+        assert seen[-1] == seen[2], seen
+    finally:
+        gc.enable()

@@ -31,12 +31,12 @@ def test_oracle_matches_reference_fixture(path):
     kind, mode = case["kind"], case.get("mode", "fusion")
     training = case.get("training", True)
     p = O.make_params(kind, 8, seed=case["param_seed"], mode=mode)
-    if kind in ("quadtree3d", "cnn_lstm"):
+    if kind in ("quadtree3d", "cnn_lstm", "resnet3d_video", "hybrid3d"):
         images, numerical, labels = O.synthetic_batch(case["batch"], case["seed"], seq_len=case["seq_len"],
                                                       clip_size=case["clip"])
     else:
         images, numerical, labels = O.synthetic_batch(case["batch"], case["seed"])
-    kw = {"mode": mode} if kind in ("quadtree", "quadtree3d") else {}
+    kw = {"mode": mode} if kind in ("quadtree", "quadtree3d", "hybrid3d") else {}
     ref_logits = torch.tensor(gold["logits"], dtype=torch.float64)
     if not training:
         with torch.no_grad():
