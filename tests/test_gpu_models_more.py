@@ -182,7 +182,9 @@ def test_r3d18_models(env, kind):
     O, M = env
     mode = "hybrid_quadtree_3d_fusion"
     p = O.make_params(kind, 8, seed=9, mode=mode)
-    clips, numerical, labels = O.synthetic_batch(2, 31, seq_len=8, clip_size=64)
+    # B = 6: layer4 works on 1 x 4 x 4 maps here, so its train-mode BatchNorm sees only 16 B values per channel; at B = 2 a
+    # single ReLU flip from bf16 rounding moves those statistics by more than the autocast-relative 1.25x bound allows
+    clips, numerical, labels = O.synthetic_batch(6, 31, seq_len=8, clip_size=64)
     if kind == "resnet3d_video":
         model = M.get_model_3d(8, "cuda", mode="resnet_3d_video_only", print_num_params=False)
         kw = {}
