@@ -87,6 +87,9 @@ int qt_wpack_stem(const float* w, void* w8, int cout, int cin, int r, int s, qt_
 /* Conv3d forward weights with 32 input channels ([cout][32][3][3][3] fp32) -> bf16 [cout][2][9][64]: the operand of the
  * slab kernel's pair mode (qt_conv_plan(d, 0) == 2), where one 128-byte slab row carries two depth planes. */
 int qt_wpack_conv3d_pair(const float* w, void* wp, int cout, qt_stream_t stream);
+/* First Conv3d layer (3dcnn/models.py:107: Conv3d(3 -> 32)) on channel-padded NDHWC8 input: weights [32][cin <= 8][3][3][3] fp32
+ * -> the resident operand tiles of the dedicated kernel (qt_conv_plan(d, 0) == 3 for in_c == 8, out_c == 32). */
+int qt_wpack_conv3d_c8(const float* w, void* wb, int cout, int cin, qt_stream_t stream);
 /* Every weight of a model repacked in ONE launch (what the training loop needs after optimizer.step(),
  * QS/Quadtree_train.py:72): fill w/wf/wd/cout/cin/taps of each item, call qt_wpack_item_plan (fills co_tile and
  * ci_tiles, returns the item's block count or -1), set first_block to the running sum of the block counts, copy the
@@ -108,7 +111,8 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream);
  * y = conv(x, wf) [+ bias] [ReLU]; with QT_EPI_STATS also writes per-tile column sum / sum-of-squares
  * partials [qt_conv_stat_rows][2][out_c] for the train-mode BatchNorm that follows. */
 /* kernel selection of a pass (0 = fprop, 1 = dgrad, 2 = wgrad): 0 generic gather GEMM, 1 persistent slab kernel,
- * 2 (fprop of a 32-channel Conv3d only) slab kernel reading pair-packed weights (qt_wpack_conv3d_pair). */
+ * 2 (fprop of a 32-channel Conv3d only) slab kernel reading pair-packed weights (qt_wpack_conv3d_pair),
+ * 3 (fprop of the 8 -> 32 channel first Conv3d only) dedicated kernel reading qt_wpack_conv3d_c8 weights. */
 int qt_conv_plan(const qt_conv_desc* d, int pass);
 int qt_conv_stat_rows(const qt_conv_desc* d);
 size_t qt_conv_fprop_workspace_bytes(const qt_conv_desc* d);

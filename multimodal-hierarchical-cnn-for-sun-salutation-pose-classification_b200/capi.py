@@ -126,6 +126,7 @@ _SIGNATURES = {
     "qt_wpack_both": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "qt_wpack_item_plan": (c_int, [ctypes.POINTER(WpackItem)]),
     "qt_wpack_multi": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "qt_wpack_conv3d_c8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "qt_wpack_conv3d_pair": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "qt_wpack_stem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "qt_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),

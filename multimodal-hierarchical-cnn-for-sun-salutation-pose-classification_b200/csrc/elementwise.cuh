@@ -246,6 +246,18 @@ __global__ void wpack_multi_kernel(const WpackItem* __restrict__ items, int nite
   const int local = b - it.first_block;
   wpack_tile(it.w, it.wf, it.wd, it.cout, it.cin, it.taps, it.co_tile, local % it.ci_tiles, local / it.ci_tiles, tile);
 }
+// First Conv3d layer: [32][Cin <= 8][3][3][3] fp32 -> [18 tiles (kd, kh, half)][2 K chunks][32 cout][8 channels] bf16 for
+// conv3d_c8_kernel: K chunk kc of half h is the pixel at dw = 2h + kc - 1 (dw = +2 does not exist: zero weights).
+__global__ void wpack_conv3d_c8_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 18 * 2 * 32 * 8) return;
+  const int c = i & 7, co = (i >> 3) & 31, kc = (i >> 8) & 1, ti = i >> 9;
+  const int half = ti & 1, kh = (ti >> 1) % 3, kd = ti / 6;
+  const int kw = 2 * half + kc;  // 0..3
+  float v = 0.f;
+  if (kw < 3 && c < Cin) v = w[(co * Cin + c) * 27 + kd * 9 + kh * 3 + kw];
+  out[i] = __float2bfloat16_rn(v);
+}
 // Conv3d weights with 32 input channels [Cout][32][3][3][3] -> pair layout [Cout][2][9][64] for the slab kernel: K chunk
 // (item, tap) = [depth tap 2*item, 32 channels | depth tap 2*item + 1, 32 channels] (the missing fourth depth tap is zero).
 __global__ void wpack_conv3d_pair_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout) {

@@ -11,6 +11,7 @@
 #include "conv3x3.cuh"
 #include "stem.cuh"
 #include "wgrad3x3.cuh"
+#include "conv3d_c8.cuh"
 #include "head.cuh"
 #include "optim.cuh"
 #include "lstm.cuh"
@@ -321,6 +322,45 @@ C3Plan plan_conv3x3(const qt_conv_desc* d, int cin, int nout, int flags, bool dg
   return pl;
 }
 
+// ------------------------------------------------------------------------------------------------
+// First Conv3d layer (8 padded input channels -> 32): conv3d_c8.cuh
+// ------------------------------------------------------------------------------------------------
+bool c8_ok(const qt_conv_desc* d, int flags) {
+  if (g_tune[7] == 1 || !g_use_conv3x3) return false;
+  if (d->k_d != 3 || !slab_geometry(d) || d->groups != 1 || d->in_c != 8 || d->out_c != kC8N) return false;
+  if (flags & (EPI_RELU | EPI_OUT_F32 | EPI_ADDEND)) return false;
+  if (!dense_nhwc(d->x_stride, d->in_d, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, d->in_d, d->in_h, d->in_w, d->out_c)) return false;
+  const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
+  return V <= (1ll << 30) && d->in_w <= 1024;
+}
+int c8_tiles(const qt_conv_desc* d) {
+  const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
+  return static_cast<int>((V + 2 * kBM - 1) / (2 * kBM));
+}
+int run_conv3d_c8(const qt_conv_desc* d, const void* x, const void* wb, void* y, const float* bias, float* stats, cudaStream_t st) {
+  Conv3dC8Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.wb = static_cast<const __nv_bfloat16*>(wb);
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.bias = bias;
+  p.stats = stats;
+  p.NP = d->n * d->in_d; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.V = p.NP * (p.H + 1) * (p.W + 2);
+  p.num_tiles = c8_tiles(d);
+  p.R = 2 * kBM + 2 * (p.W + 3) + 8;
+  const size_t slab = (static_cast<size_t>(p.R) * 16 + 1023) / 1024 * 1024;
+  const size_t smem = 1024 + 20 * 1024 + kC8Slabs * slab;
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(conv3d_c8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv3d_c8_kernel<<<grid, kC8Threads, smem, st>>>(p);
+  return cuda_status("conv3d_c8_kernel");
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time libcuda dependency).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -439,6 +479,7 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   if (d->in_c == 64 && d->out_c == 64 && d->k_d == 1) pl.cfg = 0;
   else if (d->in_c % 128 == 0 && d->out_c % 128 == 0) pl.cfg = 1;
   else if (d->in_c == 64 && d->out_c % 128 == 0) pl.cfg = 2;  // 64 -> 128k (Conv3d block3): one 64-channel slab, 128-cout dy tiles
+  else if (d->k_d == 3 && d->in_c == 32 && d->out_c == 64) pl.cfg = 3;  // Conv3d block2: pair3d on the 64 -> 64 configuration
   else return pl;
   const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
   if (V > (1ll << 30)) return pl;
@@ -446,12 +487,13 @@ W3Plan plan_wgrad3x3(const qt_conv_desc* d) {
   pl.num_kt = static_cast<int>((V + kW3KP - 1) / kW3KP);
   pl.R = (kW3KP + 2 * (d->in_w + 3) + 7) / 8 * 8;
   // cfg 0 pairs horizontally adjacent taps in one MMA (wgrad3x3.cuh): 6 MMA groups cover all 9 taps in a single CTA
-  const int nslab = pl.cfg == 1 ? 2 : 1, cb = pl.cfg == 0 ? 1 : 2, stages = pl.cfg == 0 ? 4 : (pl.cfg == 1 ? 2 : 3), taps = pl.cfg == 0 ? 9 : 3;
-  const int dy_rows = pl.cfg == 0 ? kW3KP + 8 : kW3KP;
+  const bool c0like = pl.cfg == 0 || pl.cfg == 3;
+  const int nslab = pl.cfg == 1 ? 2 : 1, cb = c0like ? 1 : 2, stages = c0like ? 4 : (pl.cfg == 1 ? 2 : 3), taps = c0like ? 9 : 3;
+  const int dy_rows = c0like ? kW3KP + 8 : kW3KP;
   pl.cout_tiles = d->out_c / (64 * cb);
-  pl.cin_groups = d->in_c / (64 * nslab);
+  pl.cin_groups = pl.cfg == 3 ? 1 : d->in_c / (64 * nslab);
   pl.tap_groups = (9 + taps - 1) / taps;
-  const int types = pl.cout_tiles * pl.cin_groups * pl.tap_groups * d->k_d;
+  const int types = pl.cout_tiles * pl.cin_groups * pl.tap_groups * (pl.cfg == 3 ? 2 : d->k_d);
   int splits = kNumSMs / types;
   if (splits < 1) splits = 1;
   if (splits > pl.num_kt / 4) splits = pl.num_kt / 4;
@@ -473,7 +515,7 @@ int launch_wgrad3x3(const Wgrad3x3Params& p, const W3Plan& pl, cudaStream_t st) 
     cudaFuncSetAttribute(wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     configured = pl.smem;
   }
-  dim3 grid(pl.cout_tiles * pl.cin_groups * pl.tap_groups, pl.splits, p.kdn);
+  dim3 grid(pl.cout_tiles * pl.cin_groups * pl.tap_groups, pl.splits, p.pair3d ? 2 : p.kdn);
   wgrad3x3_kernel<NSLAB, TAPS, CB, STAGES, NMMA><<<grid, 192, pl.smem, st>>>(p);
   return cuda_status("wgrad3x3_kernel");
 }
@@ -487,14 +529,14 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   p.dy = static_cast<const __nv_bfloat16*>(dy);
   p.ws = static_cast<float*>(ws);
   p.N = d->n * d->in_d; p.H = d->in_h; p.W = d->in_w; p.cin = d->in_c; p.cout = d->out_c;
-  p.D = d->in_d; p.kdn = d->k_d;
+  p.D = d->in_d; p.kdn = d->k_d; p.pair3d = pl.cfg == 3 ? 1 : 0;
   p.V = pl.V; p.num_kt = pl.num_kt; p.kt_per_split = pl.kt_per_split;
   p.R = pl.R;
   p.cout_tiles = pl.cout_tiles; p.cin_groups = pl.cin_groups; p.tap_groups = pl.tap_groups;
   int t = 0;
   for (int kh = 0; kh < 3; ++kh)
     for (int kw = 0; kw < 3; ++kw, ++t) { p.off_h[t] = static_cast<signed char>(kh - 1); p.off_w[t] = static_cast<signed char>(kw - 1); }
-  int rc = pl.cfg == 0 ? launch_wgrad3x3<1, 6, 1, 4, 2>(p, pl, st)
+  int rc = (pl.cfg == 0 || pl.cfg == 3) ? launch_wgrad3x3<1, 6, 1, 4, 2>(p, pl, st)
                        : (pl.cfg == 1 ? launch_wgrad3x3<2, 3, 2, 2, 2>(p, pl, st) : launch_wgrad3x3<1, 3, 2, 3, 2>(p, pl, st));
   if (rc) return rc;
   const int taps = 9 * d->k_d;
@@ -618,6 +660,11 @@ int qt_wpack_multi(const void* items_dev, int nitems, int total_blocks, int max_
   wpack_multi_kernel<<<total_blocks, 256, smem, S(stream)>>>(static_cast<const WpackItem*>(items_dev), nitems);
   return cuda_status("wpack_multi");
 }
+int qt_wpack_conv3d_c8(const float* w, void* wb, int cout, int cin, qt_stream_t stream) {
+  if (cout != kC8N || cin < 1 || cin > 8) return fail("wpack_conv3d_c8: expects a [32][cin <= 8][3][3][3] weight");
+  wpack_conv3d_c8_kernel<<<(18 * 2 * 32 * 8 + 255) / 256, 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wb), cin);
+  return cuda_status("wpack_conv3d_c8");
+}
 int qt_wpack_conv3d_pair(const float* w, void* wp, int cout, qt_stream_t stream) {
   const long long total = static_cast<long long>(cout) * 2 * 9 * 64;
   wpack_conv3d_pair_kernel<<<grid_for(total, 256, 1 << 20), 256, 0, S(stream)>>>(w, static_cast<__nv_bfloat16*>(wp), cout);
@@ -638,6 +685,7 @@ int qt_f32_to_bf16(const float* x, void* out, long long n, qt_stream_t stream) {
 int qt_conv_plan(const qt_conv_desc* d, int pass) {
   if (check_desc(d)) return -1;
   if (pass == 0) {
+    if (c8_ok(d, EPI_STATS | EPI_BIAS)) return 3;  // first Conv3d layer: conv3d_c8 kernel on qt_wpack_conv3d_c8 weights
     const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS | (d->k_d == 3 ? EPI_BIAS : 0));
     return pl.ok ? (pl.pair ? 2 : 1) : 0;  // 2: slab kernel on pair-packed weights (qt_wpack_conv3d_pair)
   }
@@ -646,6 +694,7 @@ int qt_conv_plan(const qt_conv_desc* d, int pass) {
 }
 int qt_conv_stat_rows(const qt_conv_desc* d) {
   if (check_desc(d)) return -1;
+  if (c8_ok(d, EPI_STATS | EPI_BIAS)) { const int t = c8_tiles(d); return t < kNumSMs ? t : kNumSMs; }
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, EPI_STATS | (d->k_d == 3 ? EPI_BIAS : 0));
   if (pl.ok) { const int tiles = pl.num_m_tiles * pl.num_n_tiles; return tiles < kNumSMs ? tiles : kNumSMs; }
   const OutDims o = conv_out_dims(d);
@@ -667,6 +716,7 @@ int qt_conv_fprop(const qt_conv_desc* d, const void* x, const void* wf, void* y,
   p.flags = flags & (EPI_BIAS | EPI_RELU | EPI_STATS | EPI_OUT_F32);
   if ((p.flags & EPI_BIAS) && !bias) return fail("conv_fprop: QT_EPI_BIAS without bias");
   if ((p.flags & EPI_STATS) && !stats) return fail("conv_fprop: QT_EPI_STATS without stats buffer");
+  if (c8_ok(d, p.flags)) return run_conv3d_c8(d, x, wf, y, (p.flags & EPI_BIAS) ? bias : nullptr, (p.flags & EPI_STATS) ? stats : nullptr, S(stream));
   const C3Plan pl = plan_conv3x3(d, d->in_c, d->out_c, p.flags);
   if (pl.ok) return run_conv3x3(pl, d, d->in_c, d->out_c, x, wf, y, nullptr, stats, p.flags, false, S(stream), bias);
   return run_kmajor(p, S(stream), ws, ws_bytes, 0);

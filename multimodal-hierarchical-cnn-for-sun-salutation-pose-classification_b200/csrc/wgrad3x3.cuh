@@ -32,6 +32,10 @@ struct Wgrad3x3Params {
   // Conv3d (3x3x3 / s1 / p1): N counts depth planes (clips * D); blockIdx.z = depth tap kd, whose x slab is the plane
   // kd - 1 away (zero outside the clip); partials land at tap index kd * 9 + tap of the [27 * cin][cout] workspace.
   int D, kdn;
+  // pair3d (Conv3d with 32 input channels, 64 outputs): the 64 slab "channels" are two depth planes of 32 channels each
+  // (blockIdx.z = pair item: planes (-1, 0) and (+1, none)), as in conv3x3's pair mode; accumulator columns 0..31 / 32..63
+  // belong to depth taps 2*item / 2*item + 1.
+  int pair3d;
 };
 
 template <int NSLAB, int TAPS, int CB, int STAGES, int NMMA>
@@ -100,12 +104,17 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
     // offsets are kept incrementally: +16 virtual pixels = adv, a w-carry skips the 2 pad columns, an h-carry the
     // shared zero row
     const int pW = p.W, pN = p.N, pR = p.R, pD = p.D;
-    const int dd = p.kdn > 1 ? static_cast<int>(blockIdx.z) - 1 : 0;  // source plane offset of this CTA's depth tap
-    const long long dy_pix = static_cast<long long>(p.cout) * 2, x_pix = static_cast<long long>(p.cin) * 2;
+    // source plane offset of this thread's slab chunk: the CTA's depth tap, or (pair3d) one of the item's two planes
+    int dd = p.kdn > 1 ? static_cast<int>(blockIdx.z) - 1 : 0;
+    if (p.pair3d) {
+      const int kd = 2 * static_cast<int>(blockIdx.z) + (chunk >> 2);
+      dd = kd < 3 ? kd - 1 : (1 << 20);
+    }
+    const long long dy_pix = static_cast<long long>(p.cout) * 2, x_pix = p.pair3d ? 64 : static_cast<long long>(p.cin) * 2;
     const long long dy_adv = (static_cast<long long>(adv_h) * pW + adv_w) * dy_pix, x_adv = (static_cast<long long>(adv_h) * pW + adv_w) * x_pix;
     const long long dy_row = pW * dy_pix, x_row = pW * x_pix;
     const char* dy_c = reinterpret_cast<const char*>(p.dy + cout0 + chunk * 8);
-    const char* x_c = reinterpret_cast<const char*>(p.x + cin0 + chunk * 8);
+    const char* x_c = reinterpret_cast<const char*>(p.x + (p.pair3d ? (chunk & 3) * 8 : cin0 + chunk * 8));
     const void* dummy_dy = p.dy;
     const void* dummy_x = p.x;
     for (int it = 0; it < nit; ++it) {
@@ -148,7 +157,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
           n = rest / Hp - 1;
           dz = (n + pD) % pD;
         }
-        const char* src = x_c + dd * (static_cast<long long>(p.H) * x_row) + (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
+        const char* src = x_c + (dd == (1 << 20) ? 0 : dd) * (static_cast<long long>(p.H) * x_row) +
+                          (static_cast<long long>(n * p.H + (hp - 1)) * pW + (wp - 1)) * x_pix;
         uint32_t dst = smem_u32(st + dy_bytes) + rbase * 128 + dsw;  // rows 16 apart keep the swizzle phase (row & 7)
 #pragma unroll 2
         for (int j = rbase; j < pR; j += 16) {
@@ -226,8 +236,8 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
       tc_fence_after();
     }
     const int crow = warp * 32 + lane;            // row of the 128-row accumulator
-    const long long Mpad = 9LL * p.kdn * p.cin;
-    const int tap_base = p.kdn > 1 ? static_cast<int>(blockIdx.z) * 9 : 0;
+    const long long Mpad = p.pair3d ? 27LL * 32 : 9LL * p.kdn * p.cin;
+    const int tap_base = (p.kdn > 1 && !p.pair3d) ? static_cast<int>(blockIdx.z) * 9 : 0;
     for (int tp = 0; tp < ntap; ++tp) {
       // PAIR: rows 0..63 of group tp belong to the tap the slab was started at, rows 64..127 (pair groups only) to its
       // left neighbour (kh, 1); otherwise row == cout and the accumulator is tap0 + tp
@@ -239,9 +249,11 @@ __global__ void __launch_bounds__(192, 1) wgrad3x3_kernel(const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + tp * NCH + c0, r);
         tmem_ld_wait();
-        if (row_ok) {
-          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + static_cast<long long>(tap_base + tap) * p.cin + cin0 + c0) * p.cout +
-                       cout0 + co;
+        const int kd_pair = 2 * static_cast<int>(blockIdx.z) + (c0 >> 5);  // pair3d: depth tap of this 32-column half
+        if (row_ok && !(p.pair3d && kd_pair > 2)) {
+          const long long wrow = p.pair3d ? static_cast<long long>(kd_pair * 9 + tap) * 32
+                                          : static_cast<long long>(tap_base + tap) * p.cin + cin0 + c0;
+          float* dst = p.ws + (static_cast<long long>(blockIdx.y) * Mpad + wrow) * p.cout + cout0 + co;
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.cout] = nit > 0 ? __uint_as_float(r[j]) : 0.f;
         }

@@ -332,6 +332,12 @@ def _conv3d_weights(w, cin_pad, need_dgrad, pair):
         wd = ops.packed_dgrad(w) if need_dgrad else None
         return wf, wd
     e = ops._entry(w)
+    if pair == "c8":  # first layer on the dedicated kernel: resident operand tiles straight from the fp32 parameter
+        if getattr(e, "w8", None) is None:
+            e.w8 = torch.empty(18, 2, 32, 8, device=w.device, dtype=BF16)
+            check(L().qt_wpack_conv3d_c8(ptr(w.detach().contiguous()), ptr(e.w8), cout, cin, stream()), "wpack_conv3d_c8")
+            ops._count()
+        return e.w8, None
     if getattr(e, "w8", None) is None:  # (the stem slot doubles as the cache of the padded pack)
         wp = torch.zeros(cout, cin_pad, 27, device=w.device, dtype=torch.float32)
         wp[:, :cin] = w.detach().reshape(cout, cin, 27)
@@ -354,8 +360,8 @@ class Conv3dBnReluPool(torch.autograd.Function):
         dev = x.device
         d = capi.conv_desc(n, (D, H, W), cin_pad, cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         need_x_grad = ctx.needs_input_grad[0]
-        pair = L().qt_conv_plan(d, 0) == 2
-        wf, wd = _conv3d_weights(w, cin_pad, need_x_grad, pair)
+        plan = L().qt_conv_plan(d, 0)
+        wf, wd = _conv3d_weights(w, cin_pad, need_x_grad, "c8" if plan == 3 else plan == 2)
         y = torch.empty(n, D, H, W, cout, device=dev, dtype=BF16)
         stats = ops.conv_fprop(d, x, wf, y, bias=b.detach(), relu=False, want_stats=training)
         m = n * D * H * W

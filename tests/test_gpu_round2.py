@@ -327,7 +327,7 @@ def test_lstm_dropout_between_layers(C):
 
 # Conv3d layers of Quadtree3DCNN at the BASELINE config-4 shapes (16 x 112 x 112 clips; maps after the pools), B = 2:
 # (cin, cout, D, H, W, expected forward plan: 0 gather kernel, 1 slab kernel, 2 slab kernel in pair mode)
-CONV3D_SHAPES = [(8, 32, 16, 112, 112, 0), (32, 64, 16, 56, 56, 2), (64, 128, 8, 28, 28, 1), (128, 256, 4, 14, 14, 1),
+CONV3D_SHAPES = [(8, 32, 16, 112, 112, 3), (8, 32, 3, 6, 10, 3), (8, 32, 1, 20, 130, 3), (32, 64, 16, 56, 56, 2), (64, 128, 8, 28, 28, 1), (128, 256, 4, 14, 14, 1),
                  (256, 1024, 4, 7, 7, 1), (64, 64, 3, 5, 6, 1), (32, 32, 1, 4, 9, 2)]
 
 
@@ -353,7 +353,11 @@ def test_conv3d_kernels(C, cin, cout, D, H, W, plan):
     xn = x.permute(0, 2, 3, 4, 1).contiguous()
     wparam = torch.nn.Parameter(wb.clone())
     with torch.enable_grad():
-        wf = ops.packed_pair(wparam) if plan == 2 else ops.packed_fprop(wparam)
+        if plan == 3:
+            wf = torch.empty(18, 2, 32, 8, device="cuda", dtype=torch.bfloat16)
+            C.check(lib.qt_wpack_conv3d_c8(C.ptr(wparam.detach().contiguous()), C.ptr(wf), cout, cin, C.stream()))
+        else:
+            wf = ops.packed_pair(wparam) if plan == 2 else ops.packed_fprop(wparam)
         wd = ops.packed_dgrad(wparam)
     y = torch.full((n, D, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     stats = ops.conv_fprop(d, xn, wf, y, bias=bias, want_stats=True)
