@@ -291,12 +291,12 @@ int qt_grad_clip_coef(const void* items_dev, int nitems, int total_blocks, float
 
 /* ---- nn.LSTM(batch_first=True) layers (3dcnn/models.py:144-158,200-203; cnn+lstm/models.py:43-49,82-85) ---------------- */
 int qt_transpose_f32(const float* in, float* out, int rows, int cols, qt_stream_t stream);
-/* One layer over the whole sequence: x [b][t][in_dim] fp32, wih_t [in_dim][4h], whh_t [h][4h] (transposed torch weights,
- * gate order i,f,g,o), zero initial state. in_drop_p > 0 applies nn.LSTM's inter-layer dropout to x (counter-hash mask).
- * Outputs hseq / hprev / cseq [b][t][h], activated gates [b][t][4h], optional x_used [b][t][in_dim] (x after dropout). h <= 256. */
-int qt_lstm_layer_fwd(const float* x, int in_dim, const float* wih_t, const float* whh_t, const float* bih, const float* bhh, int b,
-                      int t, int h, float in_drop_p, unsigned long long seed, float* hseq, float* hprev, float* cseq, float* gates,
-                      float* x_used, qt_stream_t stream);
+/* Recurrence of one layer over the whole sequence on clusters of 8 CTAs with the recurrent weights resident in shared memory:
+ * xproj [b][t][4h] fp32 = x Wih^T + b_ih for every step (one qt_small_linear_fwd over b*t rows; nn.LSTM's inter-layer dropout is
+ * applied to x before that), whh_t [h][4h] (transposed torch weight, gate order i,f,g,o), bhh [4h] or NULL, zero initial state.
+ * Outputs hseq / hprev / cseq [b][t][h] and the activated gates [b][t][4h]. h <= 256. */
+int qt_lstm_layer_fwd(const float* xproj, const float* whh_t, const float* bhh, int b, int t, int h, float* hseq, float* hprev,
+                      float* cseq, float* gates, qt_stream_t stream);
 /* BPTT of one layer: dhseq [b][t][h] (gradient reaching every h_t; out_drop_p/seed: mask of the dropout that sat between
  * this layer's output and its consumer), whh [4h][h] (torch layout) -> dgates [b][t][4h] (pre-activation gate gradients).
  * dX = dgates . wih, dWih = dgates^T x_used, dWhh = dgates^T hprev, db = colsum(dgates) are plain batched products

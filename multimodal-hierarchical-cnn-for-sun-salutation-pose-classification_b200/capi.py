@@ -112,8 +112,7 @@ _SIGNATURES = {
     "qt_head_tail_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_float, c_ulonglong, c_void_p,
                                  c_void_p, c_int, c_void_p]),
     "qt_transpose_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "qt_lstm_layer_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_ulonglong,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qt_lstm_layer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qt_lstm_layer_bwd": (c_int, [c_void_p, c_float, c_ulonglong, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qt_adam_item_plan": (c_int, [ctypes.POINTER(AdamItem)]),
     "qt_adam_multi": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdamGroup), c_int, c_void_p, c_float, c_void_p]),

@@ -544,6 +544,28 @@ int run_wgrad3x3(const W3Plan& pl, const qt_conv_desc* d, const void* x, const v
   return cuda_status("splitk_reduce_wgrad_kernel");
 }
 
+template <typename K, typename... Args>
+int launch_cluster8(K kernel, int clusters, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kLstmCluster);
+  cfg.blockDim = dim3(kLstmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kLstmCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "lstm cluster launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1439,39 +1461,36 @@ int qt_transpose_f32(const float* in, float* out, int rows, int cols, qt_stream_
   transpose_f32_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, S(stream)>>>(in, out, rows, cols);
   return cuda_status("transpose_f32");
 }
-namespace {
-int lstm_threads(int h) { return ((4 * h + 31) / 32) * 32; }
-}  // namespace
-int qt_lstm_layer_fwd(const float* x, int in_dim, const float* wih_t, const float* whh_t, const float* bih, const float* bhh, int b,
-                      int t, int h, float in_drop_p, unsigned long long seed, float* hseq, float* hprev, float* cseq, float* gates,
-                      float* x_used, qt_stream_t stream) {
+int qt_lstm_layer_fwd(const float* xproj, const float* whh_t, const float* bhh, int b, int t, int h, float* hseq, float* hprev,
+                      float* cseq, float* gates, qt_stream_t stream) {
   if (b < 1 || t < 1) return 0;
-  if (h < 1 || 4 * h > 1024) return fail("lstm: hidden size must be <= 256 (got %d)", h);
-  if (in_dim < 1) return fail("lstm: bad input size");
-  const size_t smem = sizeof(float) * kLstmBT * (static_cast<size_t>(in_dim) + 5 * h);
-  if (smem > 200 * 1024) return fail("lstm: input size %d too large for the shared-memory staging", in_dim);
+  if (h < 1 || h > 256) return fail("lstm: hidden size must be <= 256 (got %d)", h);
+  const int hs = (h + kLstmCluster - 1) / kLstmCluster;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(h) * 4 * hs + 2 * kLstmBT * h + kLstmBT * 4 * hs);
   static size_t configured = 0;
   if (configured < smem) {
     cudaFuncSetAttribute(lstm_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  lstm_layer_fwd_kernel<<<(b + kLstmBT - 1) / kLstmBT, lstm_threads(h), smem, S(stream)>>>(x, in_dim, wih_t, whh_t, bih, bhh, b, t, h,
-                                                                                           in_drop_p, seed, hseq, hprev, cseq, gates,
-                                                                                           x_used);
+  if (int rc = launch_cluster8(lstm_layer_fwd_kernel, (b + kLstmBT - 1) / kLstmBT, smem, S(stream), xproj, whh_t, bhh, b, t, h, hs, hseq,
+                               hprev, cseq, gates))
+    return rc;
   return cuda_status("lstm_layer_fwd");
 }
 int qt_lstm_layer_bwd(const float* dhseq, float out_drop_p, unsigned long long seed, const float* whh, const float* gates,
                       const float* cseq, int b, int t, int h, float* dgates, qt_stream_t stream) {
   if (b < 1 || t < 1) return 0;
-  if (h < 1 || 4 * h > 1024) return fail("lstm: hidden size must be <= 256 (got %d)", h);
-  const size_t smem = sizeof(float) * kLstmBT * (static_cast<size_t>(4 * h) + h + 4 * h);
+  if (h < 1 || h > 256) return fail("lstm: hidden size must be <= 256 (got %d)", h);
+  const int hs = (h + kLstmCluster - 1) / kLstmCluster;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(4 * h) * hs + 2 * kLstmBT * 4 * h + kLstmBT * hs + 512);
   static size_t configured = 0;
   if (configured < smem) {
     cudaFuncSetAttribute(lstm_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  lstm_layer_bwd_kernel<<<(b + kLstmBT - 1) / kLstmBT, lstm_threads(h), smem, S(stream)>>>(dhseq, out_drop_p, seed, whh, gates, cseq, b,
-                                                                                           t, h, dgates);
+  if (int rc = launch_cluster8(lstm_layer_bwd_kernel, (b + kLstmBT - 1) / kLstmBT, smem, S(stream), dhseq, out_drop_p, seed, whh, gates,
+                               cseq, b, t, h, hs, dgates))
+    return rc;
   return cuda_status("lstm_layer_bwd");
 }
 

@@ -212,21 +212,26 @@ class LSTM(torch.autograd.Function):
             wih, whh, bih, bhh = weights[4 * l: 4 * l + 4]
             G, I = wih.shape
             H = whh.shape[1]
-            wih_t = torch.empty(I, G, device=dev)
             whh_t = torch.empty(H, G, device=dev)
-            check(L().qt_transpose_f32(ptr(wih.detach().contiguous()), ptr(wih_t), G, I, stream()), "lstm transpose")
             check(L().qt_transpose_f32(ptr(whh.detach().contiguous()), ptr(whh_t), G, H, stream()), "lstm transpose")
+            in_p = p if l > 0 else 0.0
+            seed = ops.new_seed() if in_p > 0 else 0
+            x_used = None
+            if in_p > 0:  # nn.LSTM's inter-layer dropout: a dropped-out copy of the previous layer's output (counter-hash mask)
+                x_used = cur.clone()
+                check(L().qt_relu_dropout(ptr(x_used), None, x_used.numel(), in_p, seed, 0, stream()), "lstm dropout")
+            xin_l = x_used if x_used is not None else cur
+            # input projection of every time step in one batched product: [B*T, I] x Wih^T + b_ih
+            xproj = torch.empty(bsz, T, G, device=dev)
+            check(L().qt_small_linear_fwd(ptr(xin_l), 0, I, ptr(wih.detach().contiguous()), ptr(bih.detach()) if bih is not None else None,
+                                          bsz * T, G, I, 0, 0.0, 0, ptr(xproj), G, None, 0, stream()), "lstm input projection")
             hseq = torch.empty(bsz, T, H, device=dev)
             hprev = torch.empty_like(hseq)
             cseq = torch.empty_like(hseq)
             gates = torch.empty(bsz, T, G, device=dev)
-            in_p = p if l > 0 else 0.0
-            seed = ops.new_seed() if in_p > 0 else 0
-            x_used = torch.empty_like(cur) if in_p > 0 else None
-            check(L().qt_lstm_layer_fwd(ptr(cur), I, ptr(wih_t), ptr(whh_t), ptr(bih.detach()) if bih is not None else None,
-                                        ptr(bhh.detach()) if bhh is not None else None, bsz, T, H, in_p, seed, ptr(hseq), ptr(hprev),
-                                        ptr(cseq), ptr(gates), ptr(x_used), stream()), "lstm_layer_fwd")
-            ops._count(3)
+            check(L().qt_lstm_layer_fwd(ptr(xproj), ptr(whh_t), ptr(bhh.detach()) if bhh is not None else None, bsz, T, H, ptr(hseq),
+                                        ptr(hprev), ptr(cseq), ptr(gates), stream()), "lstm_layer_fwd")
+            ops._count(4)
             saved.append((x_used if x_used is not None else cur, hprev, cseq, gates, in_p, seed))
             cur = hseq
         if any(ctx.needs_input_grad):
