@@ -155,6 +155,10 @@ int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, 
                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                    float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
                    qt_stream_t stream);
+/* qt_bn_finalize that also increments nn.BatchNorm's `num_batches_tracked` (int64 device scalar, may be NULL) in the same launch */
+int qt_bn_finalize_tracked(const float* partial, int partial_rows, int c, double count, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                           float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes, qt_stream_t stream);
 /* eval mode: coefficients from the running statistics (mean/invstd are also returned for the backward). */
 int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, float* mean, float* invstd, float* scale, float* shift,

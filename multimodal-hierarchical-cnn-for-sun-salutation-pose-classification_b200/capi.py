@@ -156,6 +156,8 @@ _SIGNATURES = {
     "qt_bn_stats": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_int, c_void_p]),
     "qt_bn_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qt_bn_finalize_tracked": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "qt_bn_eval_coeffs": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "qt_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),

@@ -333,7 +333,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int S, int C
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                   long long* __restrict__ num_batches_tracked) {
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
@@ -393,8 +395,10 @@ __global__ void bn_finalize_rows_kernel(const float* __restrict__ partial, int T
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                         float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                        float* __restrict__ scale_out, float* __restrict__ shift_out) {
+                                        float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                        long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * 32 + threadIdx.x;
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *num_batches_tracked += 1;
   double s1, s2;
   reduce_rows_2(partial, T, C, c, threadIdx.y, s1, s2);
   if (threadIdx.y != 0 || c >= C) return;
@@ -1096,7 +1100,16 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_pool_fwd_kernel(const __n
     __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qt_smem);  // [QH*QW][Cq]
     const int n16 = QH * QW * Cq / 8;
     const uint4* src = reinterpret_cast<const uint4*>(q + (static_cast<long long>(part) * B + b) * QH * QW * Cq);
-    for (int i = threadIdx.x; i < n16; i += kQtThreads) reinterpret_cast<uint4*>(tile)[i] = ld_nc16(src + i);
+    // all of a thread's 16-byte loads are issued before the first one is consumed (four per batch: 784 chunks / 256 threads)
+    for (int i0 = threadIdx.x; i0 < n16; i0 += 4 * kQtThreads) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k * kQtThreads < n16) v[k] = ld_nc16(src + i0 + k * kQtThreads);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k * kQtThreads < n16) reinterpret_cast<uint4*>(tile)[i0 + k * kQtThreads] = v[k];
+    }
     __syncthreads();
     const int PP = PH * PW;
     const int nout8 = Cq * PP / 8;
@@ -1128,11 +1141,19 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_pool_fwd_kernel(const __n
     for (int c0 = warp * 64; c0 < Cg; c0 += (kQtThreads / 32) * 64) {
       const int c = c0 + (lane & 7) * 8;
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int p = phase; p < GHW; p += 4) {
-        float f[8];
-        unpack8(ld_nc16(src + static_cast<long long>(p) * Cg + c), f);
+      for (int p0 = phase; p0 < GHW; p0 += 16) {  // four pixels in flight per lane
+        uint4 v[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        for (int k = 0; k < 4; ++k)
+          if (p0 + 4 * k < GHW) v[k] = ld_nc16(src + static_cast<long long>(p0 + 4 * k) * Cg + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (p0 + 4 * k < GHW) {
+            float f[8];
+            unpack8(v[k], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += f[e];
+          }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -1198,13 +1219,25 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_pool_bwd_kernel(const __n
   } else {
     const int nch = Cg / 8;
     const float inv_n = static_cast<float>(GHW);
-    for (int i = threadIdx.x; i < GHW * nch; i += kQtThreads) {
-      const int ch = i % nch, p = i / nch;
+    if (kQtThreads % nch == 0) {
+      // the thread's channel chunk never changes: one load, one divide, GHW * nch / 256 stores
+      const int ch = threadIdx.x % nch;
       float f[8];
       unpack8(ld_nc16(dfeat + static_cast<long long>(b) * ldf + ch * 8), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = f[e] / inv_n;
-      *reinterpret_cast<uint4*>(dl4 + (static_cast<long long>(b) * GHW + p) * Cg + ch * 8) = pack8(f);
+      const uint4 v = pack8(f);
+      for (int p = threadIdx.x / nch; p < GHW; p += kQtThreads / nch)
+        *reinterpret_cast<uint4*>(dl4 + (static_cast<long long>(b) * GHW + p) * Cg + ch * 8) = v;
+    } else {
+      for (int i = threadIdx.x; i < GHW * nch; i += kQtThreads) {
+        const int ch = i % nch, p = i / nch;
+        float f[8];
+        unpack8(ld_nc16(dfeat + static_cast<long long>(b) * ldf + ch * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = f[e] / inv_n;
+        *reinterpret_cast<uint4*>(dl4 + (static_cast<long long>(b) * GHW + p) * Cg + ch * 8) = pack8(f);
+      }
     }
   }
 }

@@ -1064,23 +1064,37 @@ int qt_bn_stats(const void* y, long long m, int c, float* partial, int partial_r
       static_cast<const __nv_bfloat16*>(y), m, c, partial);
   return cuda_status("bn_stats");
 }
-int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, const float* gamma,
-                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                   float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
-                   qt_stream_t stream) {
+static int bn_finalize_impl(const float* partial, int partial_rows, int c, double count, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, long long* nbt, float* mean,
+                            float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes, qt_stream_t stream) {
   if (ws_bytes < static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double)) return fail("bn_finalize: workspace too small");
   if (partial_rows <= kDirectRows) {
     bn_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, partial_rows, c, count, gamma, beta, eps,
                                                                           momentum, running_mean, running_var, mean, invstd,
-                                                                          scale, shift);
+                                                                          scale, shift, nbt);
     return cuda_status("bn_finalize_rows");
   }
   double* sums = static_cast<double*>(ws);
   int slices = 0;
   if (int rc = reduce_partials(partial, partial_rows, 2 * c, sums, &slices, S(stream))) return rc;
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slices, c, count, gamma, beta, eps, momentum,
-                                                              running_mean, running_var, mean, invstd, scale, shift);
+                                                              running_mean, running_var, mean, invstd, scale, shift, nbt);
   return cuda_status("bn_finalize");
+}
+int qt_bn_finalize(const float* partial, int partial_rows, int c, double count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes,
+                   qt_stream_t stream) {
+  return bn_finalize_impl(partial, partial_rows, c, count, gamma, beta, eps, momentum, running_mean, running_var, nullptr, mean,
+                          invstd, scale, shift, ws, ws_bytes, stream);
+}
+/* The same, also counting the batch in nn.BatchNorm's `num_batches_tracked` (an int64 device scalar, may be NULL): the
+ * increment rides on the finalize launch instead of one ATen kernel per BatchNorm layer per step. */
+int qt_bn_finalize_tracked(const float* partial, int partial_rows, int c, double count, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                           float* mean, float* invstd, float* scale, float* shift, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  return bn_finalize_impl(partial, partial_rows, c, count, gamma, beta, eps, momentum, running_mean, running_var,
+                          num_batches_tracked, mean, invstd, scale, shift, ws, ws_bytes, stream);
 }
 int qt_bn_eval_coeffs(int c, const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, float* mean, float* invstd, float* scale, float* shift,

@@ -354,12 +354,14 @@ def bn_finalize(stats, count, bn, c, device, training=True) -> BNState:
         ws = workspace(L().qt_bn_workspace_bytes(c), device, "bn")
         track = bn.track_running_stats and bn.running_mean is not None
         momentum = 0.1 if bn.momentum is None else float(bn.momentum)
-        check(L().qt_bn_finalize(ptr(stats), stats.shape[0], c, float(count), ptr(gamma), ptr(beta), float(bn.eps), momentum,
-                                 ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
-                                 ptr(st.mean), ptr(st.invstd), ptr(st.scale), ptr(st.shift), ptr(ws), ws.numel(), stream()),
+        nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda
+                                         and bn.num_batches_tracked.dtype == torch.int64) else None
+        check(L().qt_bn_finalize_tracked(ptr(stats), stats.shape[0], c, float(count), ptr(gamma), ptr(beta), float(bn.eps), momentum,
+                                         ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None, ptr(nbt),
+                                         ptr(st.mean), ptr(st.invstd), ptr(st.scale), ptr(st.shift), ptr(ws), ws.numel(), stream()),
               "bn_finalize")
         _count(2)
-        if track and bn.num_batches_tracked is not None:
+        if nbt is None and track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
     else:
         check(L().qt_bn_eval_coeffs(c, ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), float(bn.eps),
