@@ -1089,7 +1089,7 @@ __global__ void quadtree_pool_bwd_generic_kernel(const __nv_bfloat16* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int kQtThreads = 256;
 
-__global__ void __launch_bounds__(kQtThreads) quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q,
+__global__ void __launch_bounds__(kQtThreads, 6) quadtree_pool_fwd_kernel(const __nv_bfloat16* __restrict__ q,
                                                                        const __nv_bfloat16* __restrict__ l4,
                                                                        __nv_bfloat16* __restrict__ feat, int B, int QH, int QW,
                                                                        int Cq, int GHW, int Cg, int ldf) {
@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_pool_fwd_kernel(const __n
 // Backward, scatter-free: the quadrant part re-derives the (first) arg-max of every 2x2 window from q, masks by the
 // fused ReLU (max > 0) and routes the gradient of output c*(PH*PW)+ph*PW+pw to that pixel, writing all four pixels of
 // the window (and the row / column the floor-mode pool dropped) as 16-byte chunks; the global part broadcasts dfeat/GHW.
-__global__ void __launch_bounds__(kQtThreads) quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat,
+__global__ void __launch_bounds__(kQtThreads, 8) quadtree_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat,
                                                                        const __nv_bfloat16* __restrict__ q,
                                                                        __nv_bfloat16* __restrict__ dq,
                                                                        __nv_bfloat16* __restrict__ dl4, int B, int QH, int QW,
