@@ -81,7 +81,7 @@ def test_ncu_summary_is_reproducible_from_the_committed_launch_list(tmp_path):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    src = os.path.join(root, "profiles", "r01_ncu_gemm_launches.csv")
+    src = os.path.join(root, "profiles", "r02_ncu_gemm_launches.csv")  # the capture ncu_gemm_summary.json was last regenerated from
     out = tmp_path / "summary.json"
     subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), src, str(out)], check=True, capture_output=True)
     with open(out) as f, open(os.path.join(root, "profiles", "ncu_gemm_summary.json")) as g:
