@@ -37,6 +37,8 @@ enum : int {
   EPI_ADDEND = 8,   // out = acc + addend (bf16, same view as out)
   EPI_OUT_F32 = 16, // store fp32 instead of bf16
   EPI_SPLITK = 32,  // store raw fp32 partials into the split-K workspace
+  EPI_WGRAD_DIRECT = 64,  // weight-gradient kernel, one split, one tap (linear layers): write dw[nout][F] straight from the
+                          // accumulator (+= with EPI_ADDEND) instead of a workspace round trip through the reduce kernel
 };
 
 struct View4 {  // element strides of an (n, d, h, w, c) view; c is contiguous
@@ -635,7 +637,21 @@ __global__ void __launch_bounds__(NPW == 8 ? kGemmThreadsWide : kGemmThreads, 2)
       tmem_ld_wait();
       const int ncol = n0 + c0;
       if (ncol >= p.Npad) break;
-      if (f < p.Mpad) {
+      if (p.flags & EPI_WGRAD_DIRECT) {
+        // dw[n][f]: for a fixed column the 32 lanes (consecutive f) write 128 contiguous bytes
+        const int F = p.ntaps * p.cin;
+        if (f < F) {
+          float* dw = reinterpret_cast<float*>(p.out) + f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (ncol + j < p.nout) {
+              float* dst = dw + static_cast<long long>(ncol + j) * F;
+              const float v = __uint_as_float(r[j]);
+              *dst = (p.flags & EPI_ADDEND) ? (*dst + v) : v;
+            }
+          }
+        }
+      } else if (f < p.Mpad) {
         float* dst = p.splitk_ws + (static_cast<long long>(blockIdx.z) * p.Mpad + f) * p.Npad + ncol;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -673,13 +689,18 @@ __global__ void splitk_reduce_rows_kernel(const float* __restrict__ ws, int nspl
 // CT x 32 tile is transposed through shared memory so the gradient is written with lanes along c (contiguous for
 // linear layers, stride ntaps for convs). CT = 8 is for the small layers (64x64x9 has only 36 tiles of 32x32, and
 // up to 148 splits to sum: the narrow tile spreads that over 144 blocks). accumulate != 0 adds.
-template <int CT>
-__global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsplit, int F, int N, int Mpad, int Npad,
-                                           int cin, int ntaps, float* __restrict__ grad, int accumulate) {
-  __shared__ float tile[CT][33];  // [c][n]
+template <int CT, int ZS>
+__global__ void __launch_bounds__(256 * ZS) splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsplit, int F, int N, int Mpad,
+                                                                       int Npad, int cin, int ntaps, float* __restrict__ grad,
+                                                                       int accumulate) {
+  // ZS > 1: the splits are divided over ZS groups of 8 warps (more loads in flight when few blocks must sum many
+  // partials, e.g. 148 partials of a 64x64x9 filter); the groups' sums are combined in fixed order
+  __shared__ float tile[ZS][CT][33];  // [z slice][c][n]
   const int c0 = blockIdx.x * CT, n0 = blockIdx.y * 32, tap = blockIdx.z;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wrp = (threadIdx.x >> 5) & 7, zs = threadIdx.x >> 8;
   const long long zstride = static_cast<long long>(Mpad) * Npad;
+  const int zper = (nsplit + ZS - 1) / ZS;
+  const int z_begin = zs * zper, z_end = min(nsplit, z_begin + zper);
 #pragma unroll
   for (int j = 0; j < CT / 8; ++j) {
     const int cl = wrp * (CT / 8) + j;
@@ -688,17 +709,18 @@ __global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsp
     if (c < cin && n < N) {
       const float* src = ws + (static_cast<long long>(tap) * cin + c) * Npad + n;
       float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int z = 0;
-      for (; z + 8 <= nsplit; z += 8) {
+      int z = z_begin;
+      for (; z + 8 <= z_end; z += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) a[u] += src[(z + u) * zstride];
       }
-      for (; z < nsplit; ++z) a[0] += src[z * zstride];
+      for (; z < z_end; ++z) a[0] += src[z * zstride];
       acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
-    tile[cl][lane] = acc;
+    tile[zs][cl][lane] = acc;
   }
   __syncthreads();
+  if (threadIdx.x >= 256) return;
   constexpr int kCLanes = CT < 32 ? CT : 32;  // lanes along c in the write phase
   const int wc = threadIdx.x % kCLanes;
   for (int nl = threadIdx.x / kCLanes; nl < 32; nl += 256 / kCLanes) {
@@ -706,7 +728,9 @@ __global__ void splitk_reduce_wgrad_kernel(const float* __restrict__ ws, int nsp
       const int n = n0 + nl, c = c0 + cl;
       if (c < cin && n < N) {
         float* dst = grad + (static_cast<long long>(n) * cin + c) * ntaps + tap;
-        const float v = tile[cl][nl];
+        float v = tile[0][cl][nl];
+#pragma unroll
+        for (int q = 1; q < ZS; ++q) v += tile[q][cl][nl];
         *dst = accumulate ? (*dst + v) : v;
       }
     }
@@ -717,10 +741,11 @@ inline void launch_splitk_reduce_wgrad(const float* ws, int nsplit, int F, int N
   const long long blocks32 = static_cast<long long>((cin + 31) / 32) * ((N + 31) / 32) * ntaps;
   if (blocks32 >= 296) {
     dim3 g((cin + 31) / 32, (N + 31) / 32, ntaps);
-    splitk_reduce_wgrad_kernel<32><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
+    splitk_reduce_wgrad_kernel<32, 1><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
   } else {
     dim3 g((cin + 7) / 8, (N + 31) / 32, ntaps);
-    splitk_reduce_wgrad_kernel<8><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
+    if (nsplit >= 32) splitk_reduce_wgrad_kernel<8, 4><<<g, 1024, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
+    else splitk_reduce_wgrad_kernel<8, 1><<<g, 256, 0, st>>>(ws, nsplit, F, N, Mpad, Npad, cin, ntaps, grad, accumulate);
   }
 }
 

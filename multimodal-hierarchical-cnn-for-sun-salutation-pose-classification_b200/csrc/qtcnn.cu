@@ -204,11 +204,17 @@ int run_wgrad(IgemmParams p, cudaStream_t st, void* ws, size_t ws_bytes, float* 
     p.adv_n = r;
   }
   dim3 grid(gx, gy, p.groups * ksplit);
+  // one split, one tap, one group (linear layers with enough tiles): the epilogue writes dw itself
+  const bool direct = ksplit == 1 && p.groups == 1 && taps_real == 1 && cin_real == F && g_tune[8] == 0;
+  if (direct) {
+    p.out = dw;
+    p.flags = EPI_WGRAD_DIRECT | (accumulate ? EPI_ADDEND : 0);
+  }
   int rc;
   if (g_tune[0] == 1) rc = (BN == 64) ? launch_wgrad<64, 8, 3, 8>(p, grid, st) : launch_wgrad<128, 6, 3, 8>(p, grid, st);
   else if (g_tune[0] == 2) rc = (BN == 64) ? launch_wgrad<64, 4, 1, 4>(p, grid, st) : launch_wgrad<128, 3, 1, 4>(p, grid, st);
   else rc = (BN == 64) ? launch_wgrad<64, 4, 1, 8>(p, grid, st) : launch_wgrad<128, 3, 1, 8>(p, grid, st);
-  if (rc) return rc;
+  if (rc || direct) return rc;
   launch_splitk_reduce_wgrad(p.splitk_ws, p.groups * ksplit, F, p.nout, p.Mpad, p.Npad, cin_real, taps_real, dw, accumulate, st);
   return cuda_status("splitk_reduce_wgrad_kernel");
 }

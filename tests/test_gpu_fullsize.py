@@ -97,3 +97,35 @@ def test_full_size_eval_is_permutation_equivariant(setup):
         shuffled = model(images[perm].contiguous(), numerical[perm].contiguous())
     assert torch.equal(shuffled, base[perm])
     assert bool(torch.isfinite(base).all())
+
+
+def test_level12_inference_at_config_batch():
+    """BASELINE.json configs[1]: AttentionHierarchicalCNN (level-1 2x2 + level-2 4x4 quadtree) inference, 224x224, batch 256,
+    eval mode with non-trivial running statistics, against the fp32 oracle evaluated on the GPU; plus batch-permutation
+    equivariance (region assignment and pooling never couple samples)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from oracle import quadtree_oracle as O
+    from qtcnn_b200 import models as M
+    p = O.make_params("attention_hierarchical", 8, seed=1)
+    g = torch.Generator().manual_seed(7)
+    for k in list(p):
+        if k.endswith("running_mean"):
+            p[k] = 0.1 * torch.randn(p[k].shape, generator=g)
+        if k.endswith("running_var"):
+            p[k] = 0.5 + torch.rand(p[k].shape, generator=g)
+    images, numerical, _ = O.synthetic_batch(B, 99)
+    images, numerical = images.cuda(), numerical.cuda()
+    model = M.AttentionHierarchicalCNN(num_classes=8)
+    load_oracle_params(model, p)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(images, numerical)
+        ref = O.attention_hier_forward({k: v.cuda() for k, v in p.items()}, images, numerical, training=False)
+        perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+        shuffled = model(images[perm].contiguous(), numerical[perm].contiguous())
+    assert out.shape == (B, 8) and out.dtype == torch.float32
+    err = float((out - ref).abs().max())
+    print(f"level-1+2 inference B={B}: logits max abs err {err:.3e} / max |logit| {float(ref.abs().max()):.3f}")
+    assert err <= parity.LOGIT_TOL * float(ref.abs().max())
+    assert torch.equal(shuffled, out[perm])
