@@ -499,11 +499,10 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
   };
   if (fixed && i0 < total8) load_coef(i0);
-  for (long long i = i0; i < total8; i += stride) {
-    if (!fixed) load_coef(i);
+  auto one = [&](long long i, const uint4& qy, const uint4& qr) {
     float f[8], r[8];
-    unpack8(ld_nc16(y + i * 8), f);
-    if (residual) unpack8(ld_nc16(residual + i * 8), r);
+    unpack8(qy, f);
+    if (residual) unpack8(qr, r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = fmaf(f[e], sc[e], sh[e]);
@@ -512,6 +511,25 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
       f[e] = v;
     }
     *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  };
+  long long i = i0;
+  if (fixed) {
+    // two vectors per iteration: all loads of both are issued before either is consumed
+    for (; i + stride < total8; i += 2 * stride) {
+      const long long j = i + stride;
+      const uint4 y0 = ld_nc16(y + i * 8), y1 = ld_nc16(y + j * 8);
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+      if (residual) { r0 = ld_nc16(residual + i * 8); r1 = ld_nc16(residual + j * 8); }
+      one(i, y0, r0);
+      one(j, y1, r1);
+    }
+  }
+  for (; i < total8; i += stride) {
+    if (!fixed) load_coef(i);
+    const uint4 y0 = ld_nc16(y + i * 8);
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    if (residual) r0 = ld_nc16(residual + i * 8);
+    one(i, y0, r0);
   }
 }
 
@@ -626,12 +644,11 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
     }
   };
   if (fixed && i0 < total8) load_coef(i0);
-  for (long long i = i0; i < total8; i += stride) {
-    if (!fixed) load_coef(i);
+  auto one = [&](long long i, const uint4& qd, const uint4& qv, const uint4& qa) {
     float d[8], a[8], v[8], o[8];
-    unpack8(ld_nc16(dout + i * 8), d);
-    unpack8(ld_nc16(y + i * 8), v);
-    if (act) unpack8(ld_nc16(act + i * 8), a);
+    unpack8(qd, d);
+    unpack8(qv, v);
+    if (act) unpack8(qa, a);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const bool off = act ? !(a[e] > 0.f) : (ymask && !(fmaf(v[e], ms[e], mh[e]) > 0.f));
@@ -641,6 +658,15 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, cons
     }
     *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
     if (dz_out) *reinterpret_cast<uint4*>(dz_out + i * 8) = pack8(d);
+  };
+  // (two vectors per iteration, as in bn_apply_kernel, measured 4 % slower here: five streams per thread already)
+  long long i = i0;
+  for (; i < total8; i += stride) {
+    if (!fixed) load_coef(i);
+    const uint4 d0 = ld_nc16(dout + i * 8), v0 = ld_nc16(y + i * 8);
+    uint4 a0 = make_uint4(0, 0, 0, 0);
+    if (act) a0 = ld_nc16(act + i * 8);
+    one(i, d0, v0, a0);
   }
 }
 
