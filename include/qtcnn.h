@@ -207,6 +207,16 @@ int qt_region_avgpool_fwd(const void* x, void* out, long long regions, int p, in
 int qt_region_avgpool_bwd(const void* dout, const void* x, void* dx, long long regions, int p, int c, long long ldo,
                           int relu_mask, qt_stream_t stream);
 
+/* Conv3d block tail (3dcnn/models.py:108-135: BatchNorm3d + ReLU + MaxPool3d((1|2,2,2))) fused: forward writes the pooled
+ * activation, the raw conv output at the arg-max (yarg) and the int8 arg-max code (both NULL in inference); backward returns dy
+ * w.r.t. the raw conv output, dgamma/dbeta and (optionally) the gradient of the conv bias, without the full-size activation.
+ * Replaces qt_bn_apply + qt_maxpool3d_fwd and qt_maxpool3d_bwd + qt_bn_backward + qt_colsum; bit-identical to them. */
+int qt_bn_relu_maxpool3d_fwd(const void* y, const float* scale, const float* shift, void* out, void* yarg, void* argmax, int n,
+                             int d, int h, int w, int c, int kd, int kh, int kw, qt_stream_t stream);
+int qt_bn_relu_maxpool3d_bwd(const void* dpool, const void* argmax, const void* y, const void* yarg, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* gamma, int n, int d, int h,
+                             int w, int c, int kd, int kh, int kw, float* dgamma, float* dbeta, float* dbias, int eval_mode,
+                             void* dy, void* ws, size_t ws_bytes, qt_stream_t stream);
 /* MaxPool3d with kernel == stride, no padding (3dcnn/models.py:111-135) on NDHWC bf16. */
 int qt_maxpool3d_fwd(const void* x, void* out, void* argmax, int n, int d, int h, int w, int c, int kd, int kh, int kw,
                      qt_stream_t stream);

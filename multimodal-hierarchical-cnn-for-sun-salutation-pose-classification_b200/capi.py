@@ -180,6 +180,9 @@ _SIGNATURES = {
     "qt_region_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_void_p]),
     "qt_region_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_longlong, c_int,
                                       c_void_p]),
+    "qt_bn_relu_maxpool3d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
+    "qt_bn_relu_maxpool3d_bwd": (c_int, [c_void_p] * 9 + [c_int] * 8 + [c_void_p] * 3 + [c_int, c_void_p, c_void_p, c_size_t,
+                                         c_void_p]),
     "qt_maxpool3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "qt_maxpool3d_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

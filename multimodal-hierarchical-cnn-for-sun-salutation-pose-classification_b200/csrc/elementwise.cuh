@@ -423,11 +423,14 @@ __global__ void bn_bwd_finalize_rows_kernel(const float* __restrict__ partial, i
                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                             const float* __restrict__ gamma, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, int accumulate, int eval_mode,
-                                            float* __restrict__ coef) {
+                                            float* __restrict__ coef, float* __restrict__ dbias = nullptr) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s1, s2;
   reduce_rows_2(partial, T, C, c, threadIdx.y, s1, s2);
   if (threadIdx.y != 0 || c >= C) return;
+  // gradient of a bias added in front of this BatchNorm = sum over positions of dy = g*is*(s1 - count*c1 - c2*sum xhat):
+  // exactly zero under batch statistics (sum xhat = 0), g*is*s1 under running statistics
+  if (dbias) dbias[c] = eval_mode ? static_cast<float>((gamma ? gamma[c] : 1.0) * invstd[c] * s1) : 0.f;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s1) : static_cast<float>(s1);
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(s2) : static_cast<float>(s2);
   const double c1 = eval_mode ? 0.0 : s1 / count;
@@ -1366,6 +1369,115 @@ __global__ void maxpool3d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, con
       }
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv3d block tail fused (3dcnn/models.py:108-135): BatchNorm3d-apply + ReLU + MaxPool3d((KD,2,2), stride = kernel) in one
+// pass over the raw conv output. The full-resolution activation is never written: the pass stores the pooled activation, the
+// int8 arg-max code ((dz*2 + dy)*2 + dx, first maximum in that order, on the bf16-rounded activation: bit-identical to
+// bn_apply + maxpool3d_fwd) and `yarg`, the raw conv output at the arg-max. With yarg the backward statistics
+// (sum dz, sum dz*xhat) come from pooled-size tensors only (bn_bwd_reduce_kernel over the pooled rows, mask recomputed from
+// yarg), and the apply pass reads y once and writes dy once — the full-size `a` and `da` round trips are gone.
+// D % KD == 0, H and W even, C % 8 == 0, vector count < 2^31.
+// ---------------------------------------------------------------------------------------------
+template <int KD>
+__global__ void __launch_bounds__(256) bn_relu_maxpool3d_fwd_kernel(
+    const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ yarg, signed char* __restrict__ argmax, int N, int D, int H,
+    int W, int C) {
+  constexpr int kTaps = KD * 4;
+  const unsigned groups = C / 8, Wo = W / 2, Ho = H / 2, Do = D / KD;
+  const unsigned total = static_cast<unsigned>(N) * Do * Ho * Wo * groups;
+  const long long row = static_cast<long long>(W) * C, plane = row * H;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i;
+    const unsigned cg = r % groups; r /= groups;
+    const unsigned wo = r % Wo; r /= Wo;
+    const unsigned ho = r % Ho; r /= Ho;  // r = n * Do + do
+    const __nv_bfloat16* base = y + (static_cast<long long>(r) * KD * H + ho * 2) * row + static_cast<long long>(wo) * 2 * C + cg * 8;
+    uint4 v[kTaps];
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) v[t] = ld_nc16(base + (t >> 2) * plane + ((t >> 1) & 1) * row + (t & 1) * C);
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+    unsigned best2[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u}, bi2[4] = {0u, 0u, 0u, 0u}, ya2[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) {
+      const unsigned raw[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(raw[j] << 16), hi = __uint_as_float(raw[j] & 0xffff0000u);
+        const unsigned a2 = pack_bf16x2(fmaxf(fmaf(lo, sc[2 * j], sh[2 * j]), 0.f),
+                                        fmaxf(fmaf(hi, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+        const unsigned m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a2),
+                                       *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
+        best2[j] = (a2 & m) | (best2[j] & ~m);
+        ya2[j] = (raw[j] & m) | (ya2[j] & ~m);
+        bi2[j] = ((t * 0x00010001u) & m) | (bi2[j] & ~m);
+      }
+    }
+    const long long o = static_cast<long long>(i) * 8;
+    *reinterpret_cast<uint4*>(out + o) = make_uint4(best2[0], best2[1], best2[2], best2[3]);
+    if (yarg) {
+      *reinterpret_cast<uint4*>(yarg + o) = make_uint4(ya2[0], ya2[1], ya2[2], ya2[3]);
+      uint2 pk;
+      pk.x = __byte_perm(bi2[0], bi2[1], 0x6420);
+      pk.y = __byte_perm(bi2[2], bi2[3], 0x6420);
+      *reinterpret_cast<uint2*>(argmax + o) = pk;
+    }
+  }
+}
+// Backward apply: dy = A*dz + B*y + K at every full-resolution position (coef = [A | B | K] from bn_bwd_finalize_rows_kernel),
+// dz = dpool routed to the arg-max position and masked by ReLU (recomputed from y with the forward's own expression). One
+// thread per pooled vector: it reads its dpool / arg-max once and streams its KD*4 window positions of y -> dy.
+template <int KD>
+__global__ void __launch_bounds__(256) bn_pool3d_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dpool, const signed char* __restrict__ argmax, const __nv_bfloat16* __restrict__ y,
+    const float* __restrict__ coef, const float* __restrict__ msc, const float* __restrict__ msh, __nv_bfloat16* __restrict__ dy,
+    int N, int D, int H, int W, int C) {
+  constexpr int kTaps = KD * 4;
+  const unsigned groups = C / 8, Wo = W / 2, Ho = H / 2, Do = D / KD;
+  const unsigned total = static_cast<unsigned>(N) * Do * Ho * Wo * groups;
+  const long long row = static_cast<long long>(W) * C, plane = row * H;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i;
+    const unsigned cg = r % groups; r /= groups;
+    const unsigned wo = r % Wo; r /= Wo;
+    const unsigned ho = r % Ho; r /= Ho;
+    const long long off = (static_cast<long long>(r) * KD * H + ho * 2) * row + static_cast<long long>(wo) * 2 * C + cg * 8;
+    uint4 v[kTaps];
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) v[t] = ld_nc16(y + off + (t >> 2) * plane + ((t >> 1) & 1) * row + (t & 1) * C);
+    const uint4 qg = ld_nc16(dpool + static_cast<long long>(i) * 8);
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(argmax + static_cast<long long>(i) * 8));
+    float ca[8], cb[8], ck[8], ms[8], mh[8], g[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 4) {
+      *reinterpret_cast<float4*>(ca + e) = __ldg(reinterpret_cast<const float4*>(coef + cg * 8 + e));
+      *reinterpret_cast<float4*>(cb + e) = __ldg(reinterpret_cast<const float4*>(coef + C + cg * 8 + e));
+      *reinterpret_cast<float4*>(ck + e) = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + cg * 8 + e));
+      *reinterpret_cast<float4*>(ms + e) = __ldg(reinterpret_cast<const float4*>(msc + cg * 8 + e));
+      *reinterpret_cast<float4*>(mh + e) = __ldg(reinterpret_cast<const float4*>(msh + cg * 8 + e));
+    }
+    unpack8(qg, g);
+    int code[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) code[e] = ((e < 4 ? (pk.x >> (8 * e)) : (pk.y >> (8 * (e - 4)))) & 0xff);
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) {
+      float f[8], o[8];
+      unpack8(v[t], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool on = (code[e] == t) && (fmaf(f[e], ms[e], mh[e]) > 0.f);
+        o[e] = fmaf(ca[e], on ? g[e] : 0.f, fmaf(cb[e], f[e], ck[e]));
+      }
+      *reinterpret_cast<uint4*>(dy + off + (t >> 2) * plane + ((t >> 1) & 1) * row + (t & 1) * C) = pack8(o);
+    }
   }
 }
 

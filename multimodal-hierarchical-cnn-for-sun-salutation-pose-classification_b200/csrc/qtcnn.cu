@@ -337,7 +337,7 @@ bool c8_ok(const qt_conv_desc* d, int flags) {
   if (flags & (EPI_RELU | EPI_OUT_F32 | EPI_ADDEND)) return false;
   if (!dense_nhwc(d->x_stride, d->in_d, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, d->in_d, d->in_h, d->in_w, d->out_c)) return false;
   const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
-  return V <= (1ll << 30) && d->in_w <= 1024;
+  return V <= (1ll << 30) && d->in_w <= 250;  // (the weight-gradient producer keeps at most 5 slab rows per thread)
 }
 int c8_tiles(const qt_conv_desc* d) {
   const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
@@ -365,6 +365,34 @@ int run_conv3d_c8(const qt_conv_desc* d, const void* x, const void* wb, void* y,
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   conv3d_c8_kernel<<<grid, kC8Threads, smem, st>>>(p);
   return cuda_status("conv3d_c8_kernel");
+}
+
+size_t c8_wgrad_ws_bytes() { return static_cast<size_t>(kNumSMs) * 9 * 32 * 32 * sizeof(float); }
+int run_conv3d_c8_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  if (ws == nullptr || ws_bytes < c8_wgrad_ws_bytes()) return fail("conv3d_c8 wgrad: workspace too small");
+  Conv3dC8WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.partial = static_cast<float*>(ws);
+  p.NP = d->n * d->in_d; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.V = p.NP * (p.H + 1) * (p.W + 2);
+  p.num_tiles = (p.V + kC8wKP - 1) / kC8wKP;
+  p.R = kC8wKP + 2 * (p.W + 3) + 8;
+  p.debug = g_tune[9];
+  const size_t slab = (static_cast<size_t>(p.R) * 16 + 1023) / 1024 * 1024;
+  const size_t smem = 1024 + kC8wDy * ((8 * (kC8wKP * 16 + 16) + 127) / 128 * 128) + 1024 + kC8wSlabs * slab;
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(conv3d_c8_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = smem;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv3d_c8_wgrad_kernel<<<grid, kC8wThreads, smem, st>>>(p);
+  if (int rc = cuda_status("conv3d_c8_wgrad_kernel")) return rc;
+  conv3d_c8_wgrad_reduce_kernel<<<(32 * 8 * 27 + 255) / 256, 256, 0, st>>>(p.partial, grid, dw, 8, accumulate);
+  return cuda_status("conv3d_c8_wgrad_reduce");
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no link-time libcuda dependency).
@@ -718,6 +746,7 @@ int qt_conv_plan(const qt_conv_desc* d, int pass) {
     return pl.ok ? (pl.pair ? 2 : 1) : 0;  // 2: slab kernel on pair-packed weights (qt_wpack_conv3d_pair)
   }
   if (pass == 1) return plan_conv3x3(d, d->out_c, d->in_c, 0, true).ok ? 1 : 0;
+  if (c8_ok(d, 0)) return 3;
   return plan_wgrad3x3(d).ok ? 1 : 0;
 }
 int qt_conv_stat_rows(const qt_conv_desc* d) {
@@ -819,11 +848,14 @@ size_t qt_conv_wgrad_workspace_bytes(const qt_conv_desc* d) {
   const long long M = static_cast<long long>(d->n) * o.d * o.h * o.w;
   const size_t generic = wgrad_ws_bytes(d->k_d * d->k_h * d->k_w * d->in_c, d->out_c, d->groups, M, nullptr);
   const W3Plan pl = plan_wgrad3x3(d);
-  return (pl.ok && pl.ws_bytes > generic) ? pl.ws_bytes : generic;
+  size_t need = (pl.ok && pl.ws_bytes > generic) ? pl.ws_bytes : generic;
+  if (c8_ok(d, 0) && c8_wgrad_ws_bytes() > need) need = c8_wgrad_ws_bytes();
+  return need;
 }
 int qt_conv_wgrad(const qt_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
                   size_t ws_bytes, qt_stream_t stream) {
   if (int rc = check_desc(d)) return rc;
+  if (c8_ok(d, 0)) return run_conv3d_c8_wgrad(d, x, dy, dw, accumulate, ws, ws_bytes, S(stream));
   {
     const W3Plan pl = plan_wgrad3x3(d);
     if (pl.ok) return run_wgrad3x3(pl, d, x, dy, dw, accumulate, ws, ws_bytes, S(stream));
@@ -1320,6 +1352,58 @@ int qt_maxpool3d_bwd(const void* dout, const void* argmax, void* dx, int n, int 
                                                                     static_cast<const signed char*>(argmax),
                                                                     static_cast<__nv_bfloat16*>(dx), n, d, h, w, c, kd, kh, kw);
   return cuda_status("maxpool3d_bwd");
+}
+static int pool3d_fused_check(int n, int d, int h, int w, int c, int kd, int kh, int kw) {
+  if (c % 8 || c > 2048) return fail("bn_relu_maxpool3d: c must be a multiple of 8 and <= 2048");
+  if ((kd != 1 && kd != 2) || kh != 2 || kw != 2) return fail("bn_relu_maxpool3d: pool must be (1|2, 2, 2)");
+  if (d % kd || (h | w) & 1) return fail("bn_relu_maxpool3d: d must divide by kd, h and w must be even");
+  if (static_cast<long long>(n) * d * h * w * (c / 8) >= (1ll << 31)) return fail("bn_relu_maxpool3d: tensor too large for 32-bit indexing");
+  return 0;
+}
+int qt_bn_relu_maxpool3d_fwd(const void* y, const float* scale, const float* shift, void* out, void* yarg, void* argmax, int n,
+                             int d, int h, int w, int c, int kd, int kh, int kw, qt_stream_t stream) {
+  if (int rc = pool3d_fused_check(n, d, h, w, c, kd, kh, kw)) return rc;
+  if ((yarg == nullptr) != (argmax == nullptr)) return fail("bn_relu_maxpool3d_fwd: yarg and argmax go together");
+  const long long total = static_cast<long long>(n) * (d / kd) * (h / 2) * (w / 2) * (c / 8);
+  const int grid = grid_for(total, 256);
+  auto* yy = static_cast<const __nv_bfloat16*>(y);
+  auto* oo = static_cast<__nv_bfloat16*>(out);
+  auto* ya = static_cast<__nv_bfloat16*>(yarg);
+  auto* am = static_cast<signed char*>(argmax);
+  if (kd == 1) bn_relu_maxpool3d_fwd_kernel<1><<<grid, 256, 0, S(stream)>>>(yy, scale, shift, oo, ya, am, n, d, h, w, c);
+  else bn_relu_maxpool3d_fwd_kernel<2><<<grid, 256, 0, S(stream)>>>(yy, scale, shift, oo, ya, am, n, d, h, w, c);
+  return cuda_status("bn_relu_maxpool3d_fwd");
+}
+int qt_bn_relu_maxpool3d_bwd(const void* dpool, const void* argmax, const void* y, const void* yarg, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* gamma, int n, int d, int h,
+                             int w, int c, int kd, int kh, int kw, float* dgamma, float* dbeta, float* dbias, int eval_mode,
+                             void* dy, void* ws, size_t ws_bytes, qt_stream_t stream) {
+  if (int rc = pool3d_fused_check(n, d, h, w, c, kd, kh, kw)) return rc;
+  if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_relu_maxpool3d_bwd: workspace too small");
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
+  float* coef = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;
+  const int block = rowlane_block(c);
+  const int lanes = block / (c / 8);
+  const long long m = static_cast<long long>(n) * d * h * w;
+  const long long mp = static_cast<long long>(n) * (d / kd) * (h / 2) * (w / 2);
+  long long want = (mp + lanes - 1) / lanes;
+  const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
+  // statistics from pooled-size tensors: every non-arg-max position has dz = 0
+  bn_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpool), nullptr, static_cast<const __nv_bfloat16*>(yarg), mean, invstd, scale, shift, mp, c,
+      partial);
+  if (int rc = cuda_status("bn_pool3d_bwd_reduce")) return rc;
+  bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
+                                                                             invstd, gamma, dgamma, dbeta, 0, eval_mode, coef, dbias);
+  if (int rc = cuda_status("bn_bwd_finalize")) return rc;
+  const int grid = grid_for(mp * (c / 8), 256);
+  auto* dp = static_cast<const __nv_bfloat16*>(dpool);
+  auto* am = static_cast<const signed char*>(argmax);
+  auto* yy = static_cast<const __nv_bfloat16*>(y);
+  auto* dd = static_cast<__nv_bfloat16*>(dy);
+  if (kd == 1) bn_pool3d_bwd_apply_kernel<1><<<grid, 256, 0, S(stream)>>>(dp, am, yy, coef, scale, shift, dd, n, d, h, w, c);
+  else bn_pool3d_bwd_apply_kernel<2><<<grid, 256, 0, S(stream)>>>(dp, am, yy, coef, scale, shift, dd, n, d, h, w, c);
+  return cuda_status("bn_pool3d_bwd_apply");
 }
 int qt_attn_pool_fwd(const float* x, const float* scores, float* wts, float* out, int b, int r, int c, qt_stream_t stream) {
   attn_pool_fwd_kernel<<<b, 64, 0, S(stream)>>>(x, scores, wts, out, r, c);

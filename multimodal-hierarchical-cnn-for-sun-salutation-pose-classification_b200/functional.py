@@ -3,6 +3,8 @@
 Function boundaries are either channels-last bf16 maps or small fp32 / bf16 feature matrices."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import capi, ops
@@ -371,44 +373,66 @@ class Conv3dBnReluPool(torch.autograd.Function):
         stats = ops.conv_fprop(d, x, wf, y, bias=b.detach(), relu=False, want_stats=training)
         m = n * D * H * W
         st = ops.bn_finalize(stats, m, bn_mod, cout, dev, training)
-        a = torch.empty_like(y)
-        ops.bn_apply(y, st, a, None, True)
-        am = None
-        if pool is not None:
+        need_grad = any(ctx.needs_input_grad)
+        a = am = yarg = None
+        fused = pool is not None and _pool_fusable(pool, D, H, W)
+        if fused:
+            # BatchNorm + ReLU + MaxPool3d in one pass: the full-size activation is never written
             kd, kh, kw = pool
             out = torch.empty(n, D // kd, H // kh, W // kw, cout, device=dev, dtype=BF16)
-            am = torch.empty(out.shape, device=dev, dtype=torch.int8) if any(ctx.needs_input_grad) else None
-            check(L().qt_maxpool3d_fwd(ptr(a), ptr(out), ptr(am), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_fwd")
-            ops._count(2)
+            if need_grad:
+                yarg = torch.empty_like(out)
+                am = torch.empty(out.shape, device=dev, dtype=torch.int8)
+            check(L().qt_bn_relu_maxpool3d_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(yarg), ptr(am), n, D, H, W, cout,
+                                               kd, kh, kw, stream()), "bn_relu_maxpool3d_fwd")
+            ops._count()
         else:
-            # a distinct tensor object: returning `a` itself would make ctx.saved reference the Function's own output
-            # (output -> grad_fn -> ctx -> saved -> output), a cycle only Python's GC can break — the whole step's
-            # activations would stay allocated until it runs
-            out = a.view(a.shape)
-        if any(ctx.needs_input_grad):
-            ctx.saved = (x, y, a, am, st, w, wd, gamma, beta, b, d)
-            ctx.cfg = (pool, training, cin_pad)
+            a = torch.empty_like(y)
+            ops.bn_apply(y, st, a, None, True)
+            if pool is not None:
+                kd, kh, kw = pool
+                out = torch.empty(n, D // kd, H // kh, W // kw, cout, device=dev, dtype=BF16)
+                am = torch.empty(out.shape, device=dev, dtype=torch.int8) if need_grad else None
+                check(L().qt_maxpool3d_fwd(ptr(a), ptr(out), ptr(am), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_fwd")
+                ops._count()
+            else:
+                # a distinct tensor object: returning `a` itself would make ctx.saved reference the Function's own output
+                # (output -> grad_fn -> ctx -> saved -> output), a cycle only Python's GC can break — the whole step's
+                # activations would stay allocated until it runs
+                out = a.view(a.shape)
+        if need_grad:
+            ctx.saved = (x, y, a, am, yarg, st, w, wd, gamma, beta, b, d)
+            ctx.cfg = (pool, training, cin_pad, fused)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, a, am, st, w, wd, gamma, beta, b, d = ctx.saved
-        pool, training, cin_pad = ctx.cfg
+        x, y, a, am, yarg, st, w, wd, gamma, beta, b, d = ctx.saved
+        pool, training, cin_pad, fused = ctx.cfg
         n, D, H, W, cout = y.shape
         dev = y.device
         dout = dout.to(BF16).contiguous()
-        if pool is not None:
-            kd, kh, kw = pool
-            da = torch.empty_like(y)
-            check(L().qt_maxpool3d_bwd(ptr(dout), ptr(am), ptr(da), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_bwd")
-            ops._count()
-        else:
-            da = dout
         dgamma, dbeta = ops.grad_out(gamma), ops.grad_out(beta)
-        dy = torch.empty_like(y)
-        ops.bn_backward(da, a, y, st, gamma.detach(), dgamma, dbeta, dy, None, eval_mode=not training)
         db = ops.grad_out(b)
-        ops.colsum(dy.view(-1, cout), db)  # conv bias before train-mode BN: analytically ~0, computed faithfully
+        dy = torch.empty_like(y)
+        if fused:
+            kd, kh, kw = pool
+            ws = ops.workspace(L().qt_bn_workspace_bytes(cout), dev, "bn")
+            check(L().qt_bn_relu_maxpool3d_bwd(ptr(dout), ptr(am), ptr(y), ptr(yarg), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
+                                               ptr(gamma.detach()), n, D, H, W, cout, kd, kh, kw, ptr(dgamma), ptr(dbeta), ptr(db),
+                                               0 if training else 1, ptr(dy), ptr(ws), ws.numel(), stream()),
+                  "bn_relu_maxpool3d_bwd")
+            ops._count(3)
+        else:
+            if pool is not None:
+                kd, kh, kw = pool
+                da = torch.empty_like(y)
+                check(L().qt_maxpool3d_bwd(ptr(dout), ptr(am), ptr(da), n, D, H, W, cout, kd, kh, kw, stream()), "maxpool3d_bwd")
+                ops._count()
+            else:
+                da = dout
+            ops.bn_backward(da, a, y, st, gamma.detach(), dgamma, dbeta, dy, None, eval_mode=not training)
+            ops.colsum(dy.view(-1, cout), db)  # conv bias before train-mode BN: analytically ~0, computed faithfully
         dw = None
         if ctx.needs_input_grad[1]:
             cin = w.shape[1]
@@ -424,6 +448,13 @@ class Conv3dBnReluPool(torch.autograd.Function):
             dx = torch.empty_like(x)
             ops.conv_dgrad(d, dy, wd, dx)
         return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+def _pool_fusable(pool, D, H, W):
+    """qt_bn_relu_maxpool3d_* cover the pools the reference uses ((1,2,2) and (2,2,2), 3dcnn/models.py:111-135) on even maps."""
+    kd, kh, kw = pool
+    return os.environ.get("QTCNN_NO_POOL_FUSION", "") != "1" and kd in (1, 2) and kh == 2 and kw == 2 and D % kd == 0 \
+        and H % 2 == 0 and W % 2 == 0
 
 
 class PackClip(torch.autograd.Function):

@@ -414,6 +414,57 @@ def test_quadtree3d_full_clip_size(C):
     assert checked >= 20
 
 
+@pytest.mark.parametrize("cin,cout,D,H,W,pool,training", [
+    (8, 32, 16, 112, 112, (1, 2, 2), True),    # block 1 of the 3-D model at the BASELINE clip size
+    (32, 64, 16, 56, 56, (2, 2, 2), True),     # block 2
+    (64, 128, 4, 12, 20, (2, 2, 2), True),
+    (64, 128, 4, 12, 20, (1, 2, 2), False),    # running statistics (frozen / eval backward)
+])
+def test_conv3d_block_tail_fused_equals_unfused(C, monkeypatch, cin, cout, D, H, W, pool, training):
+    """qt_bn_relu_maxpool3d_fwd/bwd (BatchNorm3d + ReLU + MaxPool3d in one pass, statistics from the pooled tensors) against the
+    unfused kernels they replace (bn_apply + maxpool3d_fwd, maxpool3d_bwd + bn_backward + colsum; 3dcnn/models.py:108-135):
+    pooled output, data gradient and weight gradient bit-identical, dgamma / dbeta equal up to fp32 summation order."""
+    from qtcnn_b200 import functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(cout + D)
+    n = 2
+    x0 = torch.randn(n, D, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    first = cin == 8  # the model's first block: 3 real channels padded to 8, input needs no gradient
+    if first:
+        x0[..., 3:] = 0
+    conv = torch.nn.Conv3d(3 if first else cin, cout, 3, padding=1).cuda()
+    bn = torch.nn.BatchNorm3d(cout).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(cout, device="cuda", generator=g))     # both signs: arg-max on the activation, not on y
+        bn.bias.copy_(0.3 * torch.randn(cout, device="cuda", generator=g))
+        bn.running_mean.copy_(0.1 * torch.randn(cout, device="cuda", generator=g))
+        bn.running_var.copy_(0.5 + torch.rand(cout, device="cuda", generator=g))
+    dout = None
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QTCNN_NO_POOL_FUSION", mode)
+        for prm in list(conv.parameters()) + list(bn.parameters()):
+            prm.grad = None
+        x = x0.clone().requires_grad_(not first)
+        out = Fn.Conv3dBnReluPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn, pool, training)
+        if dout is None:
+            dout = torch.randn(out.shape, device="cuda", generator=g).to(torch.bfloat16)
+        out.backward(dout)
+        res[mode] = (out.detach().clone(), conv.weight.grad.clone() if first else x.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone(), bn.weight.grad.clone(),
+                     bn.bias.grad.clone())
+    u, f = res["1"], res["0"]
+    assert torch.equal(u[0], f[0]), "pooled activation differs"
+    for name, a, b in (("dgamma", u[4], f[4]), ("dbeta", u[5], f[5])):
+        assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max()) + 1e-6, name
+    # dy feeds dx and dw: identical coefficients (up to the summation order of the statistics) -> near-identical bf16 gradients
+    for name, a, b in (("dx", u[1].float(), f[1].float()), ("dw", u[2], f[2])):
+        assert float((a - b).norm() / a.norm()) <= 2e-4, name
+    if training:
+        assert float(f[3].abs().max()) == 0.0  # conv bias in front of batch statistics: exactly zero (the unfused colsum
+        # returns the bf16 rounding noise of dy; the true gradient is 0)
+    else:
+        assert float((u[3] - f[3]).norm() / u[3].norm()) <= 2e-3
+
+
 @pytest.mark.parametrize("which", ["quadtree_forward_api", "quadtree3d"])
 def test_no_reference_cycles_keep_activations_alive(C, which):
     """A Function that stores its own output in ctx creates output -> grad_fn -> ctx -> output, which only Python's cyclic GC
