@@ -15,6 +15,7 @@
 #include "head.cuh"
 #include "optim.cuh"
 #include "lstm.cuh"
+#include "sgemm.cuh"
 
 using namespace qt;
 
@@ -1419,6 +1420,14 @@ int qt_attn_pool_bwd(const float* x, const float* wts, const float* dout, float*
 int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float* w, const float* bias, int b, int n,
                         int k, int relu, float drop_p, unsigned long long seed, float* out, long long ldo,
                         void* out16, long long ldo16, qt_stream_t stream) {
+  if (sgemm_worthwhile(b, n, k)) {
+    SgemmParams p{};
+    p.a = x; p.lda = ldx; p.b = w; p.ldb = k; p.M = b; p.N = n; p.K = k;
+    p.bias = bias; p.relu = relu; p.drop_p = drop_p; p.seed = seed;
+    p.out = out; p.ldo = ldo; p.out16 = static_cast<__nv_bfloat16*>(out16); p.ldo16 = ldo16;
+    sgemm_launch<1, 1, 0>(p, x_is_bf16 != 0, false, S(stream));
+    return cuda_status("small_linear_fwd(tiled)");
+  }
   const long long warps = static_cast<long long>(b) * n;
   const int grid = static_cast<int>((warps * 32 + 255) / 256);
   if (x_is_bf16)
@@ -1434,6 +1443,14 @@ int qt_small_linear_fwd(const void* x, int x_is_bf16, long long ldx, const float
 int qt_small_linear_bwd_dx(const void* dy, int dy_is_bf16, long long ldy, const float* w, int b, int n, int k,
                            const float* act, long long lda, float drop_p, unsigned long long seed, float* dx,
                            long long ldx, void* dx16, long long ldx16, qt_stream_t stream) {
+  if (sgemm_worthwhile(b, k, n)) {
+    SgemmParams p{};
+    p.a = dy; p.lda = ldy; p.b = w; p.ldb = k; p.M = b; p.N = k; p.K = n;
+    p.drop_p = drop_p; p.seed = seed; p.act = act; p.ldact = lda;
+    p.out = dx; p.ldo = ldx; p.out16 = static_cast<__nv_bfloat16*>(dx16); p.ldo16 = ldx16;
+    sgemm_launch<1, 0, 1>(p, dy_is_bf16 != 0, false, S(stream));
+    return cuda_status("small_linear_bwd_dx(tiled)");
+  }
   const long long total = static_cast<long long>(b) * k;
   const int grid = static_cast<int>((total + 255) / 256);
   if (dy_is_bf16)
@@ -1449,6 +1466,13 @@ int qt_small_linear_bwd_dx(const void* dy, int dy_is_bf16, long long ldy, const 
 int qt_small_linear_bwd_dw(const void* dy, int dy_is_bf16, long long ldy, const void* x, int x_is_bf16,
                            long long ldx, int b, int n, int k, float* dw, float* db, int accumulate,
                            qt_stream_t stream) {
+  if (sgemm_worthwhile(n, k, b)) {
+    SgemmParams p{};
+    p.a = dy; p.lda = ldy; p.b = x; p.ldb = ldx; p.M = n; p.N = k; p.K = b;
+    p.out = dw; p.ldo = k; p.db = db; p.accumulate = accumulate;
+    sgemm_launch<0, 0, 2>(p, dy_is_bf16 != 0, x_is_bf16 != 0, S(stream));
+    return cuda_status("small_linear_bwd_dw(tiled)");
+  }
   const dim3 grid((k + 31) / 32, n);
   const dim3 blk(32, 8);
   cudaStream_t st = S(stream);
@@ -1569,8 +1593,8 @@ int qt_lstm_layer_fwd(const float* xproj, const float* whh_t, const float* bhh, 
                       float* cseq, float* gates, qt_stream_t stream) {
   if (b < 1 || t < 1) return 0;
   if (h < 1 || h > 256) return fail("lstm: hidden size must be <= 256 (got %d)", h);
-  const int hs = (h + kLstmCluster - 1) / kLstmCluster;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(h) * 4 * hs + 2 * kLstmBT * h + kLstmBT * 4 * hs);
+  const int hs = 2 * ((h + 2 * kLstmCluster - 1) / (2 * kLstmCluster));  // units per CTA, even (row / unit pairs per thread)
+  const size_t smem = sizeof(float) * lstm_fwd_smem_floats(h, hs);
   static size_t configured = 0;
   if (configured < smem) {
     cudaFuncSetAttribute(lstm_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1585,8 +1609,8 @@ int qt_lstm_layer_bwd(const float* dhseq, float out_drop_p, unsigned long long s
                       const float* cseq, int b, int t, int h, float* dgates, qt_stream_t stream) {
   if (b < 1 || t < 1) return 0;
   if (h < 1 || h > 256) return fail("lstm: hidden size must be <= 256 (got %d)", h);
-  const int hs = (h + kLstmCluster - 1) / kLstmCluster;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(4 * h) * hs + 2 * kLstmBT * 4 * h + kLstmBT * hs + 512);
+  const int hs = 2 * ((h + 2 * kLstmCluster - 1) / (2 * kLstmCluster));
+  const size_t smem = sizeof(float) * lstm_bwd_smem_floats(h, hs);
   static size_t configured = 0;
   if (configured < smem) {
     cudaFuncSetAttribute(lstm_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -48,6 +48,7 @@ def workspace(nbytes: int, device, tag="gemm") -> torch.Tensor:
 # Fused / foreach optimizers update parameters without bumping Tensor._version, so packed bf16 weight copies
 # are also invalidated by a global optimizer-step counter (hooked once, covers every torch.optim optimizer).
 _generation = 0
+_hard_epoch = 0  # explicit invalidations: these also drop the packs of frozen parameters
 
 
 def _on_optimizer_step(*_args, **_kw):
@@ -55,8 +56,17 @@ def _on_optimizer_step(*_args, **_kw):
     _generation += 1
 
 
+def _gen_of(w) -> int:
+    """Cache generation a parameter's packs belong to. A frozen parameter (requires_grad False) is never touched by an
+    optimizer step — ours writes through raw pointers only where a gradient exists — so its packs survive steps (19 repack
+    launches per step on the frozen backbones otherwise); in-place torch edits still bump `_version`."""
+    return _generation if w.requires_grad else -1 - _hard_epoch
+
+
 def invalidate_packed_weights():
     """Call after modifying parameters through a path that neither bumps `_version` nor is a torch optimizer."""
+    global _hard_epoch
+    _hard_epoch += 1
     _on_optimizer_step()
 
 
@@ -169,7 +179,7 @@ class _PackRegistry:
         self.generation = _generation
         for ref, e in self.items:
             w = ref()
-            e.version, e.ptr = (w._version, _generation), w.data_ptr()
+            e.version, e.ptr = (w._version, _gen_of(w)), w.data_ptr()
 
 
 _registries = {}
@@ -188,9 +198,10 @@ def _entry(w: torch.Tensor) -> _Packed:
     if e is None:
         e = _Packed()
         _packed.set(w, e)
-    if e.registered and e.version is not None and e.version[1] != _generation and e.ptr == w.data_ptr():
+    gen = _gen_of(w)
+    if e.registered and e.version is not None and e.version[1] != gen and e.ptr == w.data_ptr():
         _registry(w.device).repack_all()  # optimizer stepped: every registered weight in one launch
-    ver = (w._version, _generation)
+    ver = (w._version, gen)
     if e.version != ver or e.ptr != w.data_ptr():
         e.version, e.ptr = ver, w.data_ptr()
         e.wf = e.wd = e.w8 = None

@@ -368,10 +368,15 @@ def test_quadtree_pool(C):
     report("quadtree dl4", dl.permute(0, 3, 1, 2), lf.grad, BF16_REL_L2, True)
 
 
-def test_small_linears(C):
-    b, k, n = 33, 47, 94
+@pytest.mark.parametrize("b,k,n", [
+    (33, 47, 94),       # head MLP: warp-per-output kernels
+    (256, 640, 1024),   # CnnLstm input projection over all time steps (cnn+lstm/models.py:43-49): tiled kernel (sgemm.cuh)
+    (512, 47, 752),     # Quadtree3DCNN LSTM layer-1 projection at B=32, T=16 (3dcnn/models.py:144-150), ragged K
+    (500, 188, 750),    # ragged in every dimension
+])
+def test_small_linears(C, b, k, n):
     g = torch.Generator(device="cuda").manual_seed(9)
-    x = torch.rand(b, k, device="cuda", generator=g) * 180
+    x = torch.rand(b, k, device="cuda", generator=g) * (180 if k == 47 else 1)
     w = (torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k)).requires_grad_(True)
     bias = torch.randn(n, device="cuda", generator=g).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
@@ -398,6 +403,43 @@ def test_small_linears(C):
     run(C, C.lib().qt_small_linear_bwd_dx(C.ptr(dz), 0, n, C.ptr(w), b, n, k, None, 0, 0.0, 0, C.ptr(dx), k, None, 0,
                                           C.stream()), "small_linear_bwd_dx")
     report("small_linear dx", dx, xr.grad, 1e-5)
+
+
+def test_tiled_linear_dropout_and_bf16_operands(C):
+    """Tiled path (sgemm.cuh): counter-hash dropout is keyed on the element index exactly like the warp-per-output kernels (the
+    backward gate reads the stored output), bf16-stored operands, accumulate into dw / db."""
+    b, k, n = 128, 256, 192
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x16 = torch.randn(b, k, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k)
+    out = torch.empty(b, n, device="cuda")
+    out16 = torch.empty(b, n, device="cuda", dtype=torch.bfloat16)
+    lib = C.lib()
+    run(C, lib.qt_small_linear_fwd(C.ptr(x16), 1, k, C.ptr(w), None, b, n, k, 1, 0.5, 77, C.ptr(out), n, C.ptr(out16), n, C.stream()),
+        "fwd")
+    zp = x16.float() @ w.t()
+    z = zp.relu()
+    clear = zp.abs() > 1e-4   # away from the ReLU edge, where summation order could flip the sign
+    kept = out > 0
+    assert 0.2 < float(kept.float().mean()) < 0.3   # half by ReLU, half of those by dropout
+    report("tiled fwd kept*2", out[kept & clear], 2 * z[kept & clear], 1e-5)
+    assert torch.equal(out16, out.to(torch.bfloat16))
+    # same mask as the element-wise kernel keyed on the same index
+    h = z.clone()
+    run(C, lib.qt_relu_dropout(C.ptr(h), None, b * n, 0.5, 77, 1, C.stream()), "relu_dropout")
+    assert torch.equal((h > 0)[clear], kept[clear])
+    # gate of the backward = stored output; eye weight isolates the gate
+    dy16 = torch.randn(b, n, device="cuda", generator=g).to(torch.bfloat16)
+    eye = torch.eye(n, device="cuda")
+    dz = torch.empty(b, n, device="cuda")
+    run(C, lib.qt_small_linear_bwd_dx(C.ptr(dy16), 1, n, C.ptr(eye), b, n, n, C.ptr(out), n, 0.5, 77, C.ptr(dz), n, None, 0, C.stream()),
+        "gate")
+    assert torch.equal(dz, torch.where(kept, 2 * dy16.float(), torch.zeros_like(dz)))
+    dw = torch.ones(n, k, device="cuda")
+    db = torch.ones(n, device="cuda")
+    run(C, lib.qt_small_linear_bwd_dw(C.ptr(dy16), 1, n, C.ptr(x16), 1, k, b, n, k, C.ptr(dw), C.ptr(db), 1, C.stream()), "dw acc")
+    report("tiled dw (accumulate)", dw, 1 + dy16.float().t() @ x16.float(), 1e-5)
+    report("tiled db (accumulate)", db, 1 + dy16.float().sum(0), 1e-5)
 
 
 def test_dropout_statistics(C):
