@@ -70,35 +70,55 @@ __global__ void __launch_bounds__(kC8Threads, 1) conv3d_c8_kernel(const __grid_c
   if (warp >= 4 && warp < 8) {
     // ================================================================= producers: slab row j <-> virtual pixel q0 - (W+3) + j
     const int t = threadIdx.x - 128;
-    const int adv_w = 128 % Wp, adv_h = 128 / Wp;
-    const long long pix_bytes = 16, row_bytes = static_cast<long long>(p.W) * 16, plane_bytes = row_bytes * p.H;
+    const long long row_bytes = static_cast<long long>(p.W) * 16, plane_bytes = row_bytes * p.H;
     uint32_t cnt = 0;
+    // Coordinates are carried, never divided, inside the tile loop, and the rows of a tile are decomposed once for its three
+    // depth slabs (same producer structure as conv3d_c8_wgrad_kernel below; a division set per slab made these four warps the
+    // bottleneck: 416 us per launch with a 154 us MMA floor — profiles/r02_conv3d.md).
+    const int tile_adv = gridDim.x * BM;
+    const int taw = tile_adv % Wp, tah = (tile_adv / Wp) % Hp, tan = tile_adv / (Wp * Hp);
+    const int raw = 128 % Wp, rah = (128 / Wp) % Hp, ran = 128 / (Wp * Hp);  // +128 rows inside a slab
+    int swp, shp, sn;  // virtual coordinates of this thread's first slab row: q0 - (W+3) + t
+    {
+      const int vv = blockIdx.x * BM - (p.W + 3) + t + Wp * Hp;  // shifted by one plane: non-negative
+      swp = vv % Wp; shp = (vv / Wp) % Hp; sn = vv / (Wp * Hp) - 1;
+    }
+    constexpr int kMaxRows = 6;  // ceil(R / 128) for W <= 248 (c8_ok)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int q0 = tile * BM;
+      long long roff[kMaxRows];
+      int rdz[kMaxRows];
+      bool rok[kMaxRows];
+      {
+        int wp = swp, hp = shp, n = sn;
+        int dz = n % p.D;  // n >= -1
+        if (dz < 0) dz += p.D;
+#pragma unroll
+        for (int i = 0; i < kMaxRows; ++i) {
+          rok[i] = (static_cast<unsigned>(n) < static_cast<unsigned>(p.NP)) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(p.W)) && (hp >= 1);
+          roff[i] = (static_cast<long long>(n) * p.H + (hp - 1)) * row_bytes + static_cast<long long>(wp - 1) * 16;
+          rdz[i] = dz;
+          wp += raw; hp += rah; n += ran;
+          dz += ran % p.D;
+          if (wp >= Wp) { wp -= Wp; ++hp; }
+          if (hp >= Hp) { hp -= Hp; ++n; ++dz; }
+          if (dz >= p.D) dz -= p.D;
+        }
+        swp += taw; shp += tah; sn += tan;
+        if (swp >= Wp) { swp -= Wp; ++shp; }
+        if (shp >= Hp) { shp -= Hp; ++sn; }
+      }
       for (int kd = 0; kd < 3; ++kd, ++cnt) {
         const int s = cnt % kC8Slabs;
         if (cnt >= kC8Slabs) mbar_wait(&a_empty[s], ((cnt / kC8Slabs) - 1) & 1);
         const int dd = kd - 1;
-        int n, hp, wp, dz;
-        {
-          const int vv = q0 - (p.W + 3) + t + Wp * Hp;
-          wp = vv % Wp;
-          const int rest = vv / Wp;
-          hp = rest % Hp;
-          n = rest / Hp - 1;
-          dz = (n + p.D) % p.D;
-        }
-        uint32_t dst = smem_u32(slabs + s * slab_bytes) + t * 16;
-        for (int j = t; j < p.R; j += 128) {
-          const bool ok = (static_cast<unsigned>(n) < static_cast<unsigned>(p.NP)) && (static_cast<unsigned>(wp - 1) < static_cast<unsigned>(p.W)) &&
-                          (hp >= 1) && (static_cast<unsigned>(dz + dd) < static_cast<unsigned>(p.D));
-          const char* src = reinterpret_cast<const char*>(p.x) + dd * plane_bytes +
-                            (static_cast<long long>(n) * p.H + (hp - 1)) * row_bytes + static_cast<long long>(wp - 1) * pix_bytes;
-          cp_async16(dst, ok ? static_cast<const void*>(src) : static_cast<const void*>(p.x), ok ? 16u : 0u);
-          dst += 128 * 16;
-          wp += adv_w; hp += adv_h;
-          while (wp >= Wp) { wp -= Wp; ++hp; }
-          while (hp >= Hp) { hp -= Hp; ++n; dz = (dz + 1 == p.D) ? 0 : dz + 1; }
+        const uint32_t dst0 = smem_u32(slabs + s * slab_bytes) + t * 16;
+        const char* base = reinterpret_cast<const char*>(p.x) + dd * plane_bytes;
+#pragma unroll
+        for (int i = 0; i < kMaxRows; ++i) {
+          if (t + 128 * i < p.R) {
+            const bool ok = rok[i] && (static_cast<unsigned>(rdz[i] + dd) < static_cast<unsigned>(p.D));
+            cp_async16(dst0 + i * 2048, ok ? static_cast<const void*>(base + roff[i]) : static_cast<const void*>(p.x), ok ? 16u : 0u);
+          }
         }
         cp_async_mbar_arrive_noinc(&a_full[s]);
       }
@@ -148,28 +168,36 @@ __global__ void __launch_bounds__(kC8Threads, 1) conv3d_c8_kernel(const __grid_c
   } else {
     // ================================================================= epilogue (warps 0-3): one accumulator row per lane
     float run1 = 0.f, run2 = 0.f;  // per-lane (= column) BatchNorm partial sums of this warp
+    float s1v[32] = {}, s2v[32] = {};
     const bool want_stats = p.stats != nullptr;
     float bias_r[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias_r[j] = p.bias ? __ldg(p.bias + j) : 0.f;
     uint32_t it = 0;
+    // output coordinates of this lane's row, carried across tiles like the producers' (no division in the loop)
+    const int tile_adv = gridDim.x * BM;
+    const int taw = tile_adv % Wp, tah = (tile_adv / Wp) % Hp, tan = tile_adv / (Wp * Hp);
+    const int raw = kBM % Wp, rah = (kBM / Wp) % Hp, ran = kBM / (Wp * Hp);
+    int ewp, ehp, en;
+    {
+      const int v0 = blockIdx.x * BM + warp * 32 + lane;
+      ewp = v0 % Wp; ehp = (v0 / Wp) % Hp; en = v0 / (Wp * Hp);
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t ab = it & 1;
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
+      int wp = ewp, hp = ehp, n = en;
+      ewp += taw; ehp += tah; en += tan;
+      if (ewp >= Wp) { ewp -= Wp; ++ehp; }
+      if (ehp >= Hp) { ehp -= Hp; ++en; }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int v = tile * BM + u * kBM + warp * 32 + lane;
-        bool ok = v < p.V;
-        long long orow = 0;
-        if (ok) {
-          const int wp = v % Wp;
-          const int rest = v / Wp;
-          const int hp = rest % Hp;
-          const int n = rest / Hp;
-          ok = (wp >= 1) && (wp <= p.W) && (hp >= 1);
-          orow = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * kC8N;
-        }
+        const bool ok = (n < p.NP) && (wp >= 1) && (wp <= p.W) && (hp >= 1);
+        const long long orow = ((static_cast<long long>(n) * p.H + (hp - 1)) * p.W + (wp - 1)) * kC8N;
+        wp += raw; hp += rah; n += ran;
+        if (wp >= Wp) { wp -= Wp; ++hp; }
+        if (hp >= Hp) { hp -= Hp; ++n; }
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + ab * (2 * kC8N) + u * kC8N, r);
         tmem_ld_wait();
@@ -182,22 +210,23 @@ __global__ void __launch_bounds__(kC8Threads, 1) conv3d_c8_kernel(const __grid_c
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
         if (want_stats) {
-          float s1v[32], s2v[32];
+          // per-lane (= per-row) running sums of every column; the cross-lane transpose-reduce happens once after the tile loop
+          // (two 32-value shuffle reductions per 128 pixels made these four warps the slowest role of the kernel)
           const uint32_t keep = ok ? 0xffffffffu : 0u;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float lo = __uint_as_float((pk[j] << 16) & keep), hi2 = __uint_as_float(pk[j] & 0xffff0000u & keep);
-            s1v[2 * j] = lo; s1v[2 * j + 1] = hi2;
-            s2v[2 * j] = lo * lo; s2v[2 * j + 1] = hi2 * hi2;
+            s1v[2 * j] += lo; s1v[2 * j + 1] += hi2;
+            s2v[2 * j] = fmaf(lo, lo, s2v[2 * j]); s2v[2 * j + 1] = fmaf(hi2, hi2, s2v[2 * j + 1]);
           }
-          run1 += warp_transpose_reduce(s1v);
-          run2 += warp_transpose_reduce(s2v);
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
     }
     if (want_stats) {
+      run1 = warp_transpose_reduce(s1v);
+      run2 = warp_transpose_reduce(s2v);
       scratch[(warp * 2 + 0) * 32 + lane] = run1;
       scratch[(warp * 2 + 1) * 32 + lane] = run2;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");

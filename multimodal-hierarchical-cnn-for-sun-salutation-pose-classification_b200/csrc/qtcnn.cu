@@ -338,7 +338,7 @@ bool c8_ok(const qt_conv_desc* d, int flags) {
   if (flags & (EPI_RELU | EPI_OUT_F32 | EPI_ADDEND)) return false;
   if (!dense_nhwc(d->x_stride, d->in_d, d->in_h, d->in_w, d->in_c) || !dense_nhwc(d->y_stride, d->in_d, d->in_h, d->in_w, d->out_c)) return false;
   const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
-  return V <= (1ll << 30) && d->in_w <= 250;  // (the weight-gradient producer keeps at most 5 slab rows per thread)
+  return V <= (1ll << 30) && d->in_w <= 248;  // (the producers keep at most 6 / 5 slab rows per thread in registers)
 }
 int c8_tiles(const qt_conv_desc* d) {
   const long long V = static_cast<long long>(d->n) * d->in_d * (d->in_h + 1) * (d->in_w + 2);
