@@ -516,7 +516,12 @@ class QuadtreeCNN(nn.Module):
     def _run(self, image_input, numerical_input, labels):
         base = l4 = None
         if self.mode in ("fusion", "image_only"):
-            base = self.features_extractor(image_input)
+            # frozen-backbone variant (resnet/models.py:86-88): conv1..layer3 replay from a CUDA graph; trainable backbones,
+            # hooked modules and profiling runs take the eager path inside the runner
+            runner = self.__dict__.get("_features_graph")
+            if runner is None:
+                runner = self.__dict__["_features_graph"] = GraphedFrozenForward(self.features_extractor)
+            base = runner(image_input)
             l4 = self.base_cnn.layer4(base)  # the module call keeps hooks on base_cnn.layer4 alive
         qp, mlp, cls = self.quadrant_processor[0], self.numerical_mlp, self.classifier
         return _QuadHeadFn.apply(base, l4, numerical_input, qp.weight, qp.bias, mlp[0].weight, mlp[0].bias, mlp[3].weight,
@@ -904,6 +909,93 @@ class HybridQuadtree3DCNN(nn.Module):
 # CnnLstm (cnn+lstm/models.py:14-89): every frame through the frozen ResNet-18 on the tensor cores; the temporal
 # LSTM runs on the persistent LSTM kernels (functional.LSTM)
 # =================================================================================================
+class GraphedFrozenForward:
+    """Forward of a frozen, gradient-free sub-network replayed from a CUDA graph.
+
+    The frozen ResNet-18 of CnnLstm (cnn+lstm/models.py:21-27) is ~80 kernel launches with static shapes, static (frozen)
+    weights and no autograd state; issued one by one from Python they take longer on the host than on the GPU once several
+    ranks share a box (the 8-GPU line of round 2 ran at 0.67 of linear for that reason). The launches are recorded once
+    per (input shape, dtype, train/eval mode, parameter versions) with `torch.cuda.graph` — libqtcnn launches on torch's
+    current stream, so they are captured like any other kernel — and replayed with one driver call per step. The input
+    is copied into the graph's static buffer; train-mode BatchNorm running statistics are updated by the replayed kernels
+    exactly once per step (the warm-up runs needed for capture are rolled back). Falls back to eager execution when
+    any parameter of the sub-network is trainable, the input requires a gradient, a module of the sub-network carries
+    hooks (Grad-CAM), profiling scopes are active, or `QTCNN_NO_GRAPH=1`."""
+
+    _MAX_GRAPHS = 4  # e.g. train / eval x two batch sizes; each graph owns the activations of one forward
+
+    def __init__(self, module):
+        self.module = module
+        self.cache = {}  # key -> [graph, static_in, static_out, launches]
+
+    def __deepcopy__(self, memo):  # graphs are neither copyable nor picklable: the copy re-captures on first use
+        return None
+
+    def __reduce__(self):
+        return (_no_runner, ())
+
+    def usable(self, x) -> bool:
+        if os.environ.get("QTCNN_NO_GRAPH", "") == "1" or ops.profiling() or not x.is_cuda:
+            return False
+        # only fully frozen sub-networks: a trainable weight's bf16 packs are refreshed lazily by eager forwards after an
+        # optimizer step, which a replay would bypass (frozen weights change only through `_version`-bumping torch ops or
+        # ops.invalidate_packed_weights(), both part of the capture key)
+        if any(p.requires_grad for p in self.module.parameters()) or (torch.is_grad_enabled() and x.requires_grad):
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            return False
+        for m in self.module.modules():
+            if m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or getattr(m, "_backward_pre_hooks", None):
+                return False
+        return True
+
+    def _make_key(self, x):
+        return (tuple(x.shape), x.dtype, x.device.index, self.module.training, ops._hard_epoch,
+                tuple((p.data_ptr(), p._version) for p in self.module.parameters()),
+                tuple(b.data_ptr() for b in self.module.buffers()))
+
+    def _capture(self, x):
+        bufs = [b for b in self.module.buffers()]
+        saved = [b.detach().clone() for b in bufs]
+        static_in = torch.empty_like(x)
+        static_in.copy_(x)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):  # weight packs, workspaces, kernel attributes: everything lazy happens outside the capture
+                self.module(static_in)
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(graph), torch.no_grad():
+            static_out = self.module(static_in)
+        launches = ops.launches() - n0
+        ops._count(-launches)  # recorded, not executed
+        with torch.no_grad():
+            for b, v in zip(bufs, saved):  # roll the warm-up's running-statistics updates back
+                b.copy_(v)
+        return [graph, static_in, static_out, launches]
+
+    def __call__(self, x):
+        if not self.usable(x):
+            return self.module(x)
+        key = self._make_key(x)
+        ent = self.cache.get(key)
+        if ent is None:
+            while len(self.cache) >= self._MAX_GRAPHS:
+                self.cache.pop(next(iter(self.cache)))
+            ent = self.cache[key] = self._capture(x)
+        graph, static_in, static_out, launches = ent
+        static_in.copy_(x)
+        graph.replay()
+        ops._count(launches)
+        return static_out.clone()  # the graph's output buffer is overwritten by the next replay
+
+
+def _no_runner():
+    return None
+
+
 class CnnLstm(nn.Module):
     def __init__(self, num_classes, sequence_length=4, numerical_feature_dim=47, dropout_rate=0.5, lstm_hidden_size=256):
         super().__init__()
@@ -923,7 +1015,10 @@ class CnnLstm(nn.Module):
         _require_cuda(image_sequence, "CnnLstm")
         batch_size, seq_len, c, h, w = image_sequence.shape
         c_in = image_sequence.reshape(batch_size * seq_len, c, h, w)
-        c_out = self.cnn_backbone(c_in).flatten(1).float().view(batch_size, seq_len, -1)   # (B, T, 512)
+        runner = self.__dict__.get("_backbone_graph")
+        if runner is None:
+            runner = self.__dict__["_backbone_graph"] = GraphedFrozenForward(self.cnn_backbone)  # not a submodule / state_dict entry
+        c_out = runner(c_in).flatten(1).float().view(batch_size, seq_len, -1)   # (B, T, 512)
         mlp = self.numerical_mlp
         num = numerical_sequence.to(c_out.device).float()
         n_out = Fn.SmallLinear.apply(num, mlp[0].weight, mlp[0].bias, True, 0.0, self.training)

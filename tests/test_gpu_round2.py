@@ -465,6 +465,47 @@ def test_conv3d_block_tail_fused_equals_unfused(C, monkeypatch, cin, cout, D, H,
         assert float((u[3] - f[3]).norm() / u[3].norm()) <= 2e-3
 
 
+def test_cnn_lstm_frozen_backbone_graph_replay_equals_eager(C, monkeypatch):
+    """CnnLstm's frozen ResNet-18 runs from a CUDA graph (models.GraphedFrozenForward): logits, gradients of the trainable
+    parameters and the train-mode BatchNorm running statistics after several steps must equal the eager launches bit for bit
+    (same kernels, same order), the replayed launches must be counted, and a Grad-CAM style hook must switch the graph off."""
+    import copy
+    from qtcnn_b200 import models as M, ops
+    torch.manual_seed(0)
+    monkeypatch.setenv("QTCNN_QUIET_PRETRAINED", "1")
+    ref = M.CnnLstm(num_classes=8, sequence_length=4, dropout_rate=0.0).cuda().train()
+    ref.lstm.dropout = 0.0
+    gm = copy.deepcopy(ref)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    outs = {}
+    for name, model, nograph in (("eager", ref, "1"), ("graph", gm, "0")):
+        monkeypatch.setenv("QTCNN_NO_GRAPH", nograph)
+        res = []
+        for step in range(3):
+            gg = torch.Generator(device="cuda").manual_seed(100 + step)
+            clips = torch.rand(2, 4, 3, 224, 224, device="cuda", generator=gg)
+            num = torch.rand(2, 4, 47, device="cuda", generator=gg)
+            n0 = ops.launches()
+            logits = model(clips, num)
+            logits.square().sum().backward()
+            res.append((logits.detach().clone(), ops.launches() - n0))
+        outs[name] = res
+    for step, ((le, ne), (lg, ng)) in enumerate(zip(outs["eager"], outs["graph"])):
+        assert torch.equal(le, lg)
+        if step > 0:  # (the first step also ran the two warm-up forwards the capture needs)
+            assert ng == ne, (ng, ne)   # replayed launches are reported like eager ones
+    assert len(gm.__dict__["_backbone_graph"].cache) == 1
+    for (k, be), (_, bg) in zip(ref.cnn_backbone.named_buffers(), gm.cnn_backbone.named_buffers()):
+        assert torch.equal(be, bg), k
+    for (k, pe), (_, pg) in zip(ref.named_parameters(), gm.named_parameters()):
+        if pe.grad is not None:
+            assert torch.equal(pe.grad, pg.grad), k
+    # a hook on the sub-network (Grad-CAM registers them on layer4) disables the replay
+    h = gm.cnn_backbone[7].register_forward_hook(lambda m, i, o: None)
+    assert not gm.__dict__["_backbone_graph"].usable(torch.empty(1, device="cuda"))
+    h.remove()
+
+
 @pytest.mark.parametrize("which", ["quadtree_forward_api", "quadtree3d"])
 def test_no_reference_cycles_keep_activations_alive(C, which):
     """A Function that stores its own output in ctx creates output -> grad_fn -> ctx -> output, which only Python's cyclic GC
