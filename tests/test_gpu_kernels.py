@@ -381,28 +381,40 @@ def test_small_linears(C, b, k, n):
     bias = torch.randn(n, device="cuda", generator=g).requires_grad_(True)
     xr = x.clone().requires_grad_(True)
     ref = F.linear(xr, w, bias).relu()
-    out = torch.empty(b, n, device="cuda")
-    out16 = torch.empty(b, n, device="cuda", dtype=torch.bfloat16)
+    guards = []
+
+    def guarded(*shape, dtype=torch.float32):
+        """Output tensor inside a sentinel-filled buffer: an out-of-bounds store of a ragged tile shows up in the guard bands
+        (compute-sanitizer is not available on the GPU pool)."""
+        numel, pad = math.prod(shape), 4096
+        buf = torch.full((numel + 2 * pad,), -7.0, device="cuda", dtype=dtype)
+        guards.append((buf, pad, numel))
+        return buf[pad:pad + numel].view(*shape)
+
+    out = guarded(b, n)
+    out16 = guarded(b, n, dtype=torch.bfloat16)
     run(C, C.lib().qt_small_linear_fwd(C.ptr(x), 0, k, C.ptr(w), C.ptr(bias), b, n, k, 1, 0.0, 0, C.ptr(out), n,
                                        C.ptr(out16), n, C.stream()), "small_linear_fwd")
     report("small_linear fwd", out, ref, 1e-5)
     dy = torch.randn(b, n, device="cuda", generator=g)
     ref.backward(dy)
     # dz through the ReLU using the stored output, then dW/db/dx
-    dz = torch.empty(b, n, device="cuda")
+    dz = guarded(b, n)
     eye = torch.eye(n, device="cuda")
     run(C, C.lib().qt_small_linear_bwd_dx(C.ptr(dy), 0, n, C.ptr(eye), b, n, n, C.ptr(out), n, 0.0, 0, C.ptr(dz), n, None,
                                           0, C.stream()), "relu mask via bwd_dx")
-    dw = torch.empty(n, k, device="cuda")
-    db = torch.empty(n, device="cuda")
+    dw = guarded(n, k)
+    db = guarded(n)
     run(C, C.lib().qt_small_linear_bwd_dw(C.ptr(dz), 0, n, C.ptr(x), 0, k, b, n, k, C.ptr(dw), C.ptr(db), 0, C.stream()),
         "small_linear_bwd_dw")
     report("small_linear dw", dw, w.grad, 1e-5)
     report("small_linear db", db, bias.grad, 1e-5)
-    dx = torch.empty(b, k, device="cuda")
+    dx = guarded(b, k)
     run(C, C.lib().qt_small_linear_bwd_dx(C.ptr(dz), 0, n, C.ptr(w), b, n, k, None, 0, 0.0, 0, C.ptr(dx), k, None, 0,
                                           C.stream()), "small_linear_bwd_dx")
     report("small_linear dx", dx, xr.grad, 1e-5)
+    for buf, pad, numel in guards:
+        assert bool((buf[:pad] == -7.0).all()) and bool((buf[pad + numel:] == -7.0).all()), "store outside the output tensor"
 
 
 def test_tiled_linear_dropout_and_bf16_operands(C):

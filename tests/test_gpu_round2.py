@@ -465,6 +465,63 @@ def test_conv3d_block_tail_fused_equals_unfused(C, monkeypatch, cin, cout, D, H,
         assert float((u[3] - f[3]).norm() / u[3].norm()) <= 2e-3
 
 
+@pytest.mark.parametrize("kd,n,D,H,W,c", [(1, 1, 3, 4, 6, 8), (2, 3, 2, 6, 4, 24), (2, 1, 4, 2, 2, 8)])
+def test_bn_relu_maxpool3d_c_abi_small_shapes_with_guard_bands(C, kd, n, D, H, W, c):
+    """qt_bn_relu_maxpool3d_fwd/bwd straight through the C ABI on tiny ragged shapes: forward against torch (bf16-rounded
+    activation, MaxPool3d), yarg = y at the arg-max, and every output buffer sits between sentinel guard bands — an
+    out-of-bounds store would show there (compute-sanitizer is not available on the GPU pool)."""
+    lib = C.lib()
+    g = torch.Generator(device="cuda").manual_seed(kd * 100 + c)
+    y = torch.randn(n, D, H, W, c, device="cuda", generator=g).to(torch.bfloat16)
+    scale = torch.randn(c, device="cuda", generator=g)
+    shift = 0.2 * torch.randn(c, device="cuda", generator=g)
+    guards = []
+
+    def guarded(shape, dtype, fill):
+        numel, pad = math.prod(shape), 2048
+        buf = torch.full((numel + 2 * pad,), fill, device="cuda", dtype=dtype)
+        guards.append((buf, pad, numel, fill))
+        return buf[pad:pad + numel].view(*shape)
+
+    oshape = (n, D // kd, H // 2, W // 2, c)
+    out = guarded(oshape, torch.bfloat16, -7.0)
+    yarg = guarded(oshape, torch.bfloat16, -7.0)
+    am = guarded(oshape, torch.int8, 99)
+    C.check(lib.qt_bn_relu_maxpool3d_fwd(C.ptr(y), C.ptr(scale), C.ptr(shift), C.ptr(out), C.ptr(yarg), C.ptr(am), n, D, H, W, c, kd, 2, 2,
+                                         C.stream()))
+    a = torch.relu(torch.addcmul(shift, y.float(), scale)).to(torch.bfloat16)
+    ref, idx = F.max_pool3d(a.float().permute(0, 4, 1, 2, 3), (kd, 2, 2), return_indices=True)
+    assert torch.equal(out.float().permute(0, 4, 1, 2, 3), ref)
+    # yarg: y at an element whose activation equals the pooled maximum, and the code addresses it
+    code = am.to(torch.int64)
+    dz_, dy_, dx_ = code // 4, (code // 2) % 2, code % 2
+    od = torch.arange(D // kd, device="cuda").view(1, -1, 1, 1, 1) * kd + dz_
+    oh = torch.arange(H // 2, device="cuda").view(1, 1, -1, 1, 1) * 2 + dy_
+    ow = torch.arange(W // 2, device="cuda").view(1, 1, 1, -1, 1) * 2 + dx_
+    nn_ = torch.arange(n, device="cuda").view(-1, 1, 1, 1, 1).expand_as(code)
+    cc = torch.arange(c, device="cuda").view(1, 1, 1, 1, -1).expand_as(code)
+    assert torch.equal(y[nn_, od, oh, ow, cc], yarg)
+    assert torch.equal(a[nn_, od, oh, ow, cc], out)
+    # backward: guard bands only (values are covered by test_conv3d_block_tail_fused_equals_unfused)
+    dpool = torch.randn(oshape, device="cuda", generator=g).to(torch.bfloat16)
+    mean = torch.zeros(c, device="cuda"); invstd = torch.ones(c, device="cuda"); gamma = torch.ones(c, device="cuda")
+    dy = guarded((n, D, H, W, c), torch.bfloat16, -7.0)
+    dgamma = guarded((c,), torch.float32, -7.0); dbeta = guarded((c,), torch.float32, -7.0); dbias = guarded((c,), torch.float32, -7.0)
+    wsb = lib.qt_bn_workspace_bytes(c)
+    ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    C.check(lib.qt_bn_relu_maxpool3d_bwd(C.ptr(dpool), C.ptr(am), C.ptr(y), C.ptr(yarg), C.ptr(scale), C.ptr(shift), C.ptr(mean), C.ptr(invstd),
+                                         C.ptr(gamma), n, D, H, W, c, kd, 2, 2, C.ptr(dgamma), C.ptr(dbeta), C.ptr(dbias), 1, C.ptr(dy), C.ptr(ws),
+                                         wsb, C.stream()))
+    torch.cuda.synchronize()
+    # eval-mode coefficients with mean 0 / invstd 1 / gamma 1: dy = dz = dpool at the arg-max where the activation is positive
+    dz = torch.zeros(n, D, H, W, c, device="cuda")
+    dz[nn_, od, oh, ow, cc] = torch.where(out.float() > 0, dpool.float(), torch.zeros_like(dpool.float()))
+    assert torch.equal(dy.float(), dz)
+    assert torch.allclose(dbeta, dz.sum((0, 1, 2, 3)), rtol=1e-5, atol=1e-5) and torch.allclose(dbias, dbeta)
+    for buf, pad, numel, fill in guards:
+        assert bool((buf[:pad] == fill).all()) and bool((buf[pad + numel:] == fill).all()), "store outside the output tensor"
+
+
 def test_cnn_lstm_frozen_backbone_graph_replay_equals_eager(C, monkeypatch):
     """CnnLstm's frozen ResNet-18 runs from a CUDA graph (models.GraphedFrozenForward): logits, gradients of the trainable
     parameters and the train-mode BatchNorm running statistics after several steps must equal the eager launches bit for bit
