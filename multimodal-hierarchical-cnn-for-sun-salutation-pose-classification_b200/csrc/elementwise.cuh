@@ -541,6 +541,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float
 // ReLU mask: from the stored activation (act > 0) or, when act == nullptr and msc != nullptr, recomputed from
 // the raw conv output (y*msc + msh > 0 — the forward's own expression, so the mask is identical and the
 // activation tensor need not be read).
+template <int kRows>  // rows in flight per thread and iteration (up to 3 * kRows independent 16-byte loads)
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ act,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, const float* __restrict__ msc,
@@ -560,7 +561,6 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
       ms[e] = ymask ? msc[cg * 8 + e] : 0.f; mh[e] = ymask ? msh[cg * 8 + e] : 1.f;
     }
     const long long step = static_cast<long long>(gridDim.x) * lanes;
-    constexpr int kRows = 4;  // rows in flight per iteration (up to 12 independent 16-byte loads)
     for (long long r = static_cast<long long>(blockIdx.x) * lanes + rl; r < M; r += kRows * step) {
       uint4 qd[kRows], qv[kRows], qa[kRows];
       bool has[kRows];

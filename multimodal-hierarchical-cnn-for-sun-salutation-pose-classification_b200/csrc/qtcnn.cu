@@ -1086,7 +1086,8 @@ int rowlane_block(int c) {  // threads per block for the (C/8 groups) x lanes ke
   if (lanes < 1) lanes = 1;
   return groups * lanes;
 }
-constexpr int kBwdBlocks = 148 * 4;
+constexpr int kBwdBlocks = 148 * 2;  // two resident 256-thread blocks per SM: one wave (4 per SM measured 2-3 us slower per call,
+                                     // in the reduce tail and in the finalize kernel that sums the per-block rows)
 constexpr int kDirectRows = 640;  // partial-row counts a single finalize kernel reduces by itself
 }  // namespace
 
@@ -1164,7 +1165,7 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
   const int lanes = block / (c / 8);
   long long want = (m + lanes - 1) / lanes;
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
-  bn_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+  bn_bwd_reduce_kernel<4><<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
       static_cast<const __nv_bfloat16*>(y), mean, invstd, mask_scale, mask_shift, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
@@ -1390,7 +1391,7 @@ int qt_bn_relu_maxpool3d_bwd(const void* dpool, const void* argmax, const void* 
   long long want = (mp + lanes - 1) / lanes;
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
   // statistics from pooled-size tensors: every non-arg-max position has dz = 0
-  bn_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+  bn_bwd_reduce_kernel<4><<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
       static_cast<const __nv_bfloat16*>(dpool), nullptr, static_cast<const __nv_bfloat16*>(yarg), mean, invstd, scale, shift, mp, c,
       partial);
   if (int rc = cuda_status("bn_pool3d_bwd_reduce")) return rc;
