@@ -177,11 +177,12 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
 /* Stem tail fused (bn1 -> relu -> maxpool 3x3/s2/p1, torchvision resnet.py:198-200): one pass forward; backward =
  * max-pool gather + ReLU mask recomputed from y + BatchNorm backward, never materialising the full-resolution
  * activated map or its gradient. The backward works on 2x2 pixel blocks and needs even h and w (returns an error
- * otherwise; callers then use qt_maxpool2d_bwd + qt_bn_backward). */
-int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, int n, int h,
-                           int w, int c, qt_stream_t stream);
-int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const float* scale, const float* shift,
-                           const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
+ * otherwise; callers then use qt_maxpool2d_bwd + qt_bn_backward). yarg (optional, pooled shape): the raw conv output at each
+ * window's arg-max, written by the forward; with it the backward takes its statistics from the pooled-size tensors. */
+int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, void* yarg, int n,
+                           int h, int w, int c, qt_stream_t stream);
+int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const void* yarg, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
                            float* dgamma, float* dbeta, int eval_mode, void* dy, void* ws, size_t ws_bytes,
                            qt_stream_t stream);
 int qt_relu_backward(const void* dout, const void* act, void* dz, long long n, qt_stream_t stream);

@@ -811,7 +811,8 @@ __global__ void maxpool2d_bwd_kernel(const __nv_bfloat16* __restrict__ dout, con
 // ---------------------------------------------------------------------------------------------
 __global__ void bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                                           signed char* __restrict__ argmax, int N, int H, int W, int C, int Ho, int Wo) {
+                                           signed char* __restrict__ argmax, __nv_bfloat16* __restrict__ yarg, int N, int H, int W,
+                                           int C, int Ho, int Wo) {
   const int groups = C / 8;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -843,7 +844,7 @@ __global__ void bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, 
     // running max / arg-max on packed bf16 pairs: the activated value is a bf16 (same rounding as the unfused
     // path), a > best is strict so the first maximum wins, and best starts at -inf so the first valid tap always
     // takes (activations are >= 0)
-    unsigned best2[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u}, bi2[4] = {0u, 0u, 0u, 0u};
+    unsigned best2[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u}, bi2[4] = {0u, 0u, 0u, 0u}, ya2[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       if (!((okmask >> t) & 1u)) continue;
@@ -857,10 +858,13 @@ __global__ void bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ y, 
                                        *reinterpret_cast<const __nv_bfloat162*>(&best2[j]));
         best2[j] = (a2 & m) | (best2[j] & ~m);
         bi2[j] = ((t * 0x00010001u) & m) | (bi2[j] & ~m);
+        ya2[j] = (raw[j] & m) | (ya2[j] & ~m);
       }
     }
     const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + cg * 8;
     *reinterpret_cast<uint4*>(out + o) = make_uint4(best2[0], best2[1], best2[2], best2[3]);
+    // raw conv output at the arg-max: lets the backward form its BatchNorm statistics from pooled-size tensors
+    if (yarg) *reinterpret_cast<uint4*>(yarg + o) = make_uint4(ya2[0], ya2[1], ya2[2], ya2[3]);
     if (argmax) {
       uint2 pk;
       pk.x = __byte_perm(bi2[0], bi2[1], 0x6420);

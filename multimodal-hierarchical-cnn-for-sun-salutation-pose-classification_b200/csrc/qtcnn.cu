@@ -1181,18 +1181,19 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
       static_cast<__nv_bfloat16*>(dz_out), total8, c);
   return cuda_status("bn_bwd_apply");
 }
-int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, int n, int h,
-                           int w, int c, qt_stream_t stream) {
+int qt_bn_relu_maxpool_fwd(const void* y, const float* scale, const float* shift, void* out, void* argmax, void* yarg, int n,
+                           int h, int w, int c, qt_stream_t stream) {
   if (c % 8) return fail("bn_relu_maxpool: c must be a multiple of 8");
   const int ho = out_dim(h, 3, 2, 1), wo = out_dim(w, 3, 2, 1);
   const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
   bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(y), scale, shift,
                                                                           static_cast<__nv_bfloat16*>(out),
-                                                                          static_cast<signed char*>(argmax), n, h, w, c, ho, wo);
+                                                                          static_cast<signed char*>(argmax),
+                                                                          static_cast<__nv_bfloat16*>(yarg), n, h, w, c, ho, wo);
   return cuda_status("bn_relu_maxpool_fwd");
 }
-int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const float* scale, const float* shift,
-                           const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
+int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y, const void* yarg, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, const float* gamma, int n, int h, int w, int c,
                            float* dgamma, float* dbeta, int eval_mode, void* dy, void* ws, size_t ws_bytes,
                            qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_relu_maxpool_bwd: c must be a multiple of 8 and <= 2048");
@@ -1207,9 +1208,16 @@ int qt_bn_relu_maxpool_bwd(const void* dpool, const void* argmax, const void* y,
   const long long quads = static_cast<long long>(n) * ho * wo;
   long long want = (quads + lanes - 1) / lanes;
   const int blocks = static_cast<int>(want < kBwdBlocks ? (want < 1 ? 1 : want) : kBwdBlocks);
-  stem_bn_pool_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
-      shift, mean, invstd, n, h, w, c, ho, wo, partial);
+  if (yarg)
+    // dz is non-zero only at arg-max positions and the sums are linear in the windows: statistics from the pooled-size tensors
+    // (pooled gradient + conv output at each window's arg-max) instead of a pass over the full 112 x 112 map
+    bn_bwd_reduce_kernel<4><<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dpool), nullptr, static_cast<const __nv_bfloat16*>(yarg), mean, invstd, scale, shift, quads, c,
+        partial);
+  else
+    stem_bn_pool_bwd_reduce_kernel<<<blocks, block, static_cast<size_t>(lanes) * 2 * c * sizeof(float), S(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dpool), static_cast<const signed char*>(argmax), static_cast<const __nv_bfloat16*>(y), scale,
+        shift, mean, invstd, n, h, w, c, ho, wo, partial);
   if (int rc = cuda_status("stem_bn_pool_bwd_reduce")) return rc;
   bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
                                                                              invstd, gamma, dgamma, dbeta, 0, eval_mode, coef);

@@ -69,20 +69,21 @@ class _StemFn(torch.autograd.Function):
         out = torch.empty(n, po, qo, cout, device=dev, dtype=BF16)
         need_bwd = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
         am = torch.empty(n, po, qo, cout, device=dev, dtype=torch.int8) if need_bwd else None
+        yarg = torch.empty_like(out) if need_bwd else None  # conv output at each window's arg-max (backward statistics)
         # bn1 + relu + maxpool in one pass: the 112x112 activated map is never written
-        with ops.gemm_scope("stem_tail_fwd", 0.0, 2.0 * y.numel() + 3.0 * out.numel()):  # y in; pooled out + int8 arg-max
-            check(L().qt_bn_relu_maxpool_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(am), n, ho, wo, cout, stream()),
+        with ops.gemm_scope("stem_tail_fwd", 0.0, 2.0 * y.numel() + (5.0 if need_bwd else 2.0) * out.numel()):  # y in; pooled out (+ yarg, int8 arg-max)
+            check(L().qt_bn_relu_maxpool_fwd(ptr(y), ptr(st.scale), ptr(st.shift), ptr(out), ptr(am), ptr(yarg), n, ho, wo, cout, stream()),
                   "bn_relu_maxpool_fwd")
         ops._count()
         if need_bwd:
-            ctx.saved = (xp, y, am, st, conv_w, bn_w, bn_b)
+            ctx.saved = (xp, y, am, yarg, st, conv_w, bn_w, bn_b)
             ctx.dims = (n, h, w, cout, ho, wo)
             ctx.training = training
         return ops.as_nchw_view(out)
 
     @staticmethod
     def backward(ctx, dout):
-        xp, y, am, st, conv_w, bn_w, bn_b = ctx.saved
+        xp, y, am, yarg, st, conv_w, bn_w, bn_b = ctx.saved
         n, h, w, cout, ho, wo = ctx.dims
         dev = y.device
         dout = ops.as_nhwc(dout)
@@ -94,9 +95,9 @@ class _StemFn(torch.autograd.Function):
             # passes over 2x2 pixel blocks; neither the activated 112x112 map nor its gradient is ever materialised
             wsb = L().qt_bn_workspace_bytes(cout)
             ws = ops.workspace(wsb, dev)
-            # two passes over (y, pooled gradient, arg-max plane) + one write of dy
-            with ops.gemm_scope("stem_tail_bwd", 0.0, 2.0 * (2.0 * y.numel() + 3.0 * dout.numel()) + 2.0 * dy.numel()):
-                check(L().qt_bn_relu_maxpool_bwd(ptr(dout), ptr(am), ptr(y), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
+            # statistics from the pooled gradient + yarg; then one pass over (y, pooled gradient, arg-max plane) + one write of dy
+            with ops.gemm_scope("stem_tail_bwd", 0.0, 4.0 * dout.numel() + (2.0 * y.numel() + 3.0 * dout.numel()) + 2.0 * dy.numel()):
+                check(L().qt_bn_relu_maxpool_bwd(ptr(dout), ptr(am), ptr(y), ptr(yarg), ptr(st.scale), ptr(st.shift), ptr(st.mean), ptr(st.invstd),
                                                  ptr(bn_w.detach()), n, ho, wo, cout, ptr(dgamma), ptr(dbeta), 0 if ctx.training else 1,
                                                  ptr(dy), ptr(ws), wsb, stream()), "bn_relu_maxpool_bwd")
             ops._count(3)

@@ -515,8 +515,10 @@ def test_wpack_both(C, cout, cin, taps):
     assert torch.equal(wd, bf16(w).permute(1, 2, 0).contiguous())
 
 
-def test_fused_stem_tail(C):
-    """bn1 + relu + maxpool(3,2,1) fused forward / backward vs torch autograd on the same bf16 conv output."""
+@pytest.mark.parametrize("with_yarg", [True, False])
+def test_fused_stem_tail(C, with_yarg):
+    """bn1 + relu + maxpool(3,2,1) fused forward / backward vs torch autograd on the same bf16 conv output; with `yarg` the
+    backward statistics come from the pooled-size tensors (the path the models use), without it from a pass over y."""
     n, h, w, c = 3, 22, 26, 64
     g = torch.Generator(device="cuda").manual_seed(21)
     y = bf16(torch.randn(n, c, h, w, device="cuda", generator=g) * 1.5 + 0.3)
@@ -544,12 +546,13 @@ def test_fused_stem_tail(C):
     ho, wo = pooled.shape[2], pooled.shape[3]
     out = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.bfloat16)
     am = torch.empty(n, ho, wo, c, device="cuda", dtype=torch.int8)
-    run(C, C.lib().qt_bn_relu_maxpool_fwd(C.ptr(y_nhwc), C.ptr(scale), C.ptr(shift), C.ptr(out), C.ptr(am), n, h, w, c, C.stream()),
-        "bn_relu_maxpool_fwd")
+    yarg = torch.empty_like(out) if with_yarg else None
+    run(C, C.lib().qt_bn_relu_maxpool_fwd(C.ptr(y_nhwc), C.ptr(scale), C.ptr(shift), C.ptr(out), C.ptr(am), C.ptr(yarg), n, h, w, c,
+                                          C.stream()), "bn_relu_maxpool_fwd")
     report("fused stem tail fwd", out.permute(0, 3, 1, 2), pooled.detach(), BF16_REL_L2, True)
     dy = torch.empty_like(y_nhwc)
     dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
-    run(C, C.lib().qt_bn_relu_maxpool_bwd(C.ptr(dpool.permute(0, 2, 3, 1).contiguous()), C.ptr(am), C.ptr(y_nhwc), C.ptr(scale),
+    run(C, C.lib().qt_bn_relu_maxpool_bwd(C.ptr(dpool.permute(0, 2, 3, 1).contiguous()), C.ptr(am), C.ptr(y_nhwc), C.ptr(yarg), C.ptr(scale),
                                           C.ptr(shift), C.ptr(mean), C.ptr(invstd), C.ptr(gamma), n, h, w, c, C.ptr(dgamma),
                                           C.ptr(dbeta), 0, C.ptr(dy), C.ptr(ws), ws_bytes, C.stream()), "bn_relu_maxpool_bwd")
     report("fused stem tail dgamma", dgamma, gref.grad, 2e-2)
