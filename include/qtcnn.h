@@ -58,8 +58,10 @@ void qt_set_conv3x3_enabled(int on);
 /* Developer knobs (value 0 = default everywhere). key 0 / 1: pipeline shape of the generic weight-gradient / K-major
  * kernels; 2: generic gather for the stem; 3: generic weight-gradient kernel for 3x3 convs; 4: 7x7 maps through the
  * generic kernels; 5: staged (coalesced) conv3x3 write-out 1 = never, 2 = always (default: maps at least 20 wide);
- * 6: weight tiles by cp.async instead of TMA; 7: Conv3d through the generic gather kernels; 8: linear weight gradients always through the split-K workspace. Also settable through the QTCNN_TUNE="k=v,..." environment variable
- * of the Python binding. */
+ * 6: weight tiles by cp.async instead of TMA; 7: Conv3d through the generic gather kernels; 8: linear weight gradients always
+ * through the split-K workspace; 9: ablation of the first-layer Conv3d weight-gradient kernel (1 = MMAs skipped, 2 = slab
+ * copies skipped: results are then meaningless, profiles/r02_conv3d.md). Also settable through the QTCNN_TUNE="k=v,..."
+ * environment variable of the Python binding. */
 void qt_set_tuning(int key, int value);
 
 /* ---- layout / packing ------------------------------------------------------------------------- */
