@@ -1158,7 +1158,6 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
                    qt_stream_t stream) {
   if (c % 8 || c > 2048) return fail("bn_backward: c must be a multiple of 8 and <= 2048");
   if (ws_bytes < qt_bn_workspace_bytes(c)) return fail("bn_backward: workspace too small");
-  double* sums = static_cast<double*>(ws);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + static_cast<size_t>(kRedSlices) * 2 * c * sizeof(double));
   float* coef = partial + static_cast<size_t>(kBwdBlocks) * 2 * c;  // [A | B | K]
   const int block = rowlane_block(c);
@@ -1169,7 +1168,6 @@ int qt_bn_backward(const void* dout, const void* act, const void* y, const float
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(act),
       static_cast<const __nv_bfloat16*>(y), mean, invstd, mask_scale, mask_shift, m, c, partial);
   if (int rc = cuda_status("bn_bwd_reduce")) return rc;
-  (void)sums;
   bn_bwd_finalize_rows_kernel<<<(c + 31) / 32, dim3(32, 32), 0, S(stream)>>>(partial, blocks, c, static_cast<double>(m), mean,
                                                                             invstd, gamma, dgamma, dbeta, accumulate, eval_mode,
                                                                             coef);
