@@ -968,7 +968,8 @@ class GraphedFrozenForward:
         torch.cuda.current_stream(x.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = ops.launches()
-        with torch.cuda.graph(graph), torch.no_grad():
+        # thread_local: a DataLoader pin-memory thread may call the CUDA allocator while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"), torch.no_grad():
             static_out = self.module(static_in)
         launches = ops.launches() - n0
         ops._count(-launches)  # recorded, not executed
