@@ -522,6 +522,36 @@ def test_bn_relu_maxpool3d_c_abi_small_shapes_with_guard_bands(C, kd, n, D, H, W
         assert bool((buf[:pad] == fill).all()) and bool((buf[pad + numel:] == fill).all()), "store outside the output tensor"
 
 
+def test_frozen_weight_packs_survive_optimizer_steps(C):
+    """bf16 operand copies of a frozen parameter are kept across optimizer steps (they used to be re-packed every step: 19 extra
+    launches per step on the frozen backbones), follow in-place torch edits through `_version`, and are dropped by
+    ops.invalidate_packed_weights(); a trainable parameter's copies are refreshed after every step."""
+    from qtcnn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    frozen = torch.nn.Parameter(torch.randn(64, 64, 3, 3, device="cuda", generator=g), requires_grad=False)
+    train = torch.nn.Parameter(torch.randn(64, 64, 3, 3, device="cuda", generator=g))
+    with torch.no_grad():
+        wf_f, wf_t = ops.packed_fprop(frozen), ops.packed_fprop(train)
+    ref = frozen.detach().reshape(64, 64, 9).permute(0, 2, 1).to(torch.bfloat16)
+    assert torch.equal(wf_f, ref)
+    n0 = ops.launches()
+    ops._on_optimizer_step()                      # what every torch / qtcnn optimizer step triggers
+    with torch.no_grad():
+        assert ops.packed_fprop(frozen) is wf_f   # same buffer, no launch
+        assert ops.launches() == n0
+        train.data.mul_(2.0)                      # raw update (no _version bump), like a fused optimizer
+        wf_t2 = ops.packed_fprop(train)
+        assert ops.launches() > n0
+        assert torch.equal(wf_t2, train.detach().reshape(64, 64, 9).permute(0, 2, 1).to(torch.bfloat16))
+        frozen.mul_(0.5)                          # in-place torch edit bumps _version
+        wf_f2 = ops.packed_fprop(frozen)
+        assert torch.equal(wf_f2, frozen.detach().reshape(64, 64, 9).permute(0, 2, 1).to(torch.bfloat16))
+        frozen.data.add_(1.0)                     # raw edit: invisible until the explicit invalidation
+        ops.invalidate_packed_weights()
+        wf_f3 = ops.packed_fprop(frozen)
+        assert torch.equal(wf_f3, frozen.detach().reshape(64, 64, 9).permute(0, 2, 1).to(torch.bfloat16))
+
+
 def test_cnn_lstm_frozen_backbone_graph_replay_equals_eager(C, monkeypatch):
     """CnnLstm's frozen ResNet-18 runs from a CUDA graph (models.GraphedFrozenForward): logits, gradients of the trainable
     parameters and the train-mode BatchNorm running statistics after several steps must equal the eager launches bit for bit
