@@ -585,14 +585,14 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, con
           const bool off = act ? !(a[e] > 0.f) : !(fmaf(v[e], ms[e], mh[e]) > 0.f);
           const float dz = off ? 0.f : d[e];
           s1[e] += dz;
-          s2[e] += dz * (v[e] - mu[e]) * is[e];
+          s2[e] = fmaf(dz, v[e] - mu[e], s2[e]);  // invstd is applied once per thread below, not per element
         }
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       sm[(rl * 2 + 0) * C + cg * 8 + e] = s1[e];
-      sm[(rl * 2 + 1) * C + cg * 8 + e] = s2[e];
+      sm[(rl * 2 + 1) * C + cg * 8 + e] = s2[e] * is[e];
     }
   }
   __syncthreads();
